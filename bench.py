@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""bench.py — probe states relaxed / second at N=4096 (BASELINE.json metric), one rank per GPU.
+
+A step = one pass of the hot path (initial fields GEMM -> relaxation kernel -> unique-attractor
+table) over one batch of synthetic probes.  Workload at every N: BASELINE config 3 per GPU
+(N=4096, Hebbian, 400 targets, 2^17 probes per GPU, shared 100-row schedule, dedup on) — weak scaling.
+
+  value : probes/s with the probes, schedule and W already resident in HBM (CUDA-event time)
+  e2e   : probes/s through hn_relax_batch with HOST buffers (H2D of probes+schedule, D2H of results
+          inside the timed region)
+  --impl reference : the CPU restatement of the reference (oracle/, all host cores) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "probe_states_relaxed_per_sec_N4096"
+UNIT = "probes/s"
+
+
+def synth(n, p, b, seed):
+    """i.i.d. fair +-1 states (what states/StateGenerator.go:44-52 yields), packed."""
+    rs = np.random.Generator(np.random.PCG64(seed))
+    w = (n + 63) // 64
+    def bits(count):
+        a = rs.integers(0, 2**63, size=(count, w), dtype=np.int64).astype(np.uint64) << np.uint64(1)
+        a |= rs.integers(0, 2, size=(count, w), dtype=np.int64).astype(np.uint64)
+        if n % 64:
+            a[:, -1] &= np.uint64((1 << (n % 64)) - 1)
+        return a
+    targets = bits(p)
+    probes = bits(b)
+    pool = np.empty((100, n), dtype=np.uint16)
+    lst = np.arange(n, dtype=np.uint16)
+    for r in range(100):          # one persistent list shuffled once per sweep (HopfieldNetwork.go:374,393)
+        rs.shuffle(lst)
+        pool[r] = lst
+    return targets, probes, pool
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0])); self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, cfg):
+    """CPU restatement of the reference (oracle, port) with every host core, bounded sample."""
+    from oracle import orc
+    n, p = cfg["N"], cfg["P"]
+    cores = os.cpu_count() or 1
+    targets, probes, pool = synth(n, p, max(4 * cores, 64), 0x5EED + 3)
+    t_f64 = orc.unpack(targets, n)
+    net = orc.Net(n)
+    net.hebbian(t_f64)
+    net.normalize()
+    net.set_targets(t_f64)
+    sample = cores  # one probe per core per step: O(1 s)/probe/core at N=4096
+    times = []
+    for it in range(args.warmup + args.steps):
+        pr = orc.unpack(probes[(it * sample) % probes.shape[0]:][:sample], n)
+        if pr.shape[0] < sample:
+            pr = orc.unpack(probes[:sample], n)
+        t0 = time.perf_counter()
+        net.relax_batch(pr, pool, threads=cores, want_energies=True, faithful_cost=True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    v = sample * len(times) / tot
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], **{k: cfg[k] for k in ("N", "P")}, "probes_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} probes per step x {len(times)} steps of the same workload, oracle "
+                                       "C restatement of the reference algorithm as written (N dots/sweep + 2-3 gemv)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--probes", type=int, default=1 << 17, help="probes per GPU per step")
+    ap.add_argument("--dim", type=int, default=4096)
+    ap.add_argument("--targets", type=int, default=400)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"name": f"config3: N={args.dim} Hebbian P={args.targets}, {args.probes} probes/GPU, shared 100-row schedule, dedup",
+           "N": args.dim, "P": args.targets, "B": args.probes}
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from hopfield_network_go_b200 import hopfieldnetwork as hn
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    n, p, b = cfg["N"], cfg["P"], cfg["B"]
+    _, probes, _ = synth(n, p, b, 0x5EED + 3 + 1000 * (rank + 1))
+    targets, _, pool = synth(n, p, 1, 0x5EED + 3)  # same W / schedule on every rank
+    net = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
+        hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).Build()
+    net.LearnStates(targets)
+    # pinned host staging for the e2e leg
+    probes_pinned = torch.from_numpy(probes).pin_memory()
+    probes_np = probes_pinned.numpy()
+    net.upload_perm_pool(pool)
+    net.upload_probes(probes_np)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        net.relax_resident(dedup=True)
+    barrier()
+    sampler.start()
+    dev_ms, relax_ms, launches = [], [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_ms.append(net.relax_resident(dedup=True))
+        t = net.last_timing()
+        relax_ms.append(t.relax_ms)
+        launches += t.launches
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    # counters for the roofline (same every step: deterministic)
+    import ctypes as C
+    from hopfield_network_go_b200 import capi
+    out = capi.HnRelaxOut()
+    capi.check(capi.load().hn_download_results(net._h, C.byref(out)))
+    flips, sweeps = out.total_flips, out.total_sweeps
+    alg_bytes = 8 * n * flips + 8 * n * sweeps + b * (n // 4 + 4 * p + 16)
+    step_ms = float(np.sum(dev_ms))
+    # e2e: host buffers through hn_relax_batch
+    e2e_t = []
+    for it in range(1 + min(args.steps, 2)):
+        barrier()
+        t1 = time.perf_counter()
+        res = net.relax_batch(probes_np, pool, dedup=True)
+        barrier()
+        if it > 0:
+            e2e_t.append(time.perf_counter() - t1)
+    h2d = probes_np.nbytes + pool.nbytes
+    d2h = res.FinalStates.nbytes + res.NumSteps.nbytes + res.Stable.nbytes + res.DistancesToTargets.nbytes + \
+        res.Flips.nbytes + res.MarginHits.nbytes + res.AttractorId.nbytes + 2 * 4 * len(res.UniqueFirst)
+    tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    step_ms_max, relax_ms_max, e2e_max = [float(x) for x in tmax.cpu()]
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        achieved = alg_bytes * args.steps / (relax_ms_max * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": world * b * args.steps / (step_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": cfg["name"], "N": n, "P": p, "probes_per_gpu": b,
+                           "l2": "inputs larger than L2 (W 128 MiB + 4 GiB of initial fields streamed per step)"},
+                "e2e": {"value": world * b / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                             "traffic": None, "kernel": "relax_kernel<16>",
+                             "peak_source": "measured" if peaks else "fallback",
+                             "algorithmic_bytes_per_launch": int(alg_bytes), "flips_per_probe": flips / b,
+                             "sweeps_per_probe": sweeps / b},
+                "clocks": sampler.summary(), "wall_s": wall,
+                "margin_hits_per_probe": out.total_margin_hits / b, "unique_attractors": int(out.n_unique)}
+        if not args.no_cpu:
+            from oracle import orc
+            cores = os.cpu_count() or 1
+            t_f64 = orc.unpack(targets, n)
+            onet = orc.Net(n)
+            onet.hebbian(t_f64)
+            onet.normalize()
+            onet.set_targets(t_f64)
+            sample = 2 * cores
+            pr = orc.unpack(probes[:sample], n)
+            t2 = time.perf_counter()
+            onet.relax_batch(pr, pool, threads=cores, want_energies=True, faithful_cost=True)
+            dt = time.perf_counter() - t2
+            line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} probes of the same batch, oracle C restatement of the "
+                                              "reference algorithm as written, one probe per worker thread"}
+        print(json.dumps(line))
+    net.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1002 @@
+// api.cu — C ABI of libhopfield_b200.so (include/hopfield_b200.h).
+// One handle = one network replica resident on one B200: W (float64, row-major,
+// zero padded to a multiple of 16 columns) in HBM/L2, packed states, one stream.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_f64.cuh"
+#include "kernels_misc.cuh"
+#include "relax.cuh"
+
+namespace hn {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- NCCL through dlopen (no link-time dependency; loaded on first use) ----
+struct Id128 { char bytes[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.lib) return HN_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { set_error("NCCL not loadable: %s", dlerror()); return HN_E_NCCL; }
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclBroadcast");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.Broadcast) {
+        set_error("NCCL symbols missing");
+        return HN_E_NCCL;
+    }
+    return HN_OK;
+}
+constexpr int NCCL_FLOAT64 = 8, NCCL_INT32 = 2, NCCL_SUM = 0, NCCL_MIN = 4;
+#define HN_NCCL_TRY(expr)                                                                   \
+    do {                                                                                    \
+        int _r = (expr);                                                                    \
+        if (_r != 0) {                                                                      \
+            set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+            return HN_E_NCCL;                                                               \
+        }                                                                                   \
+    } while (0)
+
+}  // namespace hn
+
+using namespace hn;
+
+struct hn_handle_s {
+    hn_config cfg;
+    int N = 0, ldw = 0, words = 0, ldp = 0, sms = 0;
+    cudaStream_t st = nullptr;
+    double* W = nullptr;
+    double* WT = nullptr;
+    double* dW = nullptr;
+    bool w_symmetric = true;   // W known symmetric -> column k == row k
+    bool margin_valid = false;
+    double tau_base = 0, tau_flip = 0;
+    int P = 0;
+    DevBuf targets;
+    // relaxation working set
+    DevBuf probes, pool, offsets, H, finals, steps, stable, flips, margin, dist, hash, energies, history;
+    DevBuf rep, first, hits, flag, rank, table, attractor, ufirst, uhits, small, partial;
+    DevBuf bitsA, bitsB, bitsC, bitsAT, bitsCT, perms, eunst, estab, esum, emargin;
+    uint16_t* d_pool = nullptr;
+    uint16_t* d_inv = nullptr;
+    int resident_B = 0, resident_pool = 0, result_B = 0, result_P = 0, result_unique = 0;
+    uint32_t result_flags = 0;
+    cudaEvent_t ev[6] = {};
+    hn_relax_timing timing = {};
+    int64_t tot_flips = 0, tot_sweeps = 0, tot_margin = 0;
+    void* comm = nullptr;
+    int rank_id = 0, n_ranks = 1;
+};
+
+namespace {
+
+int set_device(hn_handle h) {
+    HN_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    return HN_OK;
+}
+
+struct ValueMap { double lo, hi; };
+ValueMap domain_values(int domain) { return domain == HN_DOMAIN_BINARY ? ValueMap{0.0, 1.0} : ValueMap{-1.0, 1.0}; }
+
+int grid_for(int64_t total, int threads, int sms) {
+    int64_t g = (total + threads - 1) / threads;
+    int64_t cap = (int64_t)sms * 8;
+    return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+int refresh_wt(hn_handle h) {
+    if (h->w_symmetric) return HN_OK;
+    if (!h->WT) HN_CUDA_TRY(cudaMalloc(&h->WT, sizeof(double) * (size_t)h->N * h->ldw));
+    HN_CUDA_TRY(cudaMemsetAsync(h->WT, 0, sizeof(double) * (size_t)h->N * h->ldw, h->st));
+    dim3 g((h->N + SYM_T - 1) / SYM_T, (h->N + SYM_T - 1) / SYM_T), b(SYM_T, 8);
+    transpose_kernel<<<g, b, 0, h->st>>>(h->W, h->WT, h->N, h->ldw);
+    HN_CUDA_TRY(cudaGetLastError());
+    return HN_OK;
+}
+
+int ensure_margin(hn_handle h) {
+    if (h->margin_valid) return HN_OK;
+    HN_TRY(h->small.reserve(256));
+    unsigned long long* d = h->small.as<unsigned long long>();
+    HN_CUDA_TRY(cudaMemsetAsync(d, 0, 8, h->st));
+    rowabs_max_kernel<<<h->N, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, d);
+    HN_CUDA_TRY(cudaGetLastError());
+    double r = 0;
+    HN_CUDA_TRY(cudaMemcpyAsync(&r, d, 8, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    const double u = 1.1102230246251565e-16;  // 2^-53
+    // |incremental field - fresh DotUnitary field| <= (N [GEMM] + N/4+3 [fresh] + flips) * u * R; x2 safety
+    h->tau_base = 2.0 * (1.25 * h->N + 4.0) * u * r;
+    h->tau_flip = 2.0 * u * r;
+    h->margin_valid = true;
+    return HN_OK;
+}
+
+void weights_changed(hn_handle h) { h->margin_valid = false; }
+
+// exact symmetry test of the resident W (decides whether column k can be read as row k)
+int detect_symmetry(hn_handle h) {
+    HN_TRY(h->small.reserve(256));
+    int32_t* flag = h->small.as<int32_t>() + 8;
+    HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
+    dim3 g((h->N + SYM_T - 1) / SYM_T, (h->N + SYM_T - 1) / SYM_T), b(SYM_T, 8);
+    asymmetry_kernel<<<g, b, 0, h->st>>>(h->W, h->N, h->ldw, flag);
+    HN_CUDA_TRY(cudaGetLastError());
+    int32_t f = 0;
+    HN_CUDA_TRY(cudaMemcpyAsync(&f, flag, 4, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->w_symmetric = (f == 0);
+    return HN_OK;
+}
+
+// H[count][ldw] = S * W^T
+int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H, ValueMap vm) {
+    OpBits a{d_states, h->words, count, h->N, vm.lo, vm.hi};
+    OpF64 b{h->W, h->ldw, h->N};
+    EpiStore e{d_H, h->ldw, count, h->N};
+    return launch_gemm_f64(a, b, e, count, h->N, h->N, h->st);
+}
+
+template <int UPT>
+int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
+    auto kern = relax_kernel<UPT>;
+    const int nbw = (h->N + 31) / 32;
+    const size_t smem = (size_t)((nbw + 3) / 4 * 4) * 4 + (size_t)h->ldp * 2;
+    HN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    HN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RELAX_THREADS, smem));
+    if (occ < 1) occ = 1;
+    int grid = p.serial_stream ? 1 : std::min(p.B, h->sms * occ);
+    if (grid_cap > 0) grid = std::min(grid, grid_cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, RELAX_THREADS, smem, h->st>>>(p);
+    HN_CUDA_TRY(cudaGetLastError());
+    return HN_OK;
+}
+int launch_relax(hn_handle h, const RelaxParams& p) {
+    const int n = h->N;
+    if (n <= 256) return launch_relax_t<1>(h, p, 0);
+    if (n <= 512) return launch_relax_t<2>(h, p, 0);
+    if (n <= 1024) return launch_relax_t<4>(h, p, 0);
+    if (n <= 2048) return launch_relax_t<8>(h, p, 0);
+    if (n <= 4096) return launch_relax_t<16>(h, p, 0);
+    if (n <= 8192) return launch_relax_t<32>(h, p, 0);
+    if (n <= 16384) return launch_relax_t<64>(h, p, 0);
+    set_error("relaxation kernel supports dimension <= 16384 (got %d)", n);
+    return HN_E_INVALID;
+}
+
+// upload permutations [rows][N] (host, dense) into one device buffer:
+// first half = padded rows, second half = their inverses (position of each unit)
+int upload_pool(hn_handle h, const uint16_t* pool, int rows, DevBuf& buf, uint16_t** d_perm, uint16_t** d_inv) {
+    const size_t bytes = sizeof(uint16_t) * (size_t)rows * h->ldp;
+    HN_TRY(buf.reserve(2 * bytes));
+    *d_perm = buf.as<uint16_t>();
+    *d_inv = buf.as<uint16_t>() + (size_t)rows * h->ldp;
+    HN_CUDA_TRY(cudaMemsetAsync(buf.p, 0, 2 * bytes, h->st));
+    HN_CUDA_TRY(cudaMemcpy2DAsync(*d_perm, sizeof(uint16_t) * h->ldp, pool, sizeof(uint16_t) * h->N,
+                                  sizeof(uint16_t) * h->N, rows, cudaMemcpyHostToDevice, h->st));
+    dim3 g(rows, std::max(1, std::min(64, (h->N + 255) / 256)));
+    invert_perm_kernel<<<g, 256, 0, h->st>>>(*d_perm, *d_inv, h->N, h->ldp, rows);
+    HN_CUDA_TRY(cudaGetLastError());
+    return HN_OK;
+}
+
+int validate_pool_host(hn_handle h, const uint16_t* pool, int rows) {
+    // every row must be a permutation of 0..N-1 (a bad row would corrupt device memory)
+    std::vector<uint8_t> seen((size_t)h->N);
+    for (int r = 0; r < rows; r++) {
+        std::fill(seen.begin(), seen.end(), 0);
+        const uint16_t* row = pool + (size_t)r * h->N;
+        for (int i = 0; i < h->N; i++) {
+            if (row[i] >= h->N || seen[row[i]]) { set_error("perm_pool row %d is not a permutation of 0..%d", r, h->N - 1); return HN_E_INVALID; }
+            seen[row[i]] = 1;
+        }
+    }
+    return HN_OK;
+}
+
+// The whole relaxation of B probes already on the device.
+int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d_pool, const uint16_t* d_inv,
+                 int n_pool, const int32_t* d_offsets, uint32_t flags, bool want_energies, bool want_dist) {
+    const int N = h->N, words = h->words;
+    HN_TRY(ensure_margin(h));
+    HN_TRY(refresh_wt(h));
+    const bool dedup = flags & HN_RELAX_DEDUP, hist = flags & HN_RELAX_HISTORY, serial = flags & HN_RELAX_SERIAL_STREAM;
+    HN_TRY(h->H.reserve(sizeof(double) * (size_t)B * h->ldw));
+    HN_TRY(h->finals.reserve(sizeof(uint64_t) * (size_t)B * words));
+    HN_TRY(h->steps.reserve(sizeof(int32_t) * (size_t)B));
+    HN_TRY(h->stable.reserve((size_t)B));
+    HN_TRY(h->flips.reserve(sizeof(int32_t) * (size_t)B));
+    HN_TRY(h->margin.reserve(sizeof(int32_t) * (size_t)B));
+    HN_TRY(h->small.reserve(256));
+    if (want_dist && h->P > 0) HN_TRY(h->dist.reserve(sizeof(int32_t) * (size_t)B * h->P));
+    if (dedup) HN_TRY(h->hash.reserve(sizeof(uint64_t) * 2 * (size_t)B));
+    if (hist) HN_TRY(h->history.reserve(sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
+
+    int launches = 0;
+    int32_t* d_small = h->small.as<int32_t>();  // [0] work counter, [1..2] status, [4] unique total
+    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 64, h->st));
+    if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
+
+    HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
+    HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain)));
+    launches++;
+    HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
+
+    RelaxParams p{};
+    p.N = N; p.ldw = h->ldw; p.words = words;
+    p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;
+    p.H0 = h->H.as<double>(); p.ldh = h->ldw;
+    p.probes = d_probes; p.perm_pool = d_pool; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n_pool;
+    p.offsets = serial ? nullptr : d_offsets;
+    p.B = B; p.max_iter = h->cfg.max_relax_iterations; p.max_unstable = h->cfg.max_relax_unstable_units;
+    p.domain = h->cfg.domain; p.check_stability = 1; p.serial_stream = serial ? 1 : 0;
+    p.tau_base = h->tau_base; p.tau_flip = h->tau_flip;
+    p.final_states = h->finals.as<uint64_t>(); p.num_steps = h->steps.as<int32_t>();
+    p.stable = h->stable.as<uint8_t>(); p.flips = h->flips.as<int32_t>(); p.margin_hits = h->margin.as<int32_t>();
+    p.distances = (want_dist && h->P > 0) ? h->dist.as<int32_t>() : nullptr;
+    p.targets = h->targets.as<uint64_t>(); p.P = h->P;
+    p.hash = dedup ? h->hash.as<uint64_t>() : nullptr;
+    p.history = hist ? h->history.as<uint64_t>() : nullptr;
+    p.work_counter = d_small; p.status = d_small + 1;
+    HN_TRY(launch_relax(h, p));
+    launches++;
+    HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
+
+    if (want_energies) {
+        // EnergyProfile of the final states (main.go:234): fresh fields by GEMM + epilogue
+        HN_TRY(h->energies.reserve(sizeof(double) * (size_t)B * N));
+        HN_TRY(launch_fields(h, h->finals.as<uint64_t>(), B, h->H.as<double>(), domain_values(h->cfg.domain)));
+        energy_epilogue_kernel<<<B, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, h->finals.as<uint64_t>(), words,
+                                                            h->W, h->ldw, N, h->cfg.domain, h->tau_base,
+                                                            h->cfg.max_relax_unstable_units, h->energies.as<double>(),
+                                                            nullptr, nullptr, nullptr, nullptr);
+        HN_CUDA_TRY(cudaGetLastError());
+        launches += 2;
+    }
+    h->result_unique = 0;
+    if (dedup) {
+        int cap = 1024;
+        while (cap < 2 * B) cap <<= 1;
+        HN_TRY(h->table.reserve(sizeof(int32_t) * (size_t)cap));
+        HN_TRY(h->rep.reserve(sizeof(int32_t) * (size_t)B));
+        HN_TRY(h->first.reserve(sizeof(int32_t) * (size_t)B));
+        HN_TRY(h->hits.reserve(sizeof(int32_t) * (size_t)B));
+        HN_TRY(h->flag.reserve(sizeof(int32_t) * (size_t)B));
+        HN_TRY(h->rank.reserve(sizeof(int32_t) * (size_t)B));
+        HN_TRY(h->attractor.reserve(sizeof(int32_t) * (size_t)B));
+        HN_TRY(h->ufirst.reserve(sizeof(int32_t) * (size_t)B));
+        HN_TRY(h->uhits.reserve(sizeof(int32_t) * (size_t)B));
+        HN_CUDA_TRY(cudaMemsetAsync(h->table.p, 0xFF, sizeof(int32_t) * (size_t)cap, h->st));
+        HN_CUDA_TRY(cudaMemsetAsync(h->first.p, 0x7F, sizeof(int32_t) * (size_t)B, h->st));
+        HN_CUDA_TRY(cudaMemsetAsync(h->hits.p, 0, sizeof(int32_t) * (size_t)B, h->st));
+        const int tb = 256, gb = (B + tb - 1) / tb;
+        dedup_insert_kernel<<<gb, tb, 0, h->st>>>(h->finals.as<uint64_t>(), h->hash.as<uint64_t>(), B, words, N,
+                                                 h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>());
+        dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), B, h->first.as<int32_t>(), h->hits.as<int32_t>());
+        dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), B, h->flag.as<int32_t>());
+        scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), d_small + 4);
+        dedup_finalize_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), h->hits.as<int32_t>(),
+                                                   h->rank.as<int32_t>(), B, h->attractor.as<int32_t>(),
+                                                   h->ufirst.as<int32_t>(), h->uhits.as<int32_t>());
+        HN_CUDA_TRY(cudaGetLastError());
+        launches += 5;
+    }
+    HN_CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
+    int32_t small_host[8];
+    HN_CUDA_TRY(cudaMemcpyAsync(small_host, d_small, sizeof(small_host), cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (small_host[1]) {
+        set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, small_host[2]);
+        return HN_E_POOL;
+    }
+    h->result_unique = dedup ? small_host[4] : 0;
+    float f = 0, r = 0, q = 0;
+    cudaEventElapsedTime(&f, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&r, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&q, h->ev[2], h->ev[3]);
+    h->timing.fields_ms = f; h->timing.relax_ms = r; h->timing.post_ms = q; h->timing.launches = launches;
+    h->result_B = B; h->result_P = want_dist ? h->P : 0; h->result_flags = flags | (want_energies ? 0x100u : 0u);
+    return HN_OK;
+}
+
+int download_results(hn_handle h, hn_relax_out* out) {
+    const int B = h->result_B, N = h->N, words = h->words;
+    if (B <= 0) { set_error("no relaxation results on the device"); return HN_E_STATE; }
+    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (dst && bytes) HN_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st));
+        return HN_OK;
+    };
+    HN_TRY(d2h(out->final_states, h->finals.p, sizeof(uint64_t) * (size_t)B * words));
+    HN_TRY(d2h(out->num_steps, h->steps.p, sizeof(int32_t) * (size_t)B));
+    HN_TRY(d2h(out->stable, h->stable.p, (size_t)B));
+    HN_TRY(d2h(out->flips, h->flips.p, sizeof(int32_t) * (size_t)B));
+    HN_TRY(d2h(out->margin_hits, h->margin.p, sizeof(int32_t) * (size_t)B));
+    if (out->distances) {
+        if (h->result_P != h->P) { set_error("distances were not computed"); return HN_E_STATE; }
+        HN_TRY(d2h(out->distances, h->dist.p, sizeof(int32_t) * (size_t)B * h->P));
+    }
+    if (out->energies) {
+        if (!(h->result_flags & 0x100u)) { set_error("energies were not computed"); return HN_E_STATE; }
+        HN_TRY(d2h(out->energies, h->energies.p, sizeof(double) * (size_t)B * N));
+    }
+    out->n_unique = 0;
+    if (h->result_flags & HN_RELAX_DEDUP) {
+        out->n_unique = h->result_unique;
+        HN_TRY(d2h(out->attractor_id, h->attractor.p, sizeof(int32_t) * (size_t)B));
+        const int nu = std::min(h->result_unique, out->unique_cap);
+        if (nu > 0) {
+            HN_TRY(d2h(out->unique_first, h->ufirst.p, sizeof(int32_t) * (size_t)nu));
+            HN_TRY(d2h(out->unique_hits, h->uhits.p, sizeof(int32_t) * (size_t)nu));
+        }
+    }
+    if (out->history) {
+        if (!(h->result_flags & HN_RELAX_HISTORY)) { set_error("history was not captured"); return HN_E_STATE; }
+        HN_TRY(d2h(out->history, h->history.p, sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
+    }
+    // totals (small device->host reductions done on the host copies of the counters)
+    std::vector<int32_t> fl((size_t)B), stp((size_t)B), mg((size_t)B);
+    HN_CUDA_TRY(cudaMemcpyAsync(fl.data(), h->flips.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync(stp.data(), h->steps.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync(mg.data(), h->margin.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    int64_t tf = 0, ts = 0, tm = 0;
+    for (int i = 0; i < B; i++) { tf += fl[i]; ts += stp[i] - 1; tm += mg[i]; }
+    out->total_flips = tf; out->total_sweeps = ts; out->total_margin_hits = tm;
+    out->device_ms = h->timing.fields_ms + h->timing.relax_ms + h->timing.post_ms;
+    return HN_OK;
+}
+
+// dW = A^T-style contraction over the n states, written to h->dW
+int contraction_hebbian(hn_handle h, const uint64_t* d_states, int n, ValueMap vm) {
+    const int pwords = (n + 63) / 64;
+    HN_TRY(h->bitsAT.reserve(sizeof(uint64_t) * (size_t)h->N * pwords));
+    transpose_bits_kernel<<<grid_for((int64_t)h->N * pwords, 256, h->sms), 256, 0, h->st>>>(
+        d_states, h->bitsAT.as<uint64_t>(), h->N, h->words, n, pwords);
+    HN_CUDA_TRY(cudaGetLastError());
+    OpBits a{h->bitsAT.as<uint64_t>(), pwords, h->N, n, vm.lo, vm.hi};
+    EpiStore e{h->dW, h->ldw, h->N, h->N};
+    return launch_gemm_f64(a, a, e, h->N, h->N, n, h->st);
+}
+
+struct OpBitsDiffG {  // scale * (val_a(bitA) - val_b(bitB))
+    const uint64_t* a; const uint64_t* b; int words; int rows; int K; double alo, ahi, blo, bhi, scale;
+    __device__ __forceinline__ void load8(int row, int k0, double (&v)[8]) const {
+        unsigned ba = 0, bb = 0;
+        if (row < rows && k0 < K) {
+            size_t o = (size_t)row * words + (k0 >> 6);
+            ba = (unsigned)((a[o] >> (k0 & 63)) & 0xFFu);
+            bb = (unsigned)((b[o] >> (k0 & 63)) & 0xFFu);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const double va = ((ba >> e) & 1u) ? ahi : alo, vb = ((bb >> e) & 1u) ? bhi : blo;
+            v[e] = (row < rows && (k0 + e) < K) ? scale * (va - vb) : 0.0;
+        }
+    }
+};
+
+int all_reduce_dw(hn_handle h) {
+    if (!h->comm) return HN_OK;
+    HN_NCCL_TRY(g_nccl.AllReduce(h->dW, h->dW, (size_t)h->N * h->ldw, NCCL_FLOAT64, NCCL_SUM, h->comm, h->st));
+    return HN_OK;
+}
+
+int apply_update_and_constraints(hn_handle h) {
+    apply_update_kernel<<<grid_for((int64_t)h->N * h->ldw, 256, h->sms), 256, 0, h->st>>>(h->W, h->dW, h->N, h->ldw,
+                                                                                       h->cfg.learning_rate);
+    HN_CUDA_TRY(cudaGetLastError());
+    if (h->cfg.force_zero_diagonal || h->cfg.force_symmetric) {
+        dim3 g((h->N + SYM_T - 1) / SYM_T, (h->N + SYM_T - 1) / SYM_T), b(SYM_T, 8);
+        constraints_kernel<<<g, b, 0, h->st>>>(h->W, h->N, h->ldw, h->cfg.force_zero_diagonal, h->cfg.force_symmetric);
+        HN_CUDA_TRY(cudaGetLastError());
+    }
+    h->w_symmetric = h->cfg.force_symmetric != 0;
+    weights_changed(h);
+    return HN_OK;
+}
+
+int upload_states(hn_handle h, DevBuf& buf, const uint64_t* host, int n) {
+    HN_TRY(buf.reserve(sizeof(uint64_t) * (size_t)std::max(n, 1) * h->words));
+    HN_CUDA_TRY(cudaMemcpyAsync(buf.p, host, sizeof(uint64_t) * (size_t)n * h->words, cudaMemcpyHostToDevice, h->st));
+    return HN_OK;
+}
+
+int hebbian_epoch_impl(hn_handle h, const uint64_t* states, int n, ValueMap vm) {
+    HN_TRY(upload_states(h, h->bitsA, states, n));
+    HN_TRY(contraction_hebbian(h, h->bitsA.as<uint64_t>(), n, vm));
+    HN_TRY(all_reduce_dw(h));
+    return apply_update_and_constraints(h);
+}
+
+// tvm: value map of the target states as the rule sees them (mapped rules re-activate);
+// the relaxed copies always carry the network domain's values.
+int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised, const uint16_t* perms, int n,
+                     uint64_t* relaxed_out, ValueMap tvm) {
+    const int N = h->N, words = h->words;
+    HN_TRY(ensure_margin(h));
+    HN_TRY(refresh_wt(h));
+    HN_TRY(upload_states(h, h->bitsA, states, n));
+    HN_TRY(upload_states(h, h->bitsB, noised, n));
+    HN_TRY(h->bitsC.reserve(sizeof(uint64_t) * (size_t)n * words));
+    // permutations: one fresh order per copy (HopfieldNetwork.go:281-282)
+    uint16_t *d_perm = nullptr, *d_inv = nullptr;
+    HN_TRY(upload_pool(h, perms, n, h->perms, &d_perm, &d_inv));
+    // offsets[p] = p : copy p uses its own row
+    HN_TRY(h->offsets.reserve(sizeof(int32_t) * (size_t)n));
+    std::vector<int32_t> off((size_t)n);
+    for (int i = 0; i < n; i++) off[i] = i;
+    HN_CUDA_TRY(cudaMemcpyAsync(h->offsets.p, off.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));  // `off` must outlive the copy
+    // fields of the noised copies, then ONE sweep each without stability test (UpdateState)
+    HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
+    HN_TRY(h->small.reserve(256));
+    int32_t* d_small = h->small.as<int32_t>();
+    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 64, h->st));
+    RelaxParams p{};
+    p.N = N; p.ldw = h->ldw; p.words = words;
+    p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;
+    p.H0 = h->H.as<double>(); p.ldh = h->ldw;
+    p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n;
+    p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.max_unstable = 0; p.domain = h->cfg.domain;
+    p.check_stability = 0; p.serial_stream = 0; p.tau_base = h->tau_base; p.tau_flip = h->tau_flip;
+    p.final_states = h->bitsC.as<uint64_t>();
+    p.work_counter = d_small; p.status = d_small + 1;
+    HN_TRY(launch_relax(h, p));
+    if (relaxed_out)
+        HN_CUDA_TRY(cudaMemcpyAsync(relaxed_out, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));
+    // dW[i][j] = sum_mu 0.5*(t_mu,i - r_mu,i) * t_mu,j
+    const int pwords = (n + 63) / 64;
+    HN_TRY(h->bitsAT.reserve(sizeof(uint64_t) * (size_t)N * pwords));
+    HN_TRY(h->bitsCT.reserve(sizeof(uint64_t) * (size_t)N * pwords));
+    const int tg = grid_for((int64_t)N * pwords, 256, h->sms);
+    transpose_bits_kernel<<<tg, 256, 0, h->st>>>(h->bitsA.as<uint64_t>(), h->bitsAT.as<uint64_t>(), N, words, n, pwords);
+    transpose_bits_kernel<<<tg, 256, 0, h->st>>>(h->bitsC.as<uint64_t>(), h->bitsCT.as<uint64_t>(), N, words, n, pwords);
+    HN_CUDA_TRY(cudaGetLastError());
+    const ValueMap rvm = domain_values(h->cfg.domain);
+    OpBitsDiffG a{h->bitsAT.as<uint64_t>(), h->bitsCT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi, rvm.lo, rvm.hi, 0.5};
+    OpBits b{h->bitsAT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi};
+    EpiStore e{h->dW, h->ldw, N, N};
+    HN_TRY(launch_gemm_f64(a, b, e, N, N, n, h->st));
+    HN_TRY(all_reduce_dw(h));
+    HN_TRY(apply_update_and_constraints(h));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int energy_profiles_impl(hn_handle h, const uint64_t* d_states, int n, double* energies_out, int32_t* unstable_out,
+                         uint8_t* stable_out, double* state_energy_out) {
+    const int N = h->N;
+    HN_TRY(ensure_margin(h));
+    HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_TRY(launch_fields(h, d_states, n, h->H.as<double>(), domain_values(h->cfg.domain)));
+    if (energies_out) HN_TRY(h->energies.reserve(sizeof(double) * (size_t)n * N));
+    HN_TRY(h->eunst.reserve(sizeof(int32_t) * (size_t)n));
+    HN_TRY(h->estab.reserve((size_t)n));
+    HN_TRY(h->esum.reserve(sizeof(double) * (size_t)n));
+    energy_epilogue_kernel<<<n, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, d_states, h->words, h->W, h->ldw, N,
+                                                        h->cfg.domain, h->tau_base, h->cfg.max_relax_unstable_units,
+                                                        energies_out ? h->energies.as<double>() : nullptr,
+                                                        h->eunst.as<int32_t>(), h->estab.as<uint8_t>(), h->esum.as<double>(),
+                                                        nullptr);
+    HN_CUDA_TRY(cudaGetLastError());
+    if (energies_out) HN_CUDA_TRY(cudaMemcpyAsync(energies_out, h->energies.p, sizeof(double) * (size_t)n * N, cudaMemcpyDeviceToHost, h->st));
+    if (unstable_out) HN_CUDA_TRY(cudaMemcpyAsync(unstable_out, h->eunst.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+    if (stable_out) HN_CUDA_TRY(cudaMemcpyAsync(stable_out, h->estab.p, (size_t)n, cudaMemcpyDeviceToHost, h->st));
+    if (state_energy_out) HN_CUDA_TRY(cudaMemcpyAsync(state_energy_out, h->esum.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int append_targets(hn_handle h, const uint64_t* states, int n) {
+    const size_t each = sizeof(uint64_t) * (size_t)h->words;
+    DevBuf nb;
+    HN_TRY(nb.reserve(each * (size_t)(h->P + n)));
+    if (h->P > 0) HN_CUDA_TRY(cudaMemcpyAsync(nb.p, h->targets.p, each * (size_t)h->P, cudaMemcpyDeviceToDevice, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync((char*)nb.p + each * (size_t)h->P, states, each * (size_t)n, cudaMemcpyHostToDevice, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->targets.release();
+    h->targets = nb;
+    h->P += n;
+    return HN_OK;
+}
+
+bool check_handle(hn_handle h, const char* fn) {
+    if (!h) { set_error("%s: handle is NULL", fn); return false; }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hn_abi_version(void) { return HN_ABI_VERSION; }
+const char* hn_last_error(void) { return hn::g_err; }
+
+void hn_default_config(hn_config* cfg) {
+    if (!cfg) return;
+    cfg->dimension = 0;
+    cfg->domain = HN_DOMAIN_BIPOLAR;
+    cfg->force_symmetric = 1;
+    cfg->force_zero_diagonal = 1;
+    cfg->max_relax_unstable_units = 0;
+    cfg->max_relax_iterations = 100;
+    cfg->learning_rate = 1.0;
+    cfg->device = 0;
+    cfg->reserved = 0;
+}
+
+int hn_create(const hn_config* cfg, hn_handle* out) {
+    if (!cfg || !out) { set_error("hn_create: NULL argument"); return HN_E_INVALID; }
+    *out = nullptr;
+    if (cfg->dimension <= 0) {
+        // HopfieldNetworkBuilder.go:215-217
+        set_error("HopfieldNetworkBuilder encountered an error during build! Dimension must be explicitly set to a positive integer!");
+        return HN_E_INVALID;
+    }
+    if (cfg->dimension > 65535) { set_error("dimension %d exceeds 65535 (uint16 unit indices)", cfg->dimension); return HN_E_INVALID; }
+    if (cfg->domain != HN_DOMAIN_BIPOLAR && cfg->domain != HN_DOMAIN_BINARY) { set_error("unknown domain %d", cfg->domain); return HN_E_INVALID; }
+    if (cfg->max_relax_iterations <= 0) { set_error("max_relax_iterations must be positive"); return HN_E_INVALID; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libhopfield_b200 has no CPU fallback", ce != cudaSuccess ? cudaGetErrorString(ce) : "0 devices");
+        return HN_E_NO_DEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("device ordinal %d out of range (0..%d)", cfg->device, ndev - 1); return HN_E_NO_DEVICE; }
+    cudaDeviceProp prop;
+    HN_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only and has no fallback", cfg->device, prop.major, prop.minor);
+        return HN_E_NO_DEVICE;
+    }
+    hn_handle h = new (std::nothrow) hn_handle_s();
+    if (!h) return HN_E_OOM;
+    h->cfg = *cfg;
+    h->N = cfg->dimension;
+    h->ldw = round_up(h->N, 16);
+    h->ldp = round_up(h->N, 16);
+    h->words = hn_words(h->N);
+    h->sms = prop.multiProcessorCount;
+    int rc = HN_OK;
+    do {
+        if (cudaSetDevice(cfg->device) != cudaSuccess) { rc = HN_E_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { rc = HN_E_CUDA; break; }
+        const size_t wb = sizeof(double) * (size_t)h->N * h->ldw;
+        if (cudaMalloc(&h->W, wb) != cudaSuccess || cudaMalloc(&h->dW, wb) != cudaSuccess) { rc = HN_E_OOM; break; }
+        if (cudaMemsetAsync(h->W, 0, wb, h->st) != cudaSuccess) { rc = HN_E_CUDA; break; }  // matrix.Zero(), :248-250
+        if (cudaMemsetAsync(h->dW, 0, wb, h->st) != cudaSuccess) { rc = HN_E_CUDA; break; }
+        for (auto& e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) { rc = HN_E_CUDA; break; }
+        if (rc != HN_OK) break;
+        if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = HN_E_CUDA; break; }
+    } while (0);
+    if (rc != HN_OK) {
+        set_error("hn_create: CUDA setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        hn_destroy(h);
+        return rc;
+    }
+    h->w_symmetric = true;  // the zero matrix
+    *out = h;
+    return HN_OK;
+}
+
+int hn_destroy(hn_handle h) {
+    if (!h) return HN_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->st) cudaStreamSynchronize(h->st);
+    DevBuf* bufs[] = {&h->targets, &h->probes, &h->pool, &h->offsets, &h->H, &h->finals, &h->steps, &h->stable,
+                      &h->flips, &h->margin, &h->dist, &h->hash, &h->energies, &h->history, &h->rep, &h->first, &h->hits,
+                      &h->flag, &h->rank, &h->table, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
+                      &h->bitsA, &h->bitsB, &h->bitsC, &h->bitsAT, &h->bitsCT, &h->perms, &h->eunst, &h->estab, &h->esum,
+                      &h->emargin};
+    for (DevBuf* b : bufs) b->release();
+    if (h->W) cudaFree(h->W);
+    if (h->WT) cudaFree(h->WT);
+    if (h->dW) cudaFree(h->dW);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return HN_OK;
+}
+
+int hn_set_weights(hn_handle h, const double* w_host) {
+    if (!check_handle(h, "hn_set_weights") || !w_host) { if (h) set_error("hn_set_weights: NULL matrix"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_CUDA_TRY(cudaMemsetAsync(h->W, 0, sizeof(double) * (size_t)h->N * h->ldw, h->st));
+    HN_CUDA_TRY(cudaMemcpy2DAsync(h->W, sizeof(double) * h->ldw, w_host, sizeof(double) * h->N, sizeof(double) * h->N, h->N,
+                                  cudaMemcpyHostToDevice, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    HN_TRY(detect_symmetry(h));
+    weights_changed(h);
+    return HN_OK;
+}
+
+int hn_get_weights(hn_handle h, double* w_host) {
+    if (!check_handle(h, "hn_get_weights") || !w_host) { if (h) set_error("hn_get_weights: NULL matrix"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_CUDA_TRY(cudaMemcpy2DAsync(w_host, sizeof(double) * h->N, h->W, sizeof(double) * h->ldw, sizeof(double) * h->N, h->N,
+                                  cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int hn_set_targets(hn_handle h, const uint64_t* targets_packed, int32_t n_targets) {
+    if (!check_handle(h, "hn_set_targets")) return HN_E_INVALID;
+    if (n_targets < 0 || (n_targets > 0 && !targets_packed)) { set_error("hn_set_targets: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    h->targets.release();
+    h->P = 0;
+    if (n_targets > 0) HN_TRY(append_targets(h, targets_packed, n_targets));
+    return HN_OK;
+}
+int hn_num_targets(hn_handle h, int32_t* n_targets) {
+    if (!check_handle(h, "hn_num_targets") || !n_targets) return HN_E_INVALID;
+    *n_targets = h->P;
+    return HN_OK;
+}
+int hn_get_targets(hn_handle h, uint64_t* targets_packed) {
+    if (!check_handle(h, "hn_get_targets") || !targets_packed) return HN_E_INVALID;
+    HN_TRY(set_device(h));
+    if (h->P > 0) {
+        HN_CUDA_TRY(cudaMemcpyAsync(targets_packed, h->targets.p, sizeof(uint64_t) * (size_t)h->P * h->words, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    }
+    return HN_OK;
+}
+
+int hn_hebbian_epoch(hn_handle h, const uint64_t* states_packed, int32_t n) {
+    if (!check_handle(h, "hn_hebbian_epoch")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed) { set_error("hn_hebbian_epoch: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(hebbian_epoch_impl(h, states_packed, n, domain_values(h->cfg.domain)));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int hn_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* noised_packed, const uint16_t* perms,
+                   int32_t n, uint64_t* relaxed_out) {
+    if (!check_handle(h, "hn_delta_epoch")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed || !noised_packed || !perms) { set_error("hn_delta_epoch: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(validate_pool_host(h, perms, n));
+    return delta_epoch_impl(h, states_packed, noised_packed, perms, n, relaxed_out, domain_values(h->cfg.domain));
+}
+
+int hn_enforce_constraints(hn_handle h) {
+    if (!check_handle(h, "hn_enforce_constraints")) return HN_E_INVALID;
+    HN_TRY(set_device(h));
+    if (h->cfg.force_zero_diagonal || h->cfg.force_symmetric) {
+        dim3 g((h->N + SYM_T - 1) / SYM_T, (h->N + SYM_T - 1) / SYM_T), b(SYM_T, 8);
+        constraints_kernel<<<g, b, 0, h->st>>>(h->W, h->N, h->ldw, h->cfg.force_zero_diagonal, h->cfg.force_symmetric);
+        HN_CUDA_TRY(cudaGetLastError());
+        if (h->cfg.force_symmetric) h->w_symmetric = true;
+        weights_changed(h);
+    }
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int hn_normalize_frobenius(hn_handle h, double* norm_out) {
+    if (!check_handle(h, "hn_normalize_frobenius")) return HN_E_INVALID;
+    HN_TRY(set_device(h));
+    const int np = 1024;
+    HN_TRY(h->partial.reserve(sizeof(double) * (np + 2)));
+    double* part = h->partial.as<double>();
+    sumsq_partial_kernel<<<np, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, part);
+    sumsq_final_kernel<<<1, RED_THREADS, 0, h->st>>>(part, np, part + np);
+    scale_kernel<<<grid_for((int64_t)h->N * h->ldw, 256, h->sms), 256, 0, h->st>>>(h->W, h->N, h->ldw, part + np);
+    HN_CUDA_TRY(cudaGetLastError());
+    double nrm[2] = {0, 0};
+    HN_CUDA_TRY(cudaMemcpyAsync(nrm, part + np, sizeof(nrm), cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (norm_out) *norm_out = nrm[0];
+    weights_changed(h);
+    return HN_OK;
+}
+
+int hn_energy_profiles(hn_handle h, const uint64_t* states_packed, int32_t n, double* energies_out,
+                       int32_t* unstable_out, uint8_t* stable_out, double* state_energy_out) {
+    if (!check_handle(h, "hn_energy_profiles")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed) { set_error("hn_energy_profiles: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(upload_states(h, h->bitsA, states_packed, n));
+    return energy_profiles_impl(h, h->bitsA.as<uint64_t>(), n, energies_out, unstable_out, stable_out, state_energy_out);
+}
+
+int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t rule, int32_t method,
+                    int32_t epochs, int32_t noise_method, double noise_scale, hn_rng rng, int32_t learn_cap,
+                    int32_t* learn_epoch_out, int32_t* learn_index_out, uint8_t* learn_stable_out,
+                    double* learn_energy_out, int32_t* n_learn_rows) {
+    if (!check_handle(h, "hn_learn_states")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed) { set_error("hn_learn_states: bad argument"); return HN_E_INVALID; }
+    if (epochs <= 0) {  // HopfieldNetworkBuilder.go:219-221
+        set_error("HopfieldNetworkBuilder encountered an error during build! Epochs must be a positive integer!");
+        return HN_E_INVALID;
+    }
+    if (noise_scale < 0.0 || noise_scale > 1.0) {  // :223-225
+        set_error("HopfieldNetworkBuilder encountered an error during build! learningNoiseRatio must be in range [0.0, 1.0]!");
+        return HN_E_INVALID;
+    }
+    if (rule == HN_RULE_THERMAL_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA) {
+        set_error("thermal delta rules are not implemented on the device path (SURVEY 8f #3)");
+        return HN_E_INVALID;
+    }
+    if (rule < 0 || rule > 5 || (method != HN_METHOD_FULL_SET && method != HN_METHOD_ITERATIVE_BATCH)) {
+        set_error("unknown learning rule %d / method %d", rule, method);
+        return HN_E_INVALID;
+    }
+    const bool is_delta = rule == HN_RULE_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_DELTA;
+    if (is_delta && !rng) { set_error("hn_learn_states: the delta rule needs an rng"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    const int N = h->N, words = h->words;
+    HN_TRY(append_targets(h, states_packed, n));  // HopfieldNetwork.go:258
+    // value map the rule sees: bipolarMappedHebbian re-activates with the BINARY manager (sic,
+    // LearningRule.go:80); bipolarMappedDelta with the Bipolar manager (:119).
+    ValueMap tvm = domain_values(h->cfg.domain);
+    if (rule == HN_RULE_BIPOLAR_MAPPED_HEBBIAN) tvm = ValueMap{0.0, 1.0};
+    if (rule == HN_RULE_BIPOLAR_MAPPED_DELTA) tvm = ValueMap{-1.0, 1.0};
+    const ValueMap nvm = domain_values(h->cfg.domain);
+    int produced = 0, last_epoch = 0;
+    std::vector<uint64_t> noised;
+    std::vector<uint16_t> perms;
+    std::vector<double> tmp((size_t)N);
+    std::vector<uint8_t> stab;
+    std::vector<double> en;
+
+    auto full_set = [&](int cnt, int epoch_offset) -> int {  // LearningMethod.go:38-61
+        for (int epoch = 0; epoch < epochs; epoch++) {
+            if (!is_delta) {
+                HN_TRY(hebbian_epoch_impl(h, states_packed, cnt, tvm));
+            } else {
+                noised.assign((size_t)cnt * words, 0);
+                perms.resize((size_t)cnt * N);
+                for (int s = 0; s < cnt; s++) {  // LearningRule.go:98-104, draw order: noise then shuffle
+                    const uint64_t* src = states_packed + (size_t)s * words;
+                    for (int i = 0; i < N; i++) tmp[i] = ((src[i >> 6] >> (i & 63)) & 1ULL) ? tvm.hi : tvm.lo;
+                    HN_TRY(hn_rng_apply_noise(rng, noise_method, noise_scale, tmp.data(), N));
+                    uint64_t* dst = noised.data() + (size_t)s * words;
+                    for (int i = 0; i < N; i++) if (tmp[i] > 0.0) dst[i >> 6] |= 1ULL << (i & 63);  // network activation
+                    uint16_t* pr = perms.data() + (size_t)s * N;
+                    for (int i = 0; i < N; i++) pr[i] = (uint16_t)i;
+                    HN_TRY(hn_rng_shuffle_u16(rng, pr, N));
+                }
+                HN_TRY(delta_epoch_impl(h, states_packed, noised.data(), perms.data(), cnt, nullptr, tvm));
+            }
+            // per-target diagnostics (LearningMethod.go:45-53) on the ORIGINAL states in the network domain
+            stab.resize((size_t)cnt);
+            const bool want_e = learn_energy_out != nullptr && produced < learn_cap;
+            if (want_e) en.resize((size_t)cnt * N);
+            HN_TRY(upload_states(h, h->bitsA, states_packed, cnt));
+            HN_TRY(energy_profiles_impl(h, h->bitsA.as<uint64_t>(), cnt, want_e ? en.data() : nullptr, nullptr, stab.data(), nullptr));
+            bool all_stable = true;
+            for (int s = 0; s < cnt; s++) {
+                if (!stab[s]) all_stable = false;
+                if (produced < learn_cap) {
+                    if (learn_epoch_out) learn_epoch_out[produced] = epoch + epoch_offset;
+                    if (learn_index_out) learn_index_out[produced] = s;
+                    if (learn_stable_out) learn_stable_out[produced] = stab[s];
+                    if (want_e) std::memcpy(learn_energy_out + (size_t)produced * N, en.data() + (size_t)s * N, sizeof(double) * N);
+                }
+                produced++;
+                last_epoch = epoch + epoch_offset;
+            }
+            if (all_stable) break;  // AllStatesAreStable :56-58
+        }
+        return HN_OK;
+    };
+    (void)nvm;
+    if (method == HN_METHOD_FULL_SET) {
+        HN_TRY(full_set(n, 0));
+    } else {  // iterativeBatchLearningMethod, LearningMethod.go:70-89 (BATCHSIZE 5)
+        const int batches = n / 5;
+        int total = 0;
+        for (int it = 1; it <= batches; it++) {
+            HN_TRY(full_set(5 * it, total));
+            total = last_epoch;
+        }
+    }
+    HN_TRY(hn_normalize_frobenius(h, nullptr));  // HopfieldNetwork.go:260
+    if (n_learn_rows) *n_learn_rows = produced;
+    return HN_OK;
+}
+
+int hn_relax_batch(hn_handle h, const uint64_t* probes_packed, int32_t n_probes, const uint16_t* perm_pool,
+                   int32_t n_pool, const int32_t* offsets, uint32_t flags, hn_relax_out* out) {
+    if (!check_handle(h, "hn_relax_batch")) return HN_E_INVALID;
+    if (n_probes < 0 || n_pool <= 0 || !perm_pool || !out || (n_probes > 0 && !probes_packed)) {
+        set_error("hn_relax_batch: bad argument");
+        return HN_E_INVALID;
+    }
+    if (n_probes == 0) {
+        out->n_unique = 0; out->total_flips = out->total_sweeps = out->total_margin_hits = 0; out->device_ms = 0;
+        return HN_OK;
+    }
+    HN_TRY(set_device(h));
+    HN_TRY(validate_pool_host(h, perm_pool, n_pool));
+    HN_TRY(upload_states(h, h->probes, probes_packed, n_probes));
+    HN_TRY(upload_pool(h, perm_pool, n_pool, h->pool, &h->d_pool, &h->d_inv));
+    h->resident_B = n_probes; h->resident_pool = n_pool;
+    const int32_t* d_off = nullptr;
+    if (offsets && !(flags & HN_RELAX_SERIAL_STREAM)) {
+        for (int i = 0; i < n_probes; i++)
+            if (offsets[i] < 0) { set_error("hn_relax_batch: negative offset"); return HN_E_INVALID; }
+        HN_TRY(h->offsets.reserve(sizeof(int32_t) * (size_t)n_probes));
+        HN_CUDA_TRY(cudaMemcpyAsync(h->offsets.p, offsets, sizeof(int32_t) * (size_t)n_probes, cudaMemcpyHostToDevice, h->st));
+        d_off = h->offsets.as<int32_t>();
+    }
+    HN_TRY(relax_device(h, h->probes.as<uint64_t>(), n_probes, h->d_pool, h->d_inv, n_pool, d_off,
+                        flags, out->energies != nullptr, out->distances != nullptr));
+    return download_results(h, out);
+}
+
+int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint16_t* perms) {
+    if (!check_handle(h, "hn_update_states")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed || !perms) { set_error("hn_update_states: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(validate_pool_host(h, perms, n));
+    HN_TRY(ensure_margin(h));
+    HN_TRY(refresh_wt(h));
+    const int N = h->N, words = h->words;
+    HN_TRY(upload_states(h, h->bitsB, states_packed, n));
+    HN_TRY(h->bitsC.reserve(sizeof(uint64_t) * (size_t)n * words));
+    uint16_t *d_perm = nullptr, *d_inv = nullptr;
+    HN_TRY(upload_pool(h, perms, n, h->perms, &d_perm, &d_inv));
+    HN_TRY(h->offsets.reserve(sizeof(int32_t) * (size_t)n));
+    std::vector<int32_t> off((size_t)n);
+    for (int i = 0; i < n; i++) off[i] = i;
+    HN_CUDA_TRY(cudaMemcpyAsync(h->offsets.p, off.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
+    HN_TRY(h->small.reserve(256));
+    int32_t* d_small = h->small.as<int32_t>();
+    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 64, h->st));
+    RelaxParams p{};
+    p.N = N; p.ldw = h->ldw; p.words = words;
+    p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;
+    p.H0 = h->H.as<double>(); p.ldh = h->ldw;
+    p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv;
+    p.ldp = h->ldp; p.n_pool = n; p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.domain = h->cfg.domain;
+    p.check_stability = 0; p.tau_base = h->tau_base; p.tau_flip = h->tau_flip;
+    p.final_states = h->bitsC.as<uint64_t>(); p.work_counter = d_small; p.status = d_small + 1;
+    HN_TRY(launch_relax(h, p));
+    HN_CUDA_TRY(cudaMemcpyAsync(states_packed, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int hn_upload_perm_pool(hn_handle h, const uint16_t* perm_pool, int32_t n_pool) {
+    if (!check_handle(h, "hn_upload_perm_pool")) return HN_E_INVALID;
+    if (n_pool <= 0 || !perm_pool) { set_error("hn_upload_perm_pool: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(validate_pool_host(h, perm_pool, n_pool));
+    HN_TRY(upload_pool(h, perm_pool, n_pool, h->pool, &h->d_pool, &h->d_inv));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->resident_pool = n_pool;
+    return HN_OK;
+}
+int hn_upload_probes(hn_handle h, const uint64_t* probes_packed, int32_t n_probes) {
+    if (!check_handle(h, "hn_upload_probes")) return HN_E_INVALID;
+    if (n_probes <= 0 || !probes_packed) { set_error("hn_upload_probes: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(upload_states(h, h->probes, probes_packed, n_probes));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->resident_B = n_probes;
+    return HN_OK;
+}
+int hn_relax_resident(hn_handle h, uint32_t flags, double* device_ms) {
+    if (!check_handle(h, "hn_relax_resident")) return HN_E_INVALID;
+    if (h->resident_B <= 0 || h->resident_pool <= 0) { set_error("hn_relax_resident: upload probes and a pool first"); return HN_E_STATE; }
+    if (flags & (HN_RELAX_SERIAL_STREAM | HN_RELAX_HISTORY)) { set_error("hn_relax_resident: unsupported flag"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(relax_device(h, h->probes.as<uint64_t>(), h->resident_B, h->d_pool, h->d_inv,
+                        h->resident_pool, nullptr, flags, false, true));
+    if (device_ms) *device_ms = h->timing.fields_ms + h->timing.relax_ms + h->timing.post_ms;
+    return HN_OK;
+}
+int hn_download_results(hn_handle h, hn_relax_out* out) {
+    if (!check_handle(h, "hn_download_results") || !out) return HN_E_INVALID;
+    HN_TRY(set_device(h));
+    return download_results(h, out);
+}
+int hn_last_relax_timing(hn_handle h, hn_relax_timing* t) {
+    if (!check_handle(h, "hn_last_relax_timing") || !t) return HN_E_INVALID;
+    *t = h->timing;
+    return HN_OK;
+}
+int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip) {
+    if (!check_handle(h, "hn_get_margin")) return HN_E_INVALID;
+    HN_TRY(set_device(h));
+    HN_TRY(ensure_margin(h));
+    if (tau_base) *tau_base = h->tau_base;
+    if (tau_per_flip) *tau_per_flip = h->tau_flip;
+    return HN_OK;
+}
+
+int hn_pack_states_f64(int32_t dimension, int32_t n, const double* states_f64, uint64_t* packed) {
+    if (dimension <= 0 || n < 0 || !states_f64 || !packed) { set_error("hn_pack_states_f64: bad argument"); return HN_E_INVALID; }
+    const int words = hn_words(dimension);
+    std::memset(packed, 0, sizeof(uint64_t) * (size_t)n * words);
+    for (int s = 0; s < n; s++)
+        for (int i = 0; i < dimension; i++)
+            if (states_f64[(size_t)s * dimension + i] > 0.0) packed[(size_t)s * words + (i >> 6)] |= 1ULL << (i & 63);
+    return HN_OK;
+}
+int hn_unpack_states_f64(int32_t dimension, int32_t domain, int32_t n, const uint64_t* packed, double* states_f64) {
+    if (dimension <= 0 || n < 0 || !states_f64 || !packed) { set_error("hn_unpack_states_f64: bad argument"); return HN_E_INVALID; }
+    const int words = hn_words(dimension);
+    const double lo = domain == HN_DOMAIN_BINARY ? 0.0 : -1.0;
+    for (int s = 0; s < n; s++)
+        for (int i = 0; i < dimension; i++)
+            states_f64[(size_t)s * dimension + i] = ((packed[(size_t)s * words + (i >> 6)] >> (i & 63)) & 1ULL) ? 1.0 : lo;
+    return HN_OK;
+}
+
+int hn_comm_unique_id(uint8_t id[HN_NCCL_UNIQUE_ID_BYTES]) {
+    if (!id) return HN_E_INVALID;
+    HN_TRY(load_nccl());
+    HN_NCCL_TRY(g_nccl.GetUniqueId(id));
+    return HN_OK;
+}
+int hn_comm_attach(hn_handle h, const uint8_t id[HN_NCCL_UNIQUE_ID_BYTES], int32_t rank, int32_t n_ranks) {
+    if (!check_handle(h, "hn_comm_attach") || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) { set_error("hn_comm_attach: bad argument"); return HN_E_INVALID; }
+    HN_TRY(load_nccl());
+    HN_TRY(set_device(h));
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    Id128 uid;
+    std::memcpy(uid.bytes, id, 128);
+    HN_NCCL_TRY(g_nccl.CommInitRank(&h->comm, n_ranks, uid, rank));
+    h->rank_id = rank; h->n_ranks = n_ranks;
+    return HN_OK;
+}
+int hn_comm_detach(hn_handle h) {
+    if (!check_handle(h, "hn_comm_detach")) return HN_E_INVALID;
+    if (h->comm) { HN_TRY(set_device(h)); cudaStreamSynchronize(h->st); g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    h->rank_id = 0; h->n_ranks = 1;
+    return HN_OK;
+}
+int hn_broadcast_weights(hn_handle h, int32_t root) {
+    if (!check_handle(h, "hn_broadcast_weights")) return HN_E_INVALID;
+    if (!h->comm) { set_error("hn_broadcast_weights: no communicator attached"); return HN_E_STATE; }
+    HN_TRY(set_device(h));
+    HN_NCCL_TRY(g_nccl.Broadcast(h->W, h->W, (size_t)h->N * h->ldw, NCCL_FLOAT64, root, h->comm, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    weights_changed(h);
+    return detect_symmetry(h);
+}
+
+}  // extern "C"

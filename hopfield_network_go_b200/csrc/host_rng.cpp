@@ -1,0 +1,172 @@
+// host_rng.cpp — host-side restatement of the reference's random stream, so that
+// hosts which are not Go can generate the update orders and learning noise the
+// reference would draw and upload them (BASELINE north_star: "generated
+// host-side from the reference's seeded RNG and uploaded").
+//
+// Restates golang.org/x/exp/rand @ 642cacee5cc0 (go.mod:12; source not in the
+// reference tree): PCG XSL-RR 128/64 source, Rand.Uint64n / Shuffle / Float64 /
+// NormFloat64.  Reference call sites: hopfieldutils/HopfieldUtils.go:35-39,
+// noiseapplication/NoiseApplication.go:64-105, HopfieldNetworkBuilder.go:231-232.
+// A Go host does not need this file: it calls x/exp/rand directly.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/hopfield_b200.h"
+
+namespace hn { void set_error(const char* fmt, ...); }
+
+namespace {
+
+using u128 = unsigned __int128;
+
+struct Pcg {
+    u128 state;
+    static constexpr u128 kMul = ((u128)2549297995355413924ULL << 64) | 4865540595714422341ULL;
+    static constexpr u128 kInc = ((u128)6364136223846793005ULL << 64) | 1442695040888963407ULL;
+    explicit Pcg(uint64_t seed) : state(((u128)seed << 64) | seed) {}  // Seed: low = high = seed
+    uint64_t next() {
+        state = state * kMul + kInc;
+        const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
+        const unsigned rot = (unsigned)(hi >> 58);
+        const uint64_t x = hi ^ lo;
+        return (x >> rot) | (x << ((64u - rot) & 63u));
+    }
+    uint64_t below(uint64_t n) {  // Rand.Uint64n
+        if ((n & (n - 1)) == 0) return next() & (n - 1);
+        uint64_t v = next();
+        if (v > UINT64_MAX - n) {
+            const uint64_t ceiling = UINT64_MAX - UINT64_MAX % n;
+            while (v >= ceiling) v = next();
+        }
+        return v % n;
+    }
+    double unit() {  // Rand.Float64
+        for (;;) {
+            const double f = (double)below(1ULL << 53) / 9007199254740992.0;
+            if (f != 1.0) return f;
+        }
+    }
+    template <class T> void shuffle(T* list, int n) {  // Rand.Shuffle (Fisher-Yates from the top)
+        for (int i = n - 1; i > 0; i--) {
+            const int j = (int)below((uint64_t)i + 1);
+            T t = list[i]; list[i] = list[j]; list[j] = t;
+        }
+    }
+};
+
+// Ziggurat tables for NormFloat64 (Marsaglia & Tsang 2000, 128 strips); Go ships
+// them as float32/uint32 literals of the same construction.
+struct Zig {
+    uint32_t kn[128]; float wn[128], fn[128];
+    static constexpr double rn = 3.442619855899;
+    Zig() {
+        const double m1 = 2147483648.0;
+        double dn = rn, tn = dn, vn = 9.91256303526217e-3;
+        const double q = vn / std::exp(-.5 * dn * dn);
+        kn[0] = (uint32_t)((dn / q) * m1); kn[1] = 0;
+        wn[0] = (float)(q / m1); wn[127] = (float)(dn / m1);
+        fn[0] = 1.0f; fn[127] = (float)std::exp(-.5 * dn * dn);
+        for (int i = 126; i >= 1; i--) {
+            dn = std::sqrt(-2. * std::log(vn / dn + std::exp(-.5 * dn * dn)));
+            kn[i + 1] = (uint32_t)((dn / tn) * m1);
+            tn = dn;
+            fn[i] = (float)std::exp(-.5 * dn * dn);
+            wn[i] = (float)(dn / m1);
+        }
+    }
+};
+const Zig& zig() { static Zig z; return z; }
+
+double norm_float64(Pcg& g) {
+    const Zig& z = zig();
+    for (;;) {
+        const int32_t j = (int32_t)(uint32_t)(g.next() >> 32);
+        const int32_t i = j & 0x7F;
+        double x = (double)j * (double)z.wn[i];
+        const uint32_t aj = j < 0 ? (uint32_t)(-(int64_t)j) : (uint32_t)j;
+        if (aj < z.kn[i]) return x;
+        if (i == 0) {
+            for (;;) {
+                x = -std::log(g.unit()) * (1.0 / Zig::rn);
+                const double y = -std::log(g.unit());
+                if (y + y >= x * x) break;
+            }
+            return j > 0 ? Zig::rn + x : -Zig::rn - x;
+        }
+        if (z.fn[i] + (float)g.unit() * (z.fn[i - 1] - z.fn[i]) < (float)std::exp(-.5 * x * x)) return x;
+    }
+}
+
+// maximalRatioInvertSliceElements (NoiseApplication.go:64-75): the index list has
+// length Len()-1, so the last unit is never inverted; count = int(N*ratio).
+void maximal_invert(Pcg& g, double* state, int n, double ratio) {
+    const int num = (int)((double)n * ratio);
+    const int m = n - 1;
+    std::vector<int32_t> idx((size_t)(m > 0 ? m : 0));
+    for (int i = 0; i < m; i++) idx[i] = i;
+    g.shuffle(idx.data(), m);
+    for (int i = 0; i < num && i < m; i++) state[idx[i]] = -1 * state[idx[i]];
+}
+
+}  // namespace
+
+struct hn_rng_s { Pcg g; explicit hn_rng_s(uint64_t s) : g(s) {} };
+
+extern "C" {
+
+int hn_rng_create(uint64_t seed, hn_rng* out) {
+    if (!out) { hn::set_error("hn_rng_create: out is NULL"); return HN_E_INVALID; }
+    *out = new (std::nothrow) hn_rng_s(seed);
+    return *out ? HN_OK : HN_E_OOM;
+}
+int hn_rng_destroy(hn_rng r) { delete r; return HN_OK; }
+uint64_t hn_rng_uint64(hn_rng r) { return r->g.next(); }
+uint64_t hn_rng_uint64n(hn_rng r, uint64_t n) { return r->g.below(n); }
+double hn_rng_float64(hn_rng r) { return r->g.unit(); }
+double hn_rng_norm_float64(hn_rng r) { return norm_float64(r->g); }
+
+int hn_rng_shuffle_u16(hn_rng r, uint16_t* list, int32_t n) {
+    if (!r || !list || n < 0) { hn::set_error("hn_rng_shuffle_u16: bad argument"); return HN_E_INVALID; }
+    r->g.shuffle(list, n);
+    return HN_OK;
+}
+
+int hn_rng_perm_pool(hn_rng r, int32_t dimension, int32_t n_rows, int32_t start_identity,
+                     uint16_t* list_io, uint16_t* pool_out) {
+    if (!r || !list_io || !pool_out || dimension <= 0 || dimension > 65535 || n_rows < 0) {
+        hn::set_error("hn_rng_perm_pool: bad argument");
+        return HN_E_INVALID;
+    }
+    if (start_identity)
+        for (int i = 0; i < dimension; i++) list_io[i] = (uint16_t)i;  // getUnitIndices, HopfieldNetwork.go:71-77
+    for (int row = 0; row < n_rows; row++) {
+        r->g.shuffle(list_io, dimension);  // ShuffleList on the persistent list, :393
+        std::memcpy(pool_out + (size_t)row * dimension, list_io, sizeof(uint16_t) * (size_t)dimension);
+    }
+    return HN_OK;
+}
+
+int hn_rng_apply_noise(hn_rng r, int32_t noise_method, double noise_scale, double* state, int32_t n) {
+    if (!r || !state || n <= 0) { hn::set_error("hn_rng_apply_noise: bad argument"); return HN_E_INVALID; }
+    switch (noise_method) {
+    case HN_NOISE_NONE: break;  // noNoiseApplication :51
+    case HN_NOISE_MAXIMAL_INVERSION: maximal_invert(r->g, state, n, noise_scale); break;
+    case HN_NOISE_RANDOM_SUBMAXIMAL_INVERSION: {  // :87-90
+        const double sel = std::fmod(r->g.unit(), noise_scale);
+        maximal_invert(r->g, state, n, sel);
+        break;
+    }
+    case HN_NOISE_GAUSSIAN:  // :101-105
+        for (int i = 0; i < n; i++) state[i] += norm_float64(r->g) * noise_scale;
+        break;
+    default:
+        hn::set_error("hn_rng_apply_noise: unknown noise method %d", noise_method);
+        return HN_E_INVALID;
+    }
+    return HN_OK;
+}
+
+}  // extern "C"

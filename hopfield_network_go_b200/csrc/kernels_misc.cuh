@@ -1,0 +1,336 @@
+// kernels_misc.cuh — HBM-bound elementwise / reduction kernels around the contractions:
+// weight update + constraints + Frobenius normalisation, energy epilogue,
+// permutation inversion, bit-matrix transpose, unique-attractor table.
+#pragma once
+#include "common.cuh"
+#include "relax.cuh"
+
+namespace hn {
+
+// ---- W <- W + lr*dW  (LearningRule.go:72-73 / :111-112) --------------------
+// updatedMatrix.Scale(lr) rounds once, matrix.Add rounds once: keep both
+// roundings (no FMA) so non-dyadic learning rates stay bit-identical.
+__global__ void apply_update_kernel(double* __restrict__ w, const double* __restrict__ dw, int n, int ld,
+                                    double lr) {
+    const int64_t total = (int64_t)n * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ld);
+        if (c < n) w[i] = __dadd_rn(w[i], __dmul_rn(lr, dw[i]));
+    }
+}
+
+// ---- enforceConstraints (HopfieldNetwork.go:55-67) --------------------------
+// zero diagonal first, then W <- 0.5*(W + W^T) from the OLD values (gonum's Add
+// against the transposed view goes through an aliasing workspace).
+// One CTA per tile pair (bi <= bj); both tiles staged in shared memory so every
+// global access is coalesced.
+constexpr int SYM_T = 32;
+__global__ void constraints_kernel(double* __restrict__ w, int n, int ld, int zero_diag, int symmetric) {
+    __shared__ double ta[SYM_T][SYM_T + 1], tb[SYM_T][SYM_T + 1];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int r = ty; r < SYM_T; r += blockDim.y) {
+        const int i = bi * SYM_T + r, j = bj * SYM_T + tx;
+        double a = (i < n && j < n) ? w[(size_t)i * ld + j] : 0.0;
+        if (zero_diag && i == j) a = 0.0;
+        ta[r][tx] = a;
+        const int i2 = bj * SYM_T + r, j2 = bi * SYM_T + tx;
+        double b = (i2 < n && j2 < n) ? w[(size_t)i2 * ld + j2] : 0.0;
+        if (zero_diag && i2 == j2) b = 0.0;
+        tb[r][tx] = b;
+    }
+    __syncthreads();
+    for (int r = ty; r < SYM_T; r += blockDim.y) {
+        const int i = bi * SYM_T + r, j = bj * SYM_T + tx;
+        if (i < n && j < n) {
+            const double a = ta[r][tx];
+            w[(size_t)i * ld + j] = symmetric ? __dmul_rn(0.5, __dadd_rn(a, tb[tx][r])) : a;
+        }
+        if (bi != bj) {
+            const int i2 = bj * SYM_T + r, j2 = bi * SYM_T + tx;
+            if (i2 < n && j2 < n) {
+                const double b = tb[r][tx];
+                w[(size_t)i2 * ld + j2] = symmetric ? __dmul_rn(0.5, __dadd_rn(b, ta[tx][r])) : b;
+            }
+        }
+    }
+}
+
+// flag <- 1 if W_ij != W_ji anywhere (exact comparison)
+__global__ void asymmetry_kernel(const double* __restrict__ w, int n, int ld, int32_t* flag) {
+    __shared__ double t[SYM_T][SYM_T + 1];
+    const int bi = blockIdx.y, bj = blockIdx.x, tx = threadIdx.x, ty = threadIdx.y;
+    if (bj < bi) return;
+    for (int r = ty; r < SYM_T; r += blockDim.y) {
+        const int i = bj * SYM_T + r, j = bi * SYM_T + tx;
+        t[r][tx] = (i < n && j < n) ? w[(size_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < SYM_T; r += blockDim.y) {
+        const int i = bi * SYM_T + r, j = bj * SYM_T + tx;
+        if (i < n && j < n && w[(size_t)i * ld + j] != t[tx][r]) *flag = 1;
+    }
+}
+
+// WT <- W^T (kept resident when W is not symmetric: a flip of unit k needs column k)
+__global__ void transpose_kernel(const double* __restrict__ w, double* __restrict__ wt, int n, int ld) {
+    __shared__ double t[SYM_T][SYM_T + 1];
+    const int bi = blockIdx.y, bj = blockIdx.x, tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < SYM_T; r += blockDim.y) {
+        const int i = bi * SYM_T + r, j = bj * SYM_T + tx;
+        t[r][tx] = (i < n && j < n) ? w[(size_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < SYM_T; r += blockDim.y) {
+        const int i = bj * SYM_T + r, j = bi * SYM_T + tx;
+        if (i < n && j < n) wt[(size_t)i * ld + j] = t[tx][r];
+    }
+}
+
+// ---- Frobenius norm: deterministic two-pass reduction -----------------------
+constexpr int RED_THREADS = 256;
+__device__ __forceinline__ double block_reduce_sum_det(double v, double* sm) {
+    // fixed-order tree: identical result for identical launch geometry
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) for (int w = 0; w < (int)blockDim.x / 32; w++) r += sm[w];
+    __syncthreads();
+    return r;  // valid in thread 0
+}
+__global__ void sumsq_partial_kernel(const double* __restrict__ w, int n, int ld, double* __restrict__ partial) {
+    __shared__ double sm[RED_THREADS / 32];
+    double acc = 0.0;
+    const int64_t total = (int64_t)n * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = w[i];  // padding columns are zero
+        acc = fma(x, x, acc);
+    }
+    const double r = block_reduce_sum_det(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+// out[0] = sqrt(sum partial), out[1] = 1/out[0]
+__global__ void sumsq_final_kernel(const double* __restrict__ partial, int np, double* __restrict__ out) {
+    __shared__ double sm[RED_THREADS / 32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc += partial[i];
+    const double r = block_reduce_sum_det(acc, sm);
+    if (threadIdx.x == 0) { const double nrm = sqrt(r); out[0] = nrm; out[1] = 1.0 / nrm; }
+}
+// W <- fl(f * W), f = 1/||W||_F  (matrix.Scale(1/matrix.Norm(2), matrix), HopfieldNetwork.go:260)
+__global__ void scale_kernel(double* __restrict__ w, int n, int ld, const double* __restrict__ f) {
+    const double s = f[1];
+    const int64_t total = (int64_t)n * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x)
+        w[i] = __dmul_rn(s, w[i]);
+}
+
+// max_i sum_k |W_ik|  (the R of the decision margin); one CTA per row, atomicMax on the bits
+__global__ void rowabs_max_kernel(const double* __restrict__ w, int n, int ld, unsigned long long* out) {
+    __shared__ double sm[RED_THREADS / 32];
+    const double* row = w + (size_t)blockIdx.x * ld;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) acc += fabs(row[j]);
+    const double r = block_reduce_sum_det(acc, sm);
+    if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(r));
+}
+
+// ---- inverse permutations: inv[row][perm[row][i]] = i -----------------------
+__global__ void invert_perm_kernel(const uint16_t* __restrict__ perm, uint16_t* __restrict__ inv, int n,
+                                   int ldp, int rows) {
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x)
+        inv[(size_t)r * ldp + perm[(size_t)r * ldp + i]] = (uint16_t)i;
+}
+
+// ---- bit-matrix transpose: X[P][words] (state-major) -> XT[N][pwords] (unit-major)
+__global__ void transpose_bits_kernel(const uint64_t* __restrict__ x, uint64_t* __restrict__ xt, int n,
+                                      int words, int p, int pwords) {
+    const int64_t total = (int64_t)n * pwords;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+         o += (int64_t)gridDim.x * blockDim.x) {
+        const int unit = (int)(o / pwords), q = (int)(o % pwords);
+        uint64_t out = 0;
+        const int m0 = q * 64;
+        for (int b = 0; b < 64 && m0 + b < p; b++)
+            out |= ((x[(size_t)(m0 + b) * words + (unit >> 6)] >> (unit & 63)) & 1ULL) << b;
+        xt[o] = out;
+    }
+}
+
+// ---- energy profile epilogue (AllUnitEnergies / StateIsStable / StateEnergy) ----
+// BipolarDomainManager.go:39-55, BinaryDomainManager.go:54-72, HopfieldNetwork.go:214-225.
+// H holds the fields from the GEMM; e = -0.5 * (h * v), v = s (bipolar) or 2s-1 (binary).
+// A unit whose |h| is inside the margin is re-evaluated in the reference's order.
+// One CTA per state.
+__global__ void __launch_bounds__(RED_THREADS)
+energy_epilogue_kernel(const double* __restrict__ H, int ldh, const uint64_t* __restrict__ states, int words,
+                       const double* __restrict__ W, int ldw, int n, int domain, double tau,
+                       int max_unstable, double* __restrict__ energies, int32_t* __restrict__ unstable,
+                       uint8_t* __restrict__ stable, double* __restrict__ state_energy,
+                       int32_t* __restrict__ margin_hits) {
+    __shared__ double sm[RED_THREADS / 32];
+    __shared__ int s_cnt, s_margin;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(states + (size_t)s * words);
+    if (tid == 0) { s_cnt = 0; s_margin = 0; }
+    __syncthreads();
+    double esum = 0.0;
+    int cnt = 0;
+    // pass 1: units outside the margin, strided
+    for (int i = tid; i < n; i += RED_THREADS) {
+        const double h = H[(size_t)s * ldh + i];
+        const uint32_t b = (bits[i >> 5] >> (i & 31)) & 1u;
+        if (!(fabs(h) < tau)) {
+            const double v = b ? 1.0 : -1.0;
+            const double e = -0.5 * (h * v);
+            if (energies) energies[(size_t)s * n + i] = e;
+            esum += e;
+            if (e > 0.0) cnt++;
+        }
+    }
+    // pass 2: units inside the margin, one warp per unit, exact order
+    int mcount = 0;
+    for (int i0 = warp; i0 < n; i0 += RED_THREADS / 32) {
+        // warp-uniform test
+        const double h = H[(size_t)s * ldh + i0];
+        if (fabs(h) < tau) {
+            const double hx = exact_field_warp(W + (size_t)i0 * ldw, bits, n, domain, lane);
+            if (lane == 0) {
+                const uint32_t b = (bits[i0 >> 5] >> (i0 & 31)) & 1u;
+                const double v = b ? 1.0 : -1.0;
+                const double e = -0.5 * (hx * v);
+                if (energies) energies[(size_t)s * n + i0] = e;
+                esum += e;
+                if (e > 0.0) cnt++;
+                mcount++;
+            }
+        }
+    }
+    atomicAdd(&s_cnt, cnt);
+    atomicAdd(&s_margin, mcount);
+    const double r = block_reduce_sum_det(esum, sm);
+    __syncthreads();
+    if (tid == 0) {
+        if (unstable) unstable[s] = s_cnt;
+        if (stable) stable[s] = (uint8_t)(s_cnt <= max_unstable);
+        if (state_energy) state_energy[s] = r;
+        if (margin_hits) margin_hits[s] = s_margin;
+    }
+}
+
+// ---- unique-attractor table (datacollector/UniqueRelaxedStateHandler.go:41-73) ----
+// key: sign-canonical packed final state (== identical energy profile, the
+// reference's key); 128-bit hash picks the bucket, the full state decides equality.
+__device__ __forceinline__ bool same_canonical(const uint64_t* a, const uint64_t* b, int words, int n,
+                                               int domain) {
+    const bool ia = domain == HN_DOMAIN_BIPOLAR && (a[0] & 1ULL);
+    const bool ib = domain == HN_DOMAIN_BIPOLAR && (b[0] & 1ULL);
+    for (int w = 0; w < words; w++) {
+        uint64_t x = a[w], y = b[w];
+        uint64_t mask = ~0ULL;
+        if (w == words - 1 && (n & 63)) mask = (1ULL << (n & 63)) - 1ULL;
+        if (ia) x = ~x & mask;
+        if (ib) y = ~y & mask;
+        if (x != y) return false;
+    }
+    return true;
+}
+// table[slot] = representative probe index or -1. rep[p] = representative of p.
+__global__ void dedup_insert_kernel(const uint64_t* __restrict__ finals, const uint64_t* __restrict__ hash,
+                                    int B, int words, int n, int domain, int32_t* table, int cap_mask,
+                                    int32_t* __restrict__ rep) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    uint32_t slot = (uint32_t)(hash[(size_t)p * 2] ^ (hash[(size_t)p * 2 + 1] >> 17)) & cap_mask;
+    for (;;) {
+        int32_t cur = atomicCAS(&table[slot], -1, p);
+        if (cur == -1) { rep[p] = p; return; }
+        if (hash[(size_t)cur * 2] == hash[(size_t)p * 2] && hash[(size_t)cur * 2 + 1] == hash[(size_t)p * 2 + 1] &&
+            same_canonical(finals + (size_t)cur * words, finals + (size_t)p * words, words, n, domain)) {
+            rep[p] = cur;
+            return;
+        }
+        slot = (slot + 1) & cap_mask;
+    }
+}
+// first[rep] = min member index, hits[rep] = #members
+__global__ void dedup_count_kernel(const int32_t* __restrict__ rep, int B, int32_t* first, int32_t* hits) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const int r = rep[p];
+    atomicMin(&first[r], p);
+    atomicAdd(&hits[r], 1);
+}
+// flag[p] = 1 iff p is the first-seen member of its group
+__global__ void dedup_flag_kernel(const int32_t* __restrict__ rep, const int32_t* __restrict__ first, int B,
+                                  int32_t* __restrict__ flag) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    flag[p] = (first[rep[p]] == p) ? 1 : 0;
+}
+// single-CTA exclusive scan of flag -> rank (first-seen order == ascending first index)
+__global__ void __launch_bounds__(1024) scan_flags_kernel(const int32_t* __restrict__ flag, int B,
+                                                         int32_t* __restrict__ rank, int32_t* __restrict__ total) {
+    __shared__ int32_t warp_sums[32];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < B; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int32_t v = i < B ? flag[i] : 0;
+        int32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int32_t s = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += y; }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int32_t prefix = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + x - v;
+        if (i < B) rank[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+// attractor_id[p] = rank[first[rep[p]]]; table rows in first-seen order
+__global__ void dedup_finalize_kernel(const int32_t* __restrict__ rep, const int32_t* __restrict__ first,
+                                      const int32_t* __restrict__ hits, const int32_t* __restrict__ rank, int B,
+                                      int32_t* __restrict__ attractor_id, int32_t* __restrict__ ufirst,
+                                      int32_t* __restrict__ uhits) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const int r = rep[p];
+    const int f = first[r];
+    const int id = rank[f];
+    attractor_id[p] = id;
+    if (f == p) { ufirst[id] = f; uhits[id] = hits[r]; }
+}
+
+// ---- f64 -> packed with activation (x <= 0 -> 0 bit) -------------------------
+__global__ void pack_f64_kernel(const double* __restrict__ x, uint64_t* __restrict__ out, int n, int words,
+                                int count) {
+    const int64_t total = (int64_t)count * words;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+         o += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(o / words), w = (int)(o % words);
+        uint64_t v = 0;
+        for (int b = 0; b < 64 && w * 64 + b < n; b++)
+            if (x[(size_t)s * n + w * 64 + b] > 0.0) v |= 1ULL << b;
+        out[o] = v;
+    }
+}
+
+}  // namespace hn

@@ -1,0 +1,312 @@
+/*
+ * hopfield_b200.h — C ABI of libhopfield_b200.so
+ *
+ * The drop-in boundary for the one data-parallel hot path of
+ * hmcalister/Hopfield-Network-Go: batched relaxation of probe states, the
+ * per-state energy profile + stability check, and the Hebbian / Delta
+ * learning-rule weight updates, implemented as hand-written sm_100a CUDA.
+ *
+ * The reference has no FFI seam today (pure Go calling gonum); the seam this
+ * header introduces sits directly underneath the exported Go API of the
+ * `hopfieldnetwork` package.  Each entry point below cites the reference
+ * function (file:line under the reference tree) whose body it replaces; the
+ * cgo binding a maintainer would add is shown in INTEGRATION.md and in
+ * hopfield_network_go_b200/go/.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only, no C++/torch types.
+ *  - every function returns an int status: HN_OK (0) or a negative HN_E_*.
+ *    hn_last_error() returns a human readable message for the last failure.
+ *  - the caller owns every host buffer; the library copies in/out during the
+ *    call and never retains a host pointer after returning (cgo rule).
+ *  - there is NO CPU fallback: hn_create fails with HN_E_NO_DEVICE when no
+ *    sm_100 device is usable.
+ *  - a handle is single-caller (thread-compatible, not thread-safe).
+ *
+ * State formats
+ *  - "packed": one bit per unit, 64 units per little-endian uint64 word,
+ *    unit j of a state lives in bit (j % 64) of word (j / 64); a state is
+ *    hn_words(N) = ceil(N/64) words; padding bits must be 0.
+ *    bit 1 <-> +1 (bipolar) or 1 (binary); bit 0 <-> -1 (bipolar) or 0 (binary).
+ *    This is exactly the image of the reference activation function
+ *    (domain/BipolarDomainManager.go:16-22, domain/BinaryDomainManager.go:29-35):
+ *    x <= 0 -> low value, else high value.
+ *  - "f64": row-major float64, N per state, as in gonum mat.VecDense; on input
+ *    the activation function is applied (that is what the reference does
+ *    before any use of a state: HopfieldNetwork.go:255-257, states/StateGenerator.go:50).
+ *
+ * Randomness
+ *  The reference draws unit-update orders and learning noise from a
+ *  time-seeded RNG (HopfieldNetworkBuilder.go:231-232).  Here every RNG-derived
+ *  quantity is an explicit INPUT generated host-side (permutation pools,
+ *  noised target copies), so trajectories are reproducible.  hn_rng_* below is
+ *  a host-side restatement of the reference's generator (golang.org/x/exp/rand
+ *  PCG source + Shuffle/Float64/NormFloat64) for hosts that are not Go.
+ */
+#ifndef HOPFIELD_B200_H
+#define HOPFIELD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HN_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define HN_OK              0
+#define HN_E_INVALID      -1  /* bad argument / configuration              */
+#define HN_E_NO_DEVICE    -2  /* no usable sm_100 CUDA device              */
+#define HN_E_CUDA         -3  /* CUDA runtime error                        */
+#define HN_E_OOM          -4  /* device or host allocation failed          */
+#define HN_E_POOL         -5  /* permutation pool exhausted                */
+#define HN_E_NCCL         -6  /* NCCL error / NCCL not loadable            */
+#define HN_E_STATE        -7  /* call not valid in the handle's state      */
+
+/* ---- enums: numeric values equal the reference's iota values ----------- */
+/* domain/DomainEnum.go:6-9 */
+#define HN_DOMAIN_BIPOLAR 0
+#define HN_DOMAIN_BINARY  1
+/* LearningRule.go:32-39 */
+#define HN_RULE_HEBBIAN                      0
+#define HN_RULE_BIPOLAR_MAPPED_HEBBIAN       1
+#define HN_RULE_DELTA                        2
+#define HN_RULE_BIPOLAR_MAPPED_DELTA         3
+#define HN_RULE_THERMAL_DELTA                4  /* not implemented on device */
+#define HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA 5  /* not implemented on device */
+/* LearningMethod.go:22-25 */
+#define HN_METHOD_FULL_SET        0
+#define HN_METHOD_ITERATIVE_BATCH 1
+/* noiseapplication/NoiseApplication.go:24-36 */
+#define HN_NOISE_NONE                        0
+#define HN_NOISE_MAXIMAL_INVERSION           1
+#define HN_NOISE_RANDOM_SUBMAXIMAL_INVERSION 2
+#define HN_NOISE_GAUSSIAN                    3
+
+/* ---- configuration: mirrors the HopfieldNetworkBuilder fields ----------
+ * (HopfieldNetworkBuilder.go:16-34; defaults :40-55; Build checks :214-229) */
+typedef struct hn_config {
+    int32_t dimension;                 /* SetNetworkDimension; must be 1..65535              */
+    int32_t domain;                    /* SetNetworkDomain; HN_DOMAIN_*                       */
+    int32_t force_symmetric;           /* SetForceSymmetric (default 1)                       */
+    int32_t force_zero_diagonal;       /* SetForceZeroDiagonal (default 1)                    */
+    int32_t max_relax_unstable_units;  /* SetMaximumRelaxationUnstableUnits (default 0)       */
+    int32_t max_relax_iterations;      /* SetMaximumRelaxationIterations (default 100)        */
+    double  learning_rate;             /* SetLearningRate (default 1.0)                       */
+    int32_t device;                    /* CUDA device ordinal (additive extension)            */
+    int32_t reserved;
+} hn_config;
+
+typedef struct hn_handle_s* hn_handle;
+
+/* Words per packed state. */
+static inline int32_t hn_words(int32_t dimension) { return (dimension + 63) / 64; }
+
+/* Fill `cfg` with the builder defaults (HopfieldNetworkBuilder.go:40-55). */
+void hn_default_config(hn_config* cfg);
+
+int  hn_abi_version(void);
+
+/* Message for the most recent failing call on this thread ("" if none). */
+const char* hn_last_error(void);
+
+/* ---- lifetime ----------------------------------------------------------
+ * Replaces HopfieldNetworkBuilder.Build (HopfieldNetworkBuilder.go:214-279):
+ * allocates the zero N x N float64 weight matrix resident in HBM.  Random
+ * Gaussian init (:235-246) is done by the host through hn_set_weights. */
+int hn_create(const hn_config* cfg, hn_handle* out);
+int hn_destroy(hn_handle h);
+
+/* ---- weights -----------------------------------------------------------
+ * GetMatrix (HopfieldNetwork.go:93-95) hands out the live gonum matrix; with
+ * W resident in HBM the binding copies.  Row-major float64, N*N.            */
+int hn_set_weights(hn_handle h, const double* w_host);
+int hn_get_weights(hn_handle h, double* w_host);
+
+/* ---- target (learned) states -------------------------------------------
+ * network.targetStates (HopfieldNetwork.go:43, appended at :258).  Distances
+ * in relaxation results are measured against this list (:411,:432).
+ * hn_learn_* append automatically; hn_set_targets replaces the list.        */
+int hn_set_targets(hn_handle h, const uint64_t* targets_packed, int32_t n_targets);
+int hn_num_targets(hn_handle h, int32_t* n_targets);
+int hn_get_targets(hn_handle h, uint64_t* targets_packed);
+
+/* ---- learning ----------------------------------------------------------
+ * One application of the Hebbian rule over `n` states
+ * (LearningRule.go:64-75): W += lr * sum_mu x x^T, then enforceConstraints
+ * (HopfieldNetwork.go:55-67).  Does NOT append to the target list and does
+ * NOT normalise; hn_learn_states does the whole LearnStates.                */
+int hn_hebbian_epoch(hn_handle h, const uint64_t* states_packed, int32_t n);
+
+/* One application of the Delta rule (LearningRule.go:90-114).
+ *   states_packed : the n target states t_mu
+ *   noised_packed : the n copies after learning noise + activation
+ *                   (LearningRule.go:99-102), generated host-side
+ *   perms         : n permutations of 0..N-1 (uint16), the fresh shuffled unit
+ *                   order UpdateState draws for each copy (HopfieldNetwork.go:281-282)
+ *   relaxed_out   : optional (may be NULL) n packed states after the one sweep
+ * Device work: fields of the noised copies (FP64 tensor-core GEMM), one
+ * asynchronous sweep per copy, dW = sum_mu 0.5 (t - r) t^T (GEMM),
+ * [NCCL allreduce of dW when a communicator is attached], W += lr dW,
+ * enforceConstraints.                                                       */
+int hn_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* noised_packed,
+                   const uint16_t* perms, int32_t n, uint64_t* relaxed_out);
+
+/* enforceConstraints (HopfieldNetwork.go:55-67) on the resident W. */
+int hn_enforce_constraints(hn_handle h);
+
+/* W <- W * (1 / ||W||_F)  (HopfieldNetwork.go:260; gonum Norm(2) of a matrix
+ * is the Frobenius norm).  Returns the norm that was divided out.           */
+int hn_normalize_frobenius(hn_handle h, double* norm_out);
+
+/* Per-state diagnostics used by the learning methods (LearningMethod.go:45-58)
+ * and by main.go:191-204:  AllUnitEnergies (HopfieldNetwork.go:198-200 ->
+ * domain/BipolarDomainManager.go:39-46, BinaryDomainManager.go:54-63),
+ * StateIsStable (:214-225), StateEnergy (:171-173).
+ *   energies_out   : optional [n][N] float64
+ *   unstable_out   : optional [n] int32, #units with energy > 0
+ *   stable_out     : optional [n] uint8, unstable <= max_relax_unstable_units
+ *   state_energy_out: optional [n] float64                                   */
+int hn_energy_profiles(hn_handle h, const uint64_t* states_packed, int32_t n,
+                       double* energies_out, int32_t* unstable_out, uint8_t* stable_out,
+                       double* state_energy_out);
+
+/* Whole LearnStates (HopfieldNetwork.go:254-262) with the learning-method
+ * loop of LearningMethod.go:38-89 run by the library, drawing noise and
+ * permutations from `rng` (see hn_rng_*) in the reference's draw order.
+ *   learn_epoch_out / learn_index_out / learn_stable_out : optional arrays of
+ *     capacity `learn_cap` receiving one LearnStateData row each
+ *     (datacollector/LearnStateData.go:14-19) ; learn_energy_out optional
+ *     [learn_cap][N].  *n_learn_rows receives the number of rows produced
+ *     (rows beyond learn_cap are counted but not stored).
+ * Appends `states` to the target list and normalises W.                      */
+struct hn_rng_s;
+typedef struct hn_rng_s* hn_rng;
+int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n,
+                    int32_t rule, int32_t method, int32_t epochs,
+                    int32_t noise_method, double noise_scale, hn_rng rng,
+                    int32_t learn_cap, int32_t* learn_epoch_out, int32_t* learn_index_out,
+                    uint8_t* learn_stable_out, double* learn_energy_out,
+                    int32_t* n_learn_rows);
+
+/* ---- relaxation --------------------------------------------------------
+ * flags for hn_relax_batch */
+#define HN_RELAX_SERIAL_STREAM 0x1  /* emulate threads=1: probe p starts at pool row
+                                       K_p = sum_{q<p} sweeps(q); offsets ignored */
+#define HN_RELAX_DEDUP         0x2  /* fill attractor ids + unique table                 */
+#define HN_RELAX_HISTORY       0x4  /* capture per-step packed state history             */
+
+typedef struct hn_relax_out {
+    /* all pointers are host buffers owned by the caller; any may be NULL */
+    uint64_t* final_states;   /* [B][hn_words(N)] packed final state (StateHistory last, main.go:232) */
+    int32_t*  num_steps;      /* [B] NumSteps = len(StateHistory) (main.go:231)                      */
+    uint8_t*  stable;         /* [B] RelaxationResult.Stable                                         */
+    int32_t*  distances;      /* [B][P] Manhattan-with-inversion distance to every target
+                                 (distancemeasure/DistanceMeasure.go:28-42); exact small integers   */
+    double*   energies;       /* [B][N] EnergyProfile of the final state (main.go:234)               */
+    int32_t*  flips;          /* [B] counter: units flipped                                          */
+    int32_t*  margin_hits;    /* [B] counter: decisions taken by exact-order recomputation because
+                                 |h| fell below the margin tau                                       */
+    /* unique-attractor table (datacollector/UniqueRelaxedStateHandler.go:41-73), HN_RELAX_DEDUP */
+    int32_t*  attractor_id;   /* [B] index into the unique table                                     */
+    int32_t*  unique_first;   /* [unique_cap] StateIndex of first occurrence, in first-seen order    */
+    int32_t*  unique_hits;    /* [unique_cap] Hits                                                   */
+    int32_t   unique_cap;
+    int32_t   n_unique;       /* out */
+    /* history (HN_RELAX_HISTORY): packed state after every step incl. step 0 */
+    uint64_t* history;        /* [B][max_relax_iterations+1][hn_words(N)]                            */
+    /* totals (out) */
+    int64_t   total_flips;
+    int64_t   total_sweeps;
+    int64_t   total_margin_hits;
+    double    device_ms;      /* device time of the relaxation kernels, CUDA events                 */
+} hn_relax_out;
+
+/* ConcurrentRelaxStates / RelaxState (HopfieldNetwork.go:302-359, 371-442,
+ * 461-490): relax B probe states until stable or max_relax_iterations sweeps.
+ *   probes_packed : [B][hn_words(N)]
+ *   perm_pool     : [n_pool][N] uint16; row r is the unit visiting order of one
+ *                   sweep (the state of the reference's shuffled unitIndices
+ *                   list, HopfieldNetwork.go:374,393)
+ *   offsets       : [B] or NULL(=all 0); probe p uses pool rows offsets[p]+t
+ *                   for sweep t = 0,1,...                                      */
+int hn_relax_batch(hn_handle h, const uint64_t* probes_packed, int32_t n_probes,
+                   const uint16_t* perm_pool, int32_t n_pool, const int32_t* offsets,
+                   uint32_t flags, hn_relax_out* out);
+
+/* UpdateState (HopfieldNetwork.go:280-291): one sweep per state in the given
+ * fresh order, no stability test; states updated in place.                   */
+int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint16_t* perms);
+
+/* ---- device-resident bulk path (throughput / benchmarking) -------------
+ * Upload once, relax many times without host traffic; see bench.py.          */
+int hn_upload_perm_pool(hn_handle h, const uint16_t* perm_pool, int32_t n_pool);
+int hn_upload_probes(hn_handle h, const uint64_t* probes_packed, int32_t n_probes);
+/* Relax the uploaded probes with the uploaded pool (offsets all 0). Results
+ * stay on the device; *device_ms gets the CUDA-event time of the whole call. */
+int hn_relax_resident(hn_handle h, uint32_t flags, double* device_ms);
+int hn_download_results(hn_handle h, hn_relax_out* out);
+
+/* Timing breakdown of the last relaxation (CUDA events, ms) and kernel count */
+typedef struct hn_relax_timing {
+    double fields_ms;   /* initial fields GEMM  */
+    double relax_ms;    /* relaxation kernel    */
+    double post_ms;     /* energies / dedup     */
+    int32_t launches;   /* kernels launched     */
+    int32_t reserved;
+} hn_relax_timing;
+int hn_last_relax_timing(hn_handle h, hn_relax_timing* t);
+
+/* Decision margin tau = tau_base + tau_per_flip * flips currently in force
+ * (DESIGN.md "margin").                                                      */
+int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip);
+
+/* ---- conversions -------------------------------------------------------
+ * f64 rows -> packed with the domain activation function applied. Host-side
+ * helpers for hosts that hold gonum-style float64 state vectors.             */
+int hn_pack_states_f64(int32_t dimension, int32_t n, const double* states_f64, uint64_t* packed);
+int hn_unpack_states_f64(int32_t dimension, int32_t domain, int32_t n, const uint64_t* packed,
+                         double* states_f64);
+
+/* ---- multi-GPU (targets sharded for learning) --------------------------
+ * One handle per GPU.  When a communicator is attached, hn_hebbian_epoch /
+ * hn_delta_epoch treat their `states` as this rank's shard and allreduce dW
+ * (ncclAllReduce, sum, float64, N*N) before the update, so every replica of W
+ * stays bitwise identical (dW is integer valued: order independent).
+ * NCCL is dlopen()ed on first use.                                           */
+#define HN_NCCL_UNIQUE_ID_BYTES 128
+int hn_comm_unique_id(uint8_t id[HN_NCCL_UNIQUE_ID_BYTES]);
+int hn_comm_attach(hn_handle h, const uint8_t id[HN_NCCL_UNIQUE_ID_BYTES], int32_t rank, int32_t n_ranks);
+int hn_comm_detach(hn_handle h);
+/* broadcast W from `root` to all ranks of the attached communicator */
+int hn_broadcast_weights(hn_handle h, int32_t root);
+
+/* ---- host-side RNG: restatement of golang.org/x/exp/rand ----------------
+ * (module golang.org/x/exp @ 642cacee5cc0, go.mod:12 — source absent from the
+ * reference tree; algorithm restated from the published PCG XSL-RR 128/64
+ * generator and the package's documented Shuffle/Float64/NormFloat64.)        */
+int      hn_rng_create(uint64_t seed, hn_rng* out);        /* rand.New(rand.NewSource(seed)) */
+int      hn_rng_destroy(hn_rng r);
+uint64_t hn_rng_uint64(hn_rng r);                          /* Rand.Uint64   */
+uint64_t hn_rng_uint64n(hn_rng r, uint64_t n);             /* Rand.Uint64n  */
+double   hn_rng_float64(hn_rng r);                         /* Rand.Float64  */
+double   hn_rng_norm_float64(hn_rng r);                    /* Rand.NormFloat64 */
+/* hopfieldutils.ShuffleList (hopfieldutils/HopfieldUtils.go:35-39) on a uint16 list */
+int      hn_rng_shuffle_u16(hn_rng r, uint16_t* list, int32_t n);
+/* n_rows successive in-place shuffles of one persistent list that starts as
+ * `list_io` (identity when start_identity != 0); row r of pool = list after
+ * shuffle r+1.  This is the stream of orders one relaxation goroutine sees
+ * (HopfieldNetwork.go:374,393).                                              */
+int      hn_rng_perm_pool(hn_rng r, int32_t dimension, int32_t n_rows, int32_t start_identity,
+                          uint16_t* list_io, uint16_t* pool_out);
+/* learning noise on one f64 state copy, in place, drawing from r exactly as
+ * noiseapplication/NoiseApplication.go:51-105 does.                          */
+int      hn_rng_apply_noise(hn_rng r, int32_t noise_method, double noise_scale,
+                            double* state_f64, int32_t dimension);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOPFIELD_B200_H */

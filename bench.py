@@ -163,12 +163,14 @@ def main():
         net.relax_resident(dedup=True)
     barrier()
     sampler.start()
-    dev_ms, relax_ms, launches = [], [], 0
+    dev_ms, relax_ms, fields_ms, post_ms, launches = [], [], [], [], 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         dev_ms.append(net.relax_resident(dedup=True))
         t = net.last_timing()
         relax_ms.append(t.relax_ms)
+        fields_ms.append(t.fields_ms)
+        post_ms.append(t.post_ms)
         launches += t.launches
     barrier()
     wall = time.perf_counter() - t0
@@ -218,6 +220,8 @@ def main():
                              "algorithmic_bytes_per_launch": int(alg_bytes), "flips_per_probe": flips / b,
                              "sweeps_per_probe": sweeps / b},
                 "clocks": sampler.summary(), "wall_s": wall,
+                "stage_ms_per_step": {"fields_gemm": float(np.mean(fields_ms)), "relax": float(np.mean(relax_ms)),
+                                      "dedup": float(np.mean(post_ms))},
                 "margin_hits_per_probe": out.total_margin_hits / b, "unique_attractors": int(out.n_unique)}
         if not args.no_cpu:
             from oracle import orc

@@ -170,8 +170,7 @@ int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H,
 template <int UPT>
 int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
     auto kern = relax_kernel<UPT>;
-    const int nbw = (h->N + 31) / 32;
-    const size_t smem = (size_t)((nbw + 3) / 4 * 4) * 4 + (size_t)h->ldp * 2;
+    const size_t smem = relax_smem_bytes(h->N, h->ldp, UPT);
     HN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     HN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RELAX_THREADS, smem));

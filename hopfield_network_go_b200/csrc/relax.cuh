@@ -103,18 +103,38 @@ constexpr int RELAX_THREADS = 256;
 constexpr int RELAX_WARPS = RELAX_THREADS / 32;
 constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
 
-// dynamic shared memory layout: [state bits: ldbits uint32][perm row: ldp uint16]
+// Dynamic shared memory layout (see relax_smem_bytes):
+//   s_bits  [nbw, padded to 4]      uint32  master copy of the packed state (exact path, outputs)
+//   s_perm  [ldp]                   uint16  this sweep's visiting order
+//   s_a     [2][THREADS*UPT]        int32   double-buffered per-unit "aligned hi word":
+//           a_u = (hi32(h_u) ^ (bit_u ? 0 : 0x80000000)) & ~1 | bit_u.  As a signed integer a_u < T
+//           (T = hi32(tau)+2) iff the aligned field h_u*v_u is below tau, i.e. the unit wants to flip
+//           or sits inside the margin; the low bit carries the unit's current bit.
+//
+// Per flip: every thread updates its UPT fields in registers (one coalesced pass over the column),
+// rewrites its slice of the shadow, ONE __syncthreads, then every warp redundantly scans the sweep
+// order from the current position with ballots to find the next unit that may flip.
+template <int UPT> struct RelaxCfg {
+    static constexpr int VEC = UPT >= 4 ? 4 : UPT;   // contiguous units per ownership chunk
+    static constexpr int NCH = UPT / VEC;            // chunks per thread
+};
+static inline size_t relax_smem_bytes(int N, int ldp, int upt) {
+    const int nbw = (N + 31) / 32;
+    return (size_t)((nbw + 3) / 4 * 4) * 4 + (size_t)((ldp + 7) / 8 * 8) * 2 + (size_t)2 * RELAX_THREADS * upt * 4;
+}
+
 template <int UPT>
-__global__ void __launch_bounds__(RELAX_THREADS)
+__global__ void __launch_bounds__(RELAX_THREADS, (UPT <= 16 ? 3 : 1))
 relax_kernel(RelaxParams p) {
-    constexpr int VEC = (UPT >= 2) ? 2 : 1;  // units per vector load
-    constexpr int NV = UPT / VEC;            // vector loads per thread per column
-    using mask_t = typename std::conditional<(UPT > 32), uint64_t, uint32_t>::type;
+    constexpr int VEC = RelaxCfg<UPT>::VEC;
+    constexpr int NCH = RelaxCfg<UPT>::NCH;
+    constexpr int NU = RELAX_THREADS * UPT;  // padded unit count
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nbw = (p.N + 31) / 32;         // 32-bit state words
+    const int nbw = (p.N + 31) / 32;
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);
     uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem_raw + (size_t)((nbw + 3) / 4 * 4) * 4);
-    __shared__ uint32_t s_red[2][RELAX_WARPS];
+    int* s_a = reinterpret_cast<int*>(smem_raw + (size_t)((nbw + 3) / 4 * 4) * 4 + (size_t)((p.ldp + 7) / 8 * 8) * 2);
+    __shared__ __align__(16) uint32_t s_red[2][RELAX_WARPS];
     __shared__ double s_exact[4];
     __shared__ int s_probe;
     __shared__ long long s_rowbase;
@@ -122,19 +142,21 @@ relax_kernel(RelaxParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N;
     const double dscale = p.domain == HN_DOMAIN_BINARY ? 1.0 : 2.0;
+    // constant margin for the whole relaxation: tau(flips) at its largest possible flip count
+    const double tau = p.tau_base + p.tau_flip * ((double)p.max_iter * (double)N);
+    const int T = __double2hiint(tau) + 2;
     int red_buf = 0;
 
-    auto unit_of = [&](int v, int e) -> int { return (v * RELAX_THREADS + tid) * VEC + e; };
+    auto unit_of = [&](int c, int e) -> int { return (c * RELAX_THREADS + tid) * VEC + e; };
 
     auto block_min = [&](uint32_t x) -> uint32_t {
         x = __reduce_min_sync(0xFFFFFFFFu, x);
         if (lane == 0) s_red[red_buf][warp] = x;
         __syncthreads();
-        uint32_t m = s_red[red_buf][0];
-#pragma unroll
-        for (int w = 1; w < RELAX_WARPS; w++) m = min(m, s_red[red_buf][w]);
+        const uint4 a = *reinterpret_cast<const uint4*>(&s_red[red_buf][0]);
+        const uint4 b = *reinterpret_cast<const uint4*>(&s_red[red_buf][4]);
         red_buf ^= 1;
-        return m;
+        return min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
     };
     auto block_sum = [&](uint32_t x) -> uint32_t {
         x = __reduce_add_sync(0xFFFFFFFFu, x);
@@ -146,7 +168,6 @@ relax_kernel(RelaxParams p) {
         red_buf ^= 1;
         return m;
     };
-
     // exact re-evaluation of one field, block-uniform call; all threads get the value
     auto exact_field = [&](int k) -> double {
         __syncthreads();  // s_bits complete and visible
@@ -173,23 +194,41 @@ relax_kernel(RelaxParams p) {
         const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(p.probes + (size_t)pi * p.words);
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
-        double h[UPT];
-        mask_t sb = 0, valid = 0;
+        double h[UPT];     // true local fields of my units
+        int sw[UPT];       // per unit: bit31 = !bit (sign mask of v = -1), bit0 = bit
+        int abuf = 0;      // shadow buffer the next scan reads
 #pragma unroll
-        for (int v = 0; v < NV; v++) {
+        for (int c = 0; c < NCH; c++) {
 #pragma unroll
             for (int e = 0; e < VEC; e++) {
-                const int u = unit_of(v, e);
-                const int r = v * VEC + e;
+                const int u = unit_of(c, e), r = c * VEC + e;
                 if (u < N) {
-                    valid |= (mask_t)1 << r;
-                    sb |= (mask_t)((s_bits[u >> 5] >> (u & 31)) & 1u) << r;
+                    const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
+                    sw[r] = b ? 1 : (int)0x80000000;
                     h[r] = p.H0[(size_t)pi * p.ldh + u];
-                } else {
-                    h[r] = 0.0;
+                } else {  // padding: never visited by any order
+                    sw[r] = 1;
+                    h[r] = __longlong_as_double(0x7FF0000000000000LL);
                 }
             }
         }
+        auto write_shadow = [&](int buf) {
+            int* dst = s_a + (size_t)buf * NU;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                int a[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    const int r = c * VEC + e;
+                    a[e] = (__double2hiint(h[r]) & ~1) ^ sw[r];
+                }
+                int* q = dst + unit_of(c, 0);
+                if (VEC == 4) *reinterpret_cast<int4*>(q) = make_int4(a[0], a[1], a[2], a[3]);
+                else if (VEC == 2) *reinterpret_cast<int2*>(q) = make_int2(a[0], a[1]);
+                else q[0] = a[0];
+            }
+        };
+        write_shadow(abuf);
         if (p.history) {
             uint32_t* hw = reinterpret_cast<uint32_t*>(p.history + ((size_t)pi * (p.max_iter + 1)) * p.words);
             for (int w = tid; w < p.words * 2; w += RELAX_THREADS) hw[w] = w < nbw ? s_bits[w] : 0u;
@@ -199,70 +238,100 @@ relax_kernel(RelaxParams p) {
         for (int sweep = 0; sweep < p.max_iter; sweep++) {
             const long long row = rowbase + sweep;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
-            // positions of my units in this sweep's order; the order itself in smem
-            uint32_t posw[NV];  // VEC==2: two 16-bit positions per word
-            const uint16_t* invrow = p.inv_pool + (size_t)row * p.ldp;
             const uint16_t* permrow = p.perm_pool + (size_t)row * p.ldp;
-#pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const int u0 = unit_of(v, 0);
-                if (VEC == 2) posw[v] = (u0 < N) ? *reinterpret_cast<const uint32_t*>(invrow + u0) : 0u;
-                else posw[v] = (u0 < N) ? (uint32_t)invrow[u0] : 0u;
-            }
-            __syncthreads();  // previous users of s_perm are done
-            for (int i = tid; i < N; i += RELAX_THREADS) s_perm[i] = permrow[i];
+            __syncthreads();  // previous readers of s_perm are done; shadow writes visible
+            for (int i = tid; i < p.ldp / 2; i += RELAX_THREADS)
+                reinterpret_cast<uint32_t*>(s_perm)[i] = reinterpret_cast<const uint32_t*>(permrow)[i];
             __syncthreads();
 
-            int cur = -1;
+            int base = 0;  // next position of the sweep order to examine
             for (;;) {
-                const double tau = p.tau_base + p.tau_flip * (double)flips;
-                uint32_t best = RELAX_NONE;
-#pragma unroll
-                for (int r = 0; r < UPT; r++) {
-                    const double hv = h[r];
-                    const uint32_t nb = hv > 0.0 ? 1u : 0u;
-                    const uint32_t ob = (uint32_t)((sb >> r) & 1u);
-                    const uint32_t unc = fabs(hv) < tau ? 1u : 0u;
-                    const uint32_t ps = (VEC == 2) ? ((posw[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu) : posw[r];
-                    const bool cand = ((valid >> r) & 1u) && ((int)ps > cur) && (unc | (nb ^ ob));
-                    const uint32_t key = (ps << 3) | (unc << 2) | (ob << 1) | nb;
-                    if (cand) best = min(best, key);
+                // ---- scan ahead (every warp, redundantly): first position >= base whose unit has a < T ----
+                const int* sa = s_a + (size_t)abuf * NU;
+                int found = -1, fa = 0, fk = 0;
+                while (base < N) {
+                    const int p0 = base + lane, p1 = base + 32 + lane;
+                    int k0 = 0, k1 = 0, a0 = 0x7FFFFFFF, a1 = 0x7FFFFFFF;
+                    if (p0 < N) { k0 = s_perm[p0]; a0 = sa[k0]; }
+                    if (p1 < N) { k1 = s_perm[p1]; a1 = sa[k1]; }
+                    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, a0 < T);
+                    if (m0) {
+                        const int l = __ffs(m0) - 1;
+                        found = base + l; fa = __shfl_sync(0xFFFFFFFFu, a0, l); fk = __shfl_sync(0xFFFFFFFFu, k0, l);
+                        break;
+                    }
+                    const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, a1 < T);
+                    if (m1) {
+                        const int l = __ffs(m1) - 1;
+                        found = base + 32 + l; fa = __shfl_sync(0xFFFFFFFFu, a1, l); fk = __shfl_sync(0xFFFFFFFFu, k1, l);
+                        break;
+                    }
+                    base += 64;
                 }
-                best = block_min(best);
-                if (best == RELAX_NONE) break;
-                cur = (int)(best >> 3);
-                const int k = s_perm[cur];
-                uint32_t nb = best & 1u;
-                const uint32_t ob = (best >> 1) & 1u;
-                if (best & 4u) {
+                if (found < 0) break;  // sweep finished
+                base = found + 1;
+                const int k = fk;
+                const uint32_t ob = (uint32_t)fa & 1u;
+                uint32_t nb = ob ^ 1u;
+                if (((fa & 0x7FFFFFFF) | 1) < T) {  // inside the margin: decide exactly, in the reference's order
                     const double hx = exact_field(k);
                     margin++;
                     nb = hx > 0.0 ? 1u : 0u;
                 }
-                if (nb != ob) {
-                    const double d = nb ? dscale : -dscale;
-                    const double* col = p.Wcol + (size_t)k * p.ldw;
+                if (nb == ob) continue;  // exact decision: no flip; shadow unchanged, keep scanning
+
+                // ---- flip unit k: h += d * W[:,k] over my units; rewrite my slice of the other shadow ----
+                const double d = nb ? dscale : -dscale;
+                const double* col = p.Wcol + (size_t)k * p.ldw;
+                {   // owner: new bit into its sign word and the master state
+                    const int ch = k / VEC, ke = k % VEC;
+                    if ((ch % RELAX_THREADS) == tid) {
+                        const int rr = (ch / RELAX_THREADS) * VEC + ke;
 #pragma unroll
-                    for (int v = 0; v < NV; v++) {
-                        const int u0 = unit_of(v, 0);
-                        if (u0 < p.ldw) {
-                            if (VEC == 2) {
-                                const double2 w2 = __ldg(reinterpret_cast<const double2*>(col + u0));
-                                h[v * 2] = fma(d, w2.x, h[v * 2]);
-                                h[v * 2 + 1] = fma(d, w2.y, h[v * 2 + 1]);
-                            } else {
-                                h[v] = fma(d, __ldg(col + u0), h[v]);
-                            }
-                        }
-                    }
-                    // owner flips its register bit and the shared copy
-                    const int kv = k / VEC, ke = k % VEC;
-                    if ((kv % RELAX_THREADS) == tid) {
-                        sb ^= (mask_t)1 << ((kv / RELAX_THREADS) * VEC + ke);
+                        for (int r = 0; r < UPT; r++)
+                            if (r == rr) sw[r] ^= (int)0x80000001;
                         s_bits[k >> 5] ^= 1u << (k & 31);
                     }
-                    flips++;
                 }
+                abuf ^= 1;
+                int* dst = s_a + (size_t)abuf * NU;
+                auto flip_pass = [&](auto full_tag) {
+                    constexpr bool FULL = decltype(full_tag)::value;  // every chunk lies inside the padded row
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) {
+                        const int u0 = unit_of(c, 0);
+                        double w[VEC];
+                        if (FULL || u0 < p.ldw) {
+                            if (VEC == 4) {
+                                const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
+                                const double2 y = __ldg(reinterpret_cast<const double2*>(col + u0 + 2));
+                                w[0] = x.x; w[1] = x.y; w[2] = y.x; w[3] = y.y;
+                            } else if (VEC == 2) {
+                                const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
+                                w[0] = x.x; w[1] = x.y;
+                            } else {
+                                w[0] = __ldg(col + u0);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < VEC; e++) w[e] = 0.0;
+                        }
+                        int a[VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) {
+                            const int r = c * VEC + e;
+                            h[r] = fma(d, w[e], h[r]);
+                            a[e] = (__double2hiint(h[r]) & ~1) ^ sw[r];
+                        }
+                        int* q = dst + u0;
+                        if (VEC == 4) *reinterpret_cast<int4*>(q) = make_int4(a[0], a[1], a[2], a[3]);
+                        else if (VEC == 2) *reinterpret_cast<int2*>(q) = make_int2(a[0], a[1]);
+                        else q[0] = a[0];
+                    }
+                };
+                if (p.ldw == NU) flip_pass(std::true_type{}); else flip_pass(std::false_type{});
+                flips++;
+                __syncthreads();  // shadow[abuf] complete before anyone scans it
             }
             sweeps++;
 
@@ -273,33 +342,30 @@ relax_kernel(RelaxParams p) {
             }
             if (!p.check_stability) continue;
 
-            // ---- stability: #{i : e_i > 0}, e_i = -0.5 * (h_i * v_i) ----
-            const double tau = p.tau_base + p.tau_flip * (double)flips;
+            // ---- stability: #{i : e_i > 0}, e_i = -0.5 h_i v_i  (HopfieldNetwork.go:214-225) ----
             uint32_t cnt = 0;
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
-                const uint32_t ob = (uint32_t)((sb >> r) & 1u);
-                const bool ok = ((valid >> r) & 1u) && !(fabs(h[r]) < tau);
-                // v_i = +1 when the bit is set, -1 otherwise (Binary: 2s-1, same sign)
-                if (ok && (ob ? (h[r] < 0.0) : (h[r] > 0.0))) cnt++;
+                const int a = __double2hiint(h[r]) ^ (sw[r] & (int)0x80000000);
+                if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
             }
             cnt = block_sum(cnt);
             // units inside the margin: exact recomputation, in increasing unit index
             int last = -1;
             for (;;) {
-                uint32_t c = RELAX_NONE;
+                uint32_t cmin = RELAX_NONE;
 #pragma unroll
-                for (int v = 0; v < NV; v++) {
+                for (int c = 0; c < NCH; c++) {
 #pragma unroll
                     for (int e = 0; e < VEC; e++) {
-                        const int r = v * VEC + e;
-                        const int u = unit_of(v, e);
-                        if (((valid >> r) & 1u) && fabs(h[r]) < tau && u > last) c = min(c, (uint32_t)u);
+                        const int r = c * VEC + e;
+                        const int u = unit_of(c, e);
+                        if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T && u > last) cmin = min(cmin, (uint32_t)u);
                     }
                 }
-                c = block_min(c);
-                if (c == RELAX_NONE) break;
-                last = (int)c;
+                cmin = block_min(cmin);
+                if (cmin == RELAX_NONE) break;
+                last = (int)cmin;
                 const double hx = exact_field(last);
                 margin++;
                 const uint32_t ob = (s_bits[last >> 5] >> (last & 31)) & 1u;

@@ -1,0 +1,115 @@
+"""-m gpu: relaxation variants — binary domain, asymmetric W (resident W^T), random init (non-dyadic),
+history capture, maxUnstable > 0, already-stable probes, properties at BASELINE size."""
+import numpy as np
+import pytest
+
+from oracle import orc
+from tests.helpers import assert_relax_equal, gpu_net, make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def test_binary_domain(built):
+    onet, k2, pool, probes, targets = make_problem(192, 16, 96, 12, domain=1)
+    ores = onet.relax_batch(probes.copy(), pool, threads=8)
+    net = gpu_net(192, 1)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(targets))
+    res = net.relax_batch(probes, pool, dedup=True, want_energies=True)
+    assert_relax_equal(res, ores, 192)
+    assert np.allclose(res.EnergyProfiles, ores["energies"], rtol=1e-9, atol=1e-18)
+    aid, first, hits = orc.unique_table(ores["energies"])
+    assert np.array_equal(res.UniqueFirst, first) and np.array_equal(res.UniqueHits, hits)
+    net.close()
+
+
+def test_asymmetric_random_init_weights(built):
+    """forceSymmetric=false with Gaussian(0, 0.01) init + Hebbian: W is neither symmetric nor dyadic."""
+    n, p, b = 160, 14, 80
+    rng = orc.Rng(13)
+    t = rng.generate_states(0, n, p)
+    w0 = np.array([rng.norm_float64() * 0.01 for _ in range(n * n)]).reshape(n, n)
+    onet = orc.Net(n, force_symmetric=False, w=w0)
+    onet.hebbian(t)
+    onet.normalize()
+    onet.set_targets(t)
+    assert not np.array_equal(onet.w, onet.w.T)
+    probes = rng.generate_states(0, n, b)
+    pool = rng.perm_pool(n, 100)
+    ores = onet.relax_batch(probes.copy(), pool, threads=8)
+    net = gpu_net(n, SetForceSymmetric=False)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(t))
+    res = net.relax_batch(probes, pool, want_energies=True)
+    # non-dyadic weights: compare every probe with no decision inside the margin (none expected)
+    ok = ores["margin_hits"] == 0
+    assert ok.sum() >= b - 2
+    assert np.array_equal(res.FinalStates[ok], orc.pack(ores["final"])[ok])
+    assert np.array_equal(res.NumSteps[ok], ores["num_steps"][ok])
+    assert np.array_equal(res.Stable[ok], ores["stable"][ok])
+    assert np.array_equal(res.DistancesToTargets[ok], ores["distances"].astype(np.int32)[ok])
+    assert np.allclose(res.EnergyProfiles[ok], ores["energies"][ok], rtol=1e-9, atol=1e-16)
+    net.close()
+
+
+def test_history_capture(built):
+    n, p, b = 96, 9, 24
+    onet, k2, pool, probes, targets = make_problem(n, p, b, 14)
+    net = gpu_net(n)
+    net.SetMatrix(onet.w)
+    res = net.relax_batch(probes, pool, history=True)
+    import ctypes as C
+    for i in range(b):
+        st = probes[i].copy()
+        hist = np.zeros((onet.c.max_iter + 1, n))
+        info = orc.OrcRelaxInfo()
+        orc.lib().orc_relax_state(onet.ref(), st.ctypes.data_as(C.c_void_p), pool.ctypes.data_as(C.c_void_p), pool.shape[0], 0,
+                                  C.byref(info), None, None, hist.ctypes.data_as(C.c_void_p), 0)
+        k = info.num_steps
+        assert res.NumSteps[i] == k
+        assert np.array_equal(res.History[i, :k], orc.pack(hist[:k]))
+    net.close()
+
+
+def test_max_unstable_units_and_stable_probes(built):
+    n, p = 128, 6
+    onet, k2, pool, probes, targets = make_problem(n, p, 16, 15)
+    # probes that are the (stable) targets themselves: still swept once -> NumSteps == 2 (no pre-check)
+    ores = onet.relax_batch(targets.copy(), pool, threads=2)
+    net = gpu_net(n)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(targets))
+    res = net.relax_batch(targets, pool)
+    assert_relax_equal(res, ores, n)
+    assert (res.NumSteps == 2).all() and res.Stable.all()
+    assert (res.DistancesToTargets.diagonal() == 0).all()
+    net.close()
+    # tolerance of 5 unstable units
+    onet2 = orc.Net(n, max_unstable=5, w=onet.w)
+    onet2.set_targets(targets)
+    o2 = onet2.relax_batch(probes.copy(), pool, threads=2)
+    net2 = gpu_net(n, SetMaximumRelaxationUnstableUnits=5)
+    net2.SetMatrix(onet.w)
+    net2.SetLearnedStates(orc.pack(targets))
+    r2 = net2.relax_batch(probes, pool)
+    assert_relax_equal(r2, o2, n)
+    net2.close()
+
+
+def test_baseline_size_config3_sample(built):
+    """N=4096, P=400 (BASELINE config 3) on a sample of probes against the exact-integer oracle, plus
+    size-independent properties: s and -s relax to inverse states with identical step counts, distances
+    are even integers in [0, N], Stable=false => NumSteps = maxIter+1."""
+    n, p, b = 4096, 400, 48
+    onet, k2, pool, probes, targets = make_problem(n, p, b, 16)
+    ores = onet.relax_batch(probes.copy(), pool, threads=8, want_energies=False, fast_k2=k2)
+    net = gpu_net(n)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(targets))
+    res = net.relax_batch(probes, pool, dedup=True)
+    assert_relax_equal(res, ores, n)
+    assert np.array_equal(res.MarginHits, ores["margin_hits"])
+    assert ((res.DistancesToTargets % 2) == 0).all() and (res.DistancesToTargets >= 0).all() and (res.DistancesToTargets <= n).all()
+    assert ((res.Stable == 1) | (res.NumSteps == 101)).all()
+    assert (res.NumSteps >= 2).all() and (res.NumSteps <= 101).all()
+    net.close()

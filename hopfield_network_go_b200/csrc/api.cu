@@ -244,7 +244,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     if (hist) HN_TRY(h->history.reserve(sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
 
     int launches = 0;
-    int32_t* d_small = h->small.as<int32_t>();  // [0] work counter, [1..2] status, [4] unique total
+    int32_t* d_small = h->small.as<int32_t>();  // [0] work counter, [1..4] status, [6] unique total
     HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 64, h->st));
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
 
@@ -269,6 +269,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     p.hash = dedup ? h->hash.as<uint64_t>() : nullptr;
     p.history = hist ? h->history.as<uint64_t>() : nullptr;
     p.work_counter = d_small; p.status = d_small + 1;
+    { const char* ev = getenv("HN_RELAX_VARIANT"); p.variant = ev ? atoi(ev) : 0; }
     HN_TRY(launch_relax(h, p));
     launches++;
     HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
@@ -305,7 +306,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
                                                  h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>());
         dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), B, h->first.as<int32_t>(), h->hits.as<int32_t>());
         dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), B, h->flag.as<int32_t>());
-        scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), d_small + 4);
+        scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), d_small + 6);
         dedup_finalize_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), h->hits.as<int32_t>(),
                                                    h->rank.as<int32_t>(), B, h->attractor.as<int32_t>(),
                                                    h->ufirst.as<int32_t>(), h->uhits.as<int32_t>());
@@ -313,14 +314,18 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         launches += 5;
     }
     HN_CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
-    int32_t small_host[8];
+    int32_t small_host[16];
     HN_CUDA_TRY(cudaMemcpyAsync(small_host, d_small, sizeof(small_host), cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     if (small_host[1]) {
         set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, small_host[2]);
         return HN_E_POOL;
     }
-    h->result_unique = dedup ? small_host[4] : 0;
+    h->result_unique = dedup ? small_host[6] : 0;
+    if (getenv("HN_RELAX_VARIANT")) {
+        long long tt[4]; memcpy(tt, small_host + 8, sizeof(tt));
+        fprintf(stderr, "[hn] variant=%s prediction hits %d / %d  cycles(thread0): scan %lld flip %lld bar %lld other %lld\n", getenv("HN_RELAX_VARIANT"), small_host[3], small_host[4], tt[0], tt[1], tt[2], tt[3]);
+    }
     float f = 0, r = 0, q = 0;
     cudaEventElapsedTime(&f, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&r, h->ev[1], h->ev[2]);

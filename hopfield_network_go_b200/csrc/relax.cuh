@@ -61,7 +61,8 @@ struct RelaxParams {
     uint64_t* hash;          // [B][2] canonical-state hash or nullptr
     uint64_t* history;       // [B][max_iter+1][words] or nullptr
     int32_t* work_counter;   // dynamic probe scheduler
-    int32_t* status;         // [0]: set to 1 when the pool was exhausted; [1]: rows needed
+    int32_t* status;         // [0]: set to 1 when the pool was exhausted; [1]: rows needed; [2],[3]: prediction hits / made
+    int variant;             // tuning knob (HN_RELAX_VARIANT): bit0 L2 prefetch, bit1 L1 prefetch, bits 4..7 spec windows
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -102,6 +103,7 @@ __device__ __forceinline__ double exact_field_warp(const double* __restrict__ ro
 constexpr int RELAX_THREADS = 256;
 constexpr int RELAX_WARPS = RELAX_THREADS / 32;
 constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
+constexpr int RELAX_SPEC_WINDOWS = 2;  // extra 64-position windows scanned to predict the next flip
 
 // Dynamic shared memory layout (see relax_smem_bytes):
 //   s_bits  [nbw, padded to 4]      uint32  master copy of the packed state (exact path, outputs)
@@ -235,9 +237,14 @@ relax_kernel(RelaxParams p) {
         }
 
         int flips = 0, margin = 0, sweeps = 0, is_stable = 0, pool_fail = 0;
+        int pred_k = -1, n_pred = 0, n_hit = 0;
+        long long t_scan = 0, t_flip = 0, t_bar = 0, t_other = 0, t_last = clock64();
+        const bool timing = (p.variant & 256) != 0;
+        const int spec_windows = (p.variant >> 4) & 15;
         for (int sweep = 0; sweep < p.max_iter; sweep++) {
             const long long row = rowbase + sweep;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
+            pred_k = -1;
             const uint16_t* permrow = p.perm_pool + (size_t)row * p.ldp;
             __syncthreads();  // previous readers of s_perm are done; shadow writes visible
             for (int i = tid; i < p.ldp / 2; i += RELAX_THREADS)
@@ -246,28 +253,47 @@ relax_kernel(RelaxParams p) {
 
             int base = 0;  // next position of the sweep order to examine
             for (;;) {
-                // ---- scan ahead (every warp, redundantly): first position >= base whose unit has a < T ----
+                long long tc0 = 0; if (timing) { tc0 = clock64(); t_other += tc0 - t_last; }
+                // ---- scan ahead (every warp, redundantly): first position >= base whose unit has a < T;
+                //      the scan continues a little further to PREDICT the flip after this one, whose
+                //      column is prefetched so that its load overlaps this flip's work ----
                 const int* sa = s_a + (size_t)abuf * NU;
-                int found = -1, fa = 0, fk = 0;
+                int found = -1, fa = 0, fk = 0, k2 = -1, extra = 0;
                 while (base < N) {
                     const int p0 = base + lane, p1 = base + 32 + lane;
                     int k0 = 0, k1 = 0, a0 = 0x7FFFFFFF, a1 = 0x7FFFFFFF;
                     if (p0 < N) { k0 = s_perm[p0]; a0 = sa[k0]; }
                     if (p1 < N) { k1 = s_perm[p1]; a1 = sa[k1]; }
-                    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, a0 < T);
-                    if (m0) {
-                        const int l = __ffs(m0) - 1;
-                        found = base + l; fa = __shfl_sync(0xFFFFFFFFu, a0, l); fk = __shfl_sync(0xFFFFFFFFu, k0, l);
-                        break;
+                    uint32_t m0 = __ballot_sync(0xFFFFFFFFu, a0 < T);
+                    uint32_t m1 = __ballot_sync(0xFFFFFFFFu, a1 < T);
+                    if (found < 0) {
+                        if (m0) {
+                            const int l = __ffs(m0) - 1;
+                            found = base + l; fa = __shfl_sync(0xFFFFFFFFu, a0, l); fk = __shfl_sync(0xFFFFFFFFu, k0, l);
+                            m0 &= m0 - 1;
+                        } else if (m1) {
+                            const int l = __ffs(m1) - 1;
+                            found = base + 32 + l; fa = __shfl_sync(0xFFFFFFFFu, a1, l); fk = __shfl_sync(0xFFFFFFFFu, k1, l);
+                            m1 &= m1 - 1;
+                        }
                     }
-                    const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, a1 < T);
-                    if (m1) {
-                        const int l = __ffs(m1) - 1;
-                        found = base + 32 + l; fa = __shfl_sync(0xFFFFFFFFu, a1, l); fk = __shfl_sync(0xFFFFFFFFu, k1, l);
-                        break;
+                    if (found >= 0) {
+                        if (m0) { k2 = __shfl_sync(0xFFFFFFFFu, k0, __ffs(m0) - 1); break; }
+                        if (m1) { k2 = __shfl_sync(0xFFFFFFFFu, k1, __ffs(m1) - 1); break; }
+                        if (++extra > spec_windows) break;
                     }
                     base += 64;
                 }
+                if (found >= 0 && pred_k >= 0) { n_pred++; n_hit += (pred_k == fk); }
+                pred_k = k2;
+                if (k2 >= 0 && (p.variant & 3)) {  // one 128-byte line per thread covers a 32 KiB column with 256 threads
+                    const char* pc = reinterpret_cast<const char*>(p.Wcol + (size_t)k2 * p.ldw);
+                    for (int o = tid * 128; o < p.ldw * 8; o += RELAX_THREADS * 128) {
+                        if (p.variant & 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + o));
+                        else asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+                    }
+                }
+                long long tc1 = 0; if (timing) { tc1 = clock64(); t_scan += tc1 - tc0; t_last = tc1; }
                 if (found < 0) break;  // sweep finished
                 base = found + 1;
                 const int k = fk;
@@ -295,17 +321,28 @@ relax_kernel(RelaxParams p) {
                 }
                 abuf ^= 1;
                 int* dst = s_a + (size_t)abuf * NU;
-                auto flip_pass = [&](auto full_tag) {
+                auto flip_pass = [&](auto full_tag, auto mode_tag) {
                     constexpr bool FULL = decltype(full_tag)::value;  // every chunk lies inside the padded row
+                    constexpr int LDMODE = decltype(mode_tag)::value;
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         const int u0 = unit_of(c, 0);
                         double w[VEC];
                         if (FULL || u0 < p.ldw) {
                             if (VEC == 4) {
-                                const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
-                                const double2 y = __ldg(reinterpret_cast<const double2*>(col + u0 + 2));
-                                w[0] = x.x; w[1] = x.y; w[2] = y.x; w[3] = y.y;
+                                if (LDMODE == 0) {
+                                    const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
+                                    const double2 y = __ldg(reinterpret_cast<const double2*>(col + u0 + 2));
+                                    w[0] = x.x; w[1] = x.y; w[2] = y.x; w[3] = y.y;
+                                } else if (LDMODE == 1) {
+                                    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "l"(col + u0));
+                                    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(w[2]), "=d"(w[3]) : "l"(col + u0 + 2));
+                                } else if (LDMODE == 2) {
+                                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "l"(col + u0));
+                                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(w[2]), "=d"(w[3]) : "l"(col + u0 + 2));
+                                } else {
+                                    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(col + u0));
+                                }
                             } else if (VEC == 2) {
                                 const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
                                 w[0] = x.x; w[1] = x.y;
@@ -329,9 +366,19 @@ relax_kernel(RelaxParams p) {
                         else q[0] = a[0];
                     }
                 };
-                if (p.ldw == NU) flip_pass(std::true_type{}); else flip_pass(std::false_type{});
+                if (p.ldw == NU) {
+                    // default: 256-bit ld.global.nc.v4.f64 (measured 8% faster than two 128-bit loads; the
+                    // L1/LSU data pipe, not HBM, bounds this kernel: profiles/r01_relax_v3_ncu_summary.txt)
+                    const int lm = (p.variant >> 9) & 3;
+                    if (lm == 0) flip_pass(std::true_type{}, std::integral_constant<int, 3>{});
+                    else if (lm == 1) flip_pass(std::true_type{}, std::integral_constant<int, 1>{});
+                    else if (lm == 2) flip_pass(std::true_type{}, std::integral_constant<int, 2>{});
+                    else flip_pass(std::true_type{}, std::integral_constant<int, 0>{});
+                } else flip_pass(std::false_type{}, std::integral_constant<int, 0>{});
                 flips++;
+                long long tc2 = 0; if (timing) { tc2 = clock64(); t_flip += tc2 - tc1; }
                 __syncthreads();  // shadow[abuf] complete before anyone scans it
+                if (timing) { t_last = clock64(); t_bar += t_last - tc2; }
             }
             sweeps++;
 
@@ -392,6 +439,13 @@ relax_kernel(RelaxParams p) {
             if (p.flips) p.flips[pi] = flips;
             if (p.margin_hits) p.margin_hits[pi] = margin;
             if (p.serial_stream) { s_probe = pi + 1; s_rowbase = rowbase + sweeps; }
+            atomicAdd(&p.status[2], n_hit); atomicAdd(&p.status[3], n_pred);
+            if (timing) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 7), (unsigned long long)t_scan);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 9), (unsigned long long)t_flip);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 11), (unsigned long long)t_bar);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 13), (unsigned long long)t_other);
+            }
         }
         // Manhattan distance with inversion to every target (DistanceMeasure.go:28-42):
         // bipolar 2*min(dH, N-dH), binary min(dH, N-dH); exact integers.

@@ -40,7 +40,7 @@ class HnRelaxOut(C.Structure):
                 ("distances", C.c_void_p), ("energies", C.c_void_p), ("flips", C.c_void_p),
                 ("margin_hits", C.c_void_p), ("attractor_id", C.c_void_p), ("unique_first", C.c_void_p),
                 ("unique_hits", C.c_void_p), ("unique_cap", C.c_int32), ("n_unique", C.c_int32),
-                ("history", C.c_void_p), ("total_flips", C.c_int64), ("total_sweeps", C.c_int64),
+                ("history", C.c_void_p), ("state_hash", C.c_void_p), ("total_flips", C.c_int64), ("total_sweeps", C.c_int64),
                 ("total_margin_hits", C.c_int64), ("device_ms", C.c_double)]
 
 

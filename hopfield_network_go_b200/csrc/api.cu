@@ -365,6 +365,10 @@ int download_results(hn_handle h, hn_relax_out* out) {
             HN_TRY(d2h(out->unique_hits, h->uhits.p, sizeof(int32_t) * (size_t)nu));
         }
     }
+    if (out->state_hash) {
+        if (!(h->result_flags & HN_RELAX_DEDUP)) { set_error("state hashes were not computed (HN_RELAX_DEDUP)"); return HN_E_STATE; }
+        HN_TRY(d2h(out->state_hash, h->hash.p, sizeof(uint64_t) * 2 * (size_t)B));
+    }
     if (out->history) {
         if (!(h->result_flags & HN_RELAX_HISTORY)) { set_error("history was not captured"); return HN_E_STATE; }
         HN_TRY(d2h(out->history, h->history.p, sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));

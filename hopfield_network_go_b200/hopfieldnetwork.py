@@ -87,6 +87,7 @@ class RelaxationBatchResult:
     UniqueFirst: Optional[np.ndarray] = None
     UniqueHits: Optional[np.ndarray] = None
     History: Optional[np.ndarray] = None
+    StateHash: Optional[np.ndarray] = None
     total_flips: int = 0
     total_sweeps: int = 0
     total_margin_hits: int = 0
@@ -252,13 +253,15 @@ class HopfieldNetwork:
         out.attractor_id, out.unique_first, out.unique_hits = ptr(aid), ptr(uf), ptr(uh)
         out.unique_cap = b if dedup else 0
         out.history = ptr(hist)
+        sh = np.zeros((b, 2), dtype=np.uint64) if dedup else None
+        out.state_hash = ptr(sh)
         flags = (capi.HN_RELAX_SERIAL_STREAM if serial_stream else 0) | (capi.HN_RELAX_DEDUP if dedup else 0) | \
                 (capi.HN_RELAX_HISTORY if history else 0)
         off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int32)
         check(capi.load().hn_relax_batch(self._h, ptr(p), b, ptr(pool), pool.shape[0], ptr(off), flags, C.byref(out)))
         nu = out.n_unique
         return RelaxationBatchResult(finals, steps, stable, dist, en, flips, margin, aid,
-                                     uf[:nu].copy() if dedup else None, uh[:nu].copy() if dedup else None, hist,
+                                     uf[:nu].copy() if dedup else None, uh[:nu].copy() if dedup else None, hist, sh,
                                      out.total_flips, out.total_sweeps, out.total_margin_hits, out.device_ms)
 
     def ConcurrentRelaxStates(self, states, numThreads: int = 1, **kw) -> RelaxationBatchResult:

@@ -1,0 +1,96 @@
+"""Multi-GPU host logic: one process per GPU, W replicated, probes sharded, results gathered on the host.
+
+The path shards by independent units: probe relaxation needs NO data-path collective;
+each rank relaxes a contiguous index range and the per-rank unique-attractor tables are merged on the
+host in ascending probe index so that first-seen StateIndex and Hits equal the single-stream answer
+(main.go:226 iterates results in index order; datacollector/UniqueRelaxedStateHandler.go:41-66).
+Learning shards the TARGETS and all-reduces dW (NCCL, inside the C library: hn_comm_attach).
+
+torch.distributed is used only as plumbing (gather of small arrays); works on gloo (CPU tests) and nccl.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) range of rank: sizes differ by at most one, earlier ranks get the extra."""
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def merge_unique_tables(tables: List[dict]) -> dict:
+    """Merge per-rank unique tables.
+
+    tables[r] = {"offset": global index of the rank's first probe,
+                 "first":  int32 [U_r]  local index of first occurrence (first-seen order),
+                 "hits":   int32 [U_r],
+                 "hash":   uint64 [U_r][2] 128-bit hash of the canonical final state of that first occurrence,
+                 "states": optional uint64 [U_r][words] canonical-comparable packed states (for verification)}
+    Returns {"first": global StateIndex per unique attractor in first-seen order, "hits", "rank_of", "local_id"}.
+    Equality is decided on the 128-bit hash; where `states` are supplied, hash-equal entries from different
+    ranks are verified on the full state (a mismatch raises)."""
+    firsts, hits, hashes, ranks, lids, states = [], [], [], [], [], []
+    for r, t in enumerate(tables):
+        u = len(t["first"])
+        firsts.append(np.asarray(t["first"], dtype=np.int64) + int(t["offset"]))
+        hits.append(np.asarray(t["hits"], dtype=np.int64))
+        hashes.append(np.asarray(t["hash"], dtype=np.uint64).reshape(u, 2))
+        ranks.append(np.full(u, r, dtype=np.int32))
+        lids.append(np.arange(u, dtype=np.int32))
+        if t.get("states") is not None:
+            states.append(np.asarray(t["states"], dtype=np.uint64).reshape(u, -1))
+    first = np.concatenate(firsts) if firsts else np.zeros(0, np.int64)
+    hit = np.concatenate(hits) if hits else np.zeros(0, np.int64)
+    hsh = np.concatenate(hashes) if hashes else np.zeros((0, 2), np.uint64)
+    rk = np.concatenate(ranks) if ranks else np.zeros(0, np.int32)
+    lid = np.concatenate(lids) if lids else np.zeros(0, np.int32)
+    st = np.concatenate(states) if len(states) == len(tables) and states else None
+    if first.size == 0:
+        return {"first": first.astype(np.int32), "hits": hit.astype(np.int32), "rank_of": rk, "local_id": lid}
+    order = np.lexsort((first, hsh[:, 1], hsh[:, 0]))           # group by hash, earliest first inside a group
+    h_sorted = hsh[order]
+    new_group = np.ones(order.size, dtype=bool)
+    new_group[1:] = (h_sorted[1:] != h_sorted[:-1]).any(axis=1)
+    gid = np.cumsum(new_group) - 1
+    n_groups = int(gid[-1]) + 1
+    g_first = np.full(n_groups, np.iinfo(np.int64).max)
+    np.minimum.at(g_first, gid, first[order])
+    g_hits = np.zeros(n_groups, dtype=np.int64)
+    np.add.at(g_hits, gid, hit[order])
+    rep = order[new_group]                                        # earliest member of each group
+    if st is not None:
+        same = (st[order] == st[rep][gid]).all(axis=1)
+        if not same.all():
+            raise RuntimeError("128-bit state-hash collision between distinct attractors")
+    out_order = np.argsort(g_first, kind="stable")                # first-seen order == ascending first index
+    return {"first": g_first[out_order].astype(np.int32), "hits": g_hits[out_order].astype(np.int32),
+            "rank_of": rk[rep][out_order], "local_id": lid[rep][out_order]}
+
+
+def canonical_states(packed: np.ndarray, n: int, domain: int) -> np.ndarray:
+    """Sign-canonical form used by the dedup key: bipolar states with unit 0 set are inverted
+    (s and -s share one energy profile bit for bit, which is the reference's key)."""
+    p = np.ascontiguousarray(packed, dtype=np.uint64).copy()
+    if domain != 0 or p.size == 0:
+        return p
+    inv = (p[:, 0] & np.uint64(1)).astype(bool)
+    p[inv] = ~p[inv]
+    if n % 64:
+        p[:, -1] &= np.uint64((1 << (n % 64)) - 1)
+    return p
+
+
+def gather_unique_tables(local: dict, group=None) -> Optional[dict]:
+    """All ranks call; rank 0 returns the merged table, the others None.  `local` as in merge_unique_tables."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gathered: List[Optional[dict]] = [None] * world
+    dist.gather_object(local, gathered if rank == 0 else None, dst=0, group=group)
+    if rank != 0:
+        return None
+    return merge_unique_tables(gathered)  # type: ignore[arg-type]

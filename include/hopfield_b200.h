@@ -217,6 +217,9 @@ typedef struct hn_relax_out {
     int32_t   n_unique;       /* out */
     /* history (HN_RELAX_HISTORY): packed state after every step incl. step 0 */
     uint64_t* history;        /* [B][max_relax_iterations+1][hn_words(N)]                            */
+    /* 128-bit hash of the sign-canonical final state (HN_RELAX_DEDUP): lets several GPUs merge their
+       unique tables without shipping the states (hopfield_network_go_b200/multigpu.py)               */
+    uint64_t* state_hash;     /* [B][2]                                                              */
     /* totals (out) */
     int64_t   total_flips;
     int64_t   total_sweeps;

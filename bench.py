@@ -185,16 +185,23 @@ def main():
     step_ms = float(np.sum(dev_ms))
     # e2e: host buffers through hn_relax_batch
     e2e_t = []
+    n_unique_global = None
     for it in range(1 + min(args.steps, 2)):
         barrier()
         t1 = time.perf_counter()
         res = net.relax_batch(probes_np, pool, dedup=True)
+        if world > 1:   # host-side merge of the per-GPU unique-attractor tables (first-seen order, hits)
+            from hopfield_network_go_b200 import multigpu
+            merged = multigpu.gather_unique_tables({"offset": rank * b, "first": res.UniqueFirst, "hits": res.UniqueHits,
+                                                    "hash": res.StateHash[res.UniqueFirst]})
+            if rank == 0:
+                n_unique_global = len(merged["first"])
         barrier()
         if it > 0:
             e2e_t.append(time.perf_counter() - t1)
     h2d = probes_np.nbytes + pool.nbytes
     d2h = res.FinalStates.nbytes + res.NumSteps.nbytes + res.Stable.nbytes + res.DistancesToTargets.nbytes + \
-        res.Flips.nbytes + res.MarginHits.nbytes + res.AttractorId.nbytes + 2 * 4 * len(res.UniqueFirst)
+        res.Flips.nbytes + res.MarginHits.nbytes + res.AttractorId.nbytes + 2 * 4 * len(res.UniqueFirst) + res.StateHash.nbytes
     tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t))], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -222,7 +229,8 @@ def main():
                 "clocks": sampler.summary(), "wall_s": wall,
                 "stage_ms_per_step": {"fields_gemm": float(np.mean(fields_ms)), "relax": float(np.mean(relax_ms)),
                                       "dedup": float(np.mean(post_ms))},
-                "margin_hits_per_probe": out.total_margin_hits / b, "unique_attractors": int(out.n_unique)}
+                "margin_hits_per_probe": out.total_margin_hits / b,
+                "unique_attractors": int(n_unique_global if n_unique_global is not None else out.n_unique)}
         if not args.no_cpu:
             from oracle import orc
             cores = os.cpu_count() or 1

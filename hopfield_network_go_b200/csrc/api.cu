@@ -245,7 +245,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
 
     int launches = 0;
     int32_t* d_small = h->small.as<int32_t>();  // [0] work counter, [1..4] status, [6] unique total
-    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 64, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
 
     HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
@@ -314,7 +314,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         launches += 5;
     }
     HN_CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
-    int32_t small_host[16];
+    int32_t small_host[24];
     HN_CUDA_TRY(cudaMemcpyAsync(small_host, d_small, sizeof(small_host), cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     if (small_host[1]) {
@@ -323,8 +323,9 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     }
     h->result_unique = dedup ? small_host[6] : 0;
     if (getenv("HN_RELAX_VARIANT")) {
-        long long tt[4]; memcpy(tt, small_host + 8, sizeof(tt));
-        fprintf(stderr, "[hn] variant=%s prediction hits %d / %d  cycles(thread0): scan %lld flip %lld bar %lld other %lld\n", getenv("HN_RELAX_VARIANT"), small_host[3], small_host[4], tt[0], tt[1], tt[2], tt[3]);
+        long long tt[6]; memcpy(tt, small_host + 8, sizeof(tt));
+        fprintf(stderr, "[hn] variant=%s cycles(thread0) scan %lld owner %lld barriers %lld load+fma %lld cand+atomics %lld sweepsetup+stability %lld\n",
+                getenv("HN_RELAX_VARIANT"), tt[0], tt[1], tt[2], tt[3], tt[4], tt[5]);
     }
     float f = 0, r = 0, q = 0;
     cudaEventElapsedTime(&f, h->ev[0], h->ev[1]);
@@ -472,7 +473,7 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
     HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
     HN_TRY(h->small.reserve(256));
     int32_t* d_small = h->small.as<int32_t>();
-    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 64, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
     RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;
@@ -892,7 +893,7 @@ int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint
     HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
     HN_TRY(h->small.reserve(256));
     int32_t* d_small = h->small.as<int32_t>();
-    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 64, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
     RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;

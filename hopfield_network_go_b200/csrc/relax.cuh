@@ -103,42 +103,50 @@ __device__ __forceinline__ double exact_field_warp(const double* __restrict__ ro
 constexpr int RELAX_THREADS = 256;
 constexpr int RELAX_WARPS = RELAX_THREADS / 32;
 constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
-constexpr int RELAX_SPEC_WINDOWS = 2;  // extra 64-position windows scanned to predict the next flip
+#ifndef RELAX_MIN_CTAS
+#define RELAX_MIN_CTAS 3
+#endif
 
 // Dynamic shared memory layout (see relax_smem_bytes):
-//   s_bits  [nbw, padded to 4]      uint32  master copy of the packed state (exact path, outputs)
-//   s_perm  [ldp]                   uint16  this sweep's visiting order
-//   s_a     [2][THREADS*UPT]        int32   double-buffered per-unit "aligned hi word":
-//           a_u = (hi32(h_u) ^ (bit_u ? 0 : 0x80000000)) & ~1 | bit_u.  As a signed integer a_u < T
-//           (T = hi32(tau)+2) iff the aligned field h_u*v_u is below tau, i.e. the unit wants to flip
-//           or sits inside the margin; the low bit carries the unit's current bit.
+//   s_bits  [nbw, padded to 4]   uint32  packed state (exact path, outputs)
+//   s_perm  [ldp]                uint16  this sweep's visiting order        (position -> unit)
+//   s_inv   [ldp]                uint16  its inverse                        (unit -> position)
+//   s_cand  [ncw, padded to 4]   uint32  POSITION-indexed candidate bitmap: bit i is set iff the unit at
+//           position i of this sweep has aligned field h*v < tau, i.e. wants to flip or sits inside the margin.
 //
-// Per flip: every thread updates its UPT fields in registers (one coalesced pass over the column),
-// rewrites its slice of the shadow, ONE __syncthreads, then every warp redundantly scans the sweep
-// order from the current position with ballots to find the next unit that may flip.
+// Per flip: every thread updates its UPT fields in registers (one coalesced 256-bit pass over the column),
+// re-derives the candidacy of its units (hi-word integer compare) and toggles the bitmap only where it
+// changed; __syncthreads; every warp finds the next candidate position with one coalesced read of the bitmap
+// (32 words = 1024 positions per step) + ballot/ffs; the unit's owner publishes (inside-margin?, old bit);
+// __syncthreads.  The L1/LSU data pipe carries the column and almost nothing else.
 template <int UPT> struct RelaxCfg {
     static constexpr int VEC = UPT >= 4 ? 4 : UPT;   // contiguous units per ownership chunk
     static constexpr int NCH = UPT / VEC;            // chunks per thread
 };
 static inline size_t relax_smem_bytes(int N, int ldp, int upt) {
     const int nbw = (N + 31) / 32;
-    return (size_t)((nbw + 3) / 4 * 4) * 4 + (size_t)((ldp + 7) / 8 * 8) * 2 + (size_t)2 * RELAX_THREADS * upt * 4;
+    (void)upt;
+    return (size_t)((nbw + 3) / 4 * 4) * 4 * 2 + (size_t)((ldp + 7) / 8 * 8) * 2 * 2;
 }
 
 template <int UPT>
-__global__ void __launch_bounds__(RELAX_THREADS, (UPT <= 16 ? 3 : 1))
+__global__ void __launch_bounds__(RELAX_THREADS, (UPT <= 16 ? RELAX_MIN_CTAS : 1))
 relax_kernel(RelaxParams p) {
     constexpr int VEC = RelaxCfg<UPT>::VEC;
     constexpr int NCH = RelaxCfg<UPT>::NCH;
     constexpr int NU = RELAX_THREADS * UPT;  // padded unit count
+    using mask_t = typename std::conditional<(UPT > 32), uint64_t, uint32_t>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbw = (p.N + 31) / 32;
+    const int nbw4 = (nbw + 3) / 4 * 4, ldp8 = (p.ldp + 7) / 8 * 8;
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);
-    uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem_raw + (size_t)((nbw + 3) / 4 * 4) * 4);
-    int* s_a = reinterpret_cast<int*>(smem_raw + (size_t)((nbw + 3) / 4 * 4) * 4 + (size_t)((p.ldp + 7) / 8 * 8) * 2);
+    uint32_t* s_cand = s_bits + nbw4;
+    uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_cand + nbw4);
+    uint16_t* s_inv = s_perm + ldp8;
     __shared__ __align__(16) uint32_t s_red[2][RELAX_WARPS];
     __shared__ double s_exact[4];
     __shared__ int s_probe;
+    __shared__ int s_flag;
     __shared__ long long s_rowbase;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -146,10 +154,11 @@ relax_kernel(RelaxParams p) {
     const double dscale = p.domain == HN_DOMAIN_BINARY ? 1.0 : 2.0;
     // constant margin for the whole relaxation: tau(flips) at its largest possible flip count
     const double tau = p.tau_base + p.tau_flip * ((double)p.max_iter * (double)N);
-    const int T = __double2hiint(tau) + 2;
+    const int T = __double2hiint(tau) + 1;
     int red_buf = 0;
 
     auto unit_of = [&](int c, int e) -> int { return (c * RELAX_THREADS + tid) * VEC + e; };
+    auto unit_of_r = [&](int r) -> int { return ((r / VEC) * RELAX_THREADS + tid) * VEC + (r % VEC); };
 
     auto block_min = [&](uint32_t x) -> uint32_t {
         x = __reduce_min_sync(0xFFFFFFFFu, x);
@@ -197,8 +206,7 @@ relax_kernel(RelaxParams p) {
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
         double h[UPT];     // true local fields of my units
-        int sw[UPT];       // per unit: bit31 = !bit (sign mask of v = -1), bit0 = bit
-        int abuf = 0;      // shadow buffer the next scan reads
+        int sw[UPT];       // per unit: 0x80000000 when the bit is clear (v = -1), else 0: hi32(h) ^ sw = hi32(h*v)
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
 #pragma unroll
@@ -206,143 +214,125 @@ relax_kernel(RelaxParams p) {
                 const int u = unit_of(c, e), r = c * VEC + e;
                 if (u < N) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
-                    sw[r] = b ? 1 : (int)0x80000000;
+                    sw[r] = b ? 0 : (int)0x80000000;
                     h[r] = p.H0[(size_t)pi * p.ldh + u];
-                } else {  // padding: never visited by any order
-                    sw[r] = 1;
+                } else {  // padding: never a candidate, never visited
+                    sw[r] = 0;
                     h[r] = __longlong_as_double(0x7FF0000000000000LL);
                 }
             }
         }
-        auto write_shadow = [&](int buf) {
-            int* dst = s_a + (size_t)buf * NU;
+        // candidacy of my units: bit r set iff hi32(h*v) < T   (aligned field below tau)
+        auto cand_mask = [&]() -> mask_t {
+            mask_t m = 0;
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                int a[VEC];
-#pragma unroll
-                for (int e = 0; e < VEC; e++) {
-                    const int r = c * VEC + e;
-                    a[e] = (__double2hiint(h[r]) & ~1) ^ sw[r];
-                }
-                int* q = dst + unit_of(c, 0);
-                if (VEC == 4) *reinterpret_cast<int4*>(q) = make_int4(a[0], a[1], a[2], a[3]);
-                else if (VEC == 2) *reinterpret_cast<int2*>(q) = make_int2(a[0], a[1]);
-                else q[0] = a[0];
-            }
+            for (int r = 0; r < UPT; r++)
+                if ((__double2hiint(h[r]) ^ sw[r]) < T) m |= (mask_t)1 << r;
+            return m;
         };
-        write_shadow(abuf);
+        mask_t cm = cand_mask();
         if (p.history) {
             uint32_t* hw = reinterpret_cast<uint32_t*>(p.history + ((size_t)pi * (p.max_iter + 1)) * p.words);
             for (int w = tid; w < p.words * 2; w += RELAX_THREADS) hw[w] = w < nbw ? s_bits[w] : 0u;
         }
 
         int flips = 0, margin = 0, sweeps = 0, is_stable = 0, pool_fail = 0;
-        int pred_k = -1, n_pred = 0, n_hit = 0;
-        long long t_scan = 0, t_flip = 0, t_bar = 0, t_other = 0, t_last = clock64();
         const bool timing = (p.variant & 256) != 0;
-        const int spec_windows = (p.variant >> 4) & 15;
+        long long tph[6] = {0, 0, 0, 0, 0, 0}, tl = timing ? clock64() : 0;
+#define HN_TICK(i) if (timing) { const long long tn = clock64(); tph[i] += tn - tl; tl = tn; }
         for (int sweep = 0; sweep < p.max_iter; sweep++) {
             const long long row = rowbase + sweep;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
-            pred_k = -1;
             const uint16_t* permrow = p.perm_pool + (size_t)row * p.ldp;
-            __syncthreads();  // previous readers of s_perm are done; shadow writes visible
-            for (int i = tid; i < p.ldp / 2; i += RELAX_THREADS)
+            const uint16_t* invrow = p.inv_pool + (size_t)row * p.ldp;
+            __syncthreads();  // previous readers of s_perm / s_inv / s_cand are done
+            for (int i = tid; i < p.ldp / 2; i += RELAX_THREADS) {
                 reinterpret_cast<uint32_t*>(s_perm)[i] = reinterpret_cast<const uint32_t*>(permrow)[i];
+                reinterpret_cast<uint32_t*>(s_inv)[i] = reinterpret_cast<const uint32_t*>(invrow)[i];
+            }
+            for (int w = tid; w < nbw4; w += RELAX_THREADS) s_cand[w] = 0u;
+            __syncthreads();
+            {   // bitmap of this sweep's order from the candidacy masks held in registers
+                mask_t m = cm;
+                while (m) {
+                    const int r = (sizeof(mask_t) == 8) ? (__ffsll((long long)m) - 1) : (__ffs((int)m) - 1);
+                    m &= m - 1;
+                    const int pos = s_inv[unit_of_r(r)];
+                    atomicOr(&s_cand[pos >> 5], 1u << (pos & 31));
+                }
+            }
             __syncthreads();
 
             int base = 0;  // next position of the sweep order to examine
+            HN_TICK(5)
             for (;;) {
-                long long tc0 = 0; if (timing) { tc0 = clock64(); t_other += tc0 - t_last; }
-                // ---- scan ahead (every warp, redundantly): first position >= base whose unit has a < T;
-                //      the scan continues a little further to PREDICT the flip after this one, whose
-                //      column is prefetched so that its load overlaps this flip's work ----
-                const int* sa = s_a + (size_t)abuf * NU;
-                int found = -1, fa = 0, fk = 0, k2 = -1, extra = 0;
-                while (base < N) {
-                    const int p0 = base + lane, p1 = base + 32 + lane;
-                    int k0 = 0, k1 = 0, a0 = 0x7FFFFFFF, a1 = 0x7FFFFFFF;
-                    if (p0 < N) { k0 = s_perm[p0]; a0 = sa[k0]; }
-                    if (p1 < N) { k1 = s_perm[p1]; a1 = sa[k1]; }
-                    uint32_t m0 = __ballot_sync(0xFFFFFFFFu, a0 < T);
-                    uint32_t m1 = __ballot_sync(0xFFFFFFFFu, a1 < T);
-                    if (found < 0) {
-                        if (m0) {
-                            const int l = __ffs(m0) - 1;
-                            found = base + l; fa = __shfl_sync(0xFFFFFFFFu, a0, l); fk = __shfl_sync(0xFFFFFFFFu, k0, l);
-                            m0 &= m0 - 1;
-                        } else if (m1) {
-                            const int l = __ffs(m1) - 1;
-                            found = base + 32 + l; fa = __shfl_sync(0xFFFFFFFFu, a1, l); fk = __shfl_sync(0xFFFFFFFFu, k1, l);
-                            m1 &= m1 - 1;
-                        }
-                    }
-                    if (found >= 0) {
-                        if (m0) { k2 = __shfl_sync(0xFFFFFFFFu, k0, __ffs(m0) - 1); break; }
-                        if (m1) { k2 = __shfl_sync(0xFFFFFFFFu, k1, __ffs(m1) - 1); break; }
-                        if (++extra > spec_windows) break;
-                    }
-                    base += 64;
-                }
-                if (found >= 0 && pred_k >= 0) { n_pred++; n_hit += (pred_k == fk); }
-                pred_k = k2;
-                if (k2 >= 0 && (p.variant & 3)) {  // one 128-byte line per thread covers a 32 KiB column with 256 threads
-                    const char* pc = reinterpret_cast<const char*>(p.Wcol + (size_t)k2 * p.ldw);
-                    for (int o = tid * 128; o < p.ldw * 8; o += RELAX_THREADS * 128) {
-                        if (p.variant & 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + o));
-                        else asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+                // ---- scan ahead (every warp, redundantly): first set bit of the bitmap at position >= base ----
+                int found = -1;
+                for (int w0 = base >> 5; w0 < nbw; w0 += 32) {
+                    const int wi = w0 + lane;
+                    uint32_t word = wi < nbw ? s_cand[wi] : 0u;
+                    if (wi == (base >> 5)) word &= 0xFFFFFFFFu << (base & 31);
+                    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0u);
+                    if (nz) {
+                        const int l = __ffs(nz) - 1;
+                        const uint32_t wsel = __shfl_sync(0xFFFFFFFFu, word, l);
+                        found = (w0 + l) * 32 + __ffs(wsel) - 1;
+                        break;
                     }
                 }
-                long long tc1 = 0; if (timing) { tc1 = clock64(); t_scan += tc1 - tc0; t_last = tc1; }
+                HN_TICK(0)
                 if (found < 0) break;  // sweep finished
                 base = found + 1;
-                const int k = fk;
-                const uint32_t ob = (uint32_t)fa & 1u;
+                const int k = s_perm[found];
+                {   // owner of k publishes: bit1 = inside the margin, bit0 = current (old) bit
+                    const int ch = k / VEC, ke = k % VEC;
+                    if ((ch % RELAX_THREADS) == tid) {
+                        const int rr = (ch / RELAX_THREADS) * VEC + ke;
+                        int a = 0, sg = 0;
+#pragma unroll
+                        for (int r = 0; r < UPT; r++)
+                            if (r == rr) { a = __double2hiint(h[r]); sg = sw[r]; }
+                        s_flag = ((((a & 0x7FFFFFFF) < T) ? 2 : 0) | (sg ? 0 : 1));
+                    }
+                }
+                HN_TICK(1)
+                __syncthreads();
+                HN_TICK(2)
+                const int fl = s_flag;
+                const uint32_t ob = (uint32_t)fl & 1u;
                 uint32_t nb = ob ^ 1u;
-                if (((fa & 0x7FFFFFFF) | 1) < T) {  // inside the margin: decide exactly, in the reference's order
+                if (fl & 2) {  // inside the margin: decide exactly, in the reference's summation order
                     const double hx = exact_field(k);
                     margin++;
                     nb = hx > 0.0 ? 1u : 0u;
                 }
-                if (nb == ob) continue;  // exact decision: no flip; shadow unchanged, keep scanning
+                if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
-                // ---- flip unit k: h += d * W[:,k] over my units; rewrite my slice of the other shadow ----
+                // ---- flip unit k: h += d * W[:,k] over my units; toggle the bitmap where candidacy changed ----
                 const double d = nb ? dscale : -dscale;
                 const double* col = p.Wcol + (size_t)k * p.ldw;
-                {   // owner: new bit into its sign word and the master state
+                {   // owner: new bit into its sign word and the packed state
                     const int ch = k / VEC, ke = k % VEC;
                     if ((ch % RELAX_THREADS) == tid) {
                         const int rr = (ch / RELAX_THREADS) * VEC + ke;
 #pragma unroll
                         for (int r = 0; r < UPT; r++)
-                            if (r == rr) sw[r] ^= (int)0x80000001;
+                            if (r == rr) sw[r] ^= (int)0x80000000;
                         s_bits[k >> 5] ^= 1u << (k & 31);
                     }
                 }
-                abuf ^= 1;
-                int* dst = s_a + (size_t)abuf * NU;
-                auto flip_pass = [&](auto full_tag, auto mode_tag) {
+                auto flip_pass = [&](auto full_tag) {
                     constexpr bool FULL = decltype(full_tag)::value;  // every chunk lies inside the padded row
-                    constexpr int LDMODE = decltype(mode_tag)::value;
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         const int u0 = unit_of(c, 0);
                         double w[VEC];
                         if (FULL || u0 < p.ldw) {
                             if (VEC == 4) {
-                                if (LDMODE == 0) {
-                                    const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
-                                    const double2 y = __ldg(reinterpret_cast<const double2*>(col + u0 + 2));
-                                    w[0] = x.x; w[1] = x.y; w[2] = y.x; w[3] = y.y;
-                                } else if (LDMODE == 1) {
-                                    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "l"(col + u0));
-                                    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(w[2]), "=d"(w[3]) : "l"(col + u0 + 2));
-                                } else if (LDMODE == 2) {
-                                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(w[0]), "=d"(w[1]) : "l"(col + u0));
-                                    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(w[2]), "=d"(w[3]) : "l"(col + u0 + 2));
-                                } else {
-                                    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(col + u0));
-                                }
+                                // 256-bit load: 8% faster than two 128-bit loads here; the column stream is
+                                // bounded by the L2->SM fabric (profiles/r01_relax_v4_ncu_summary.txt)
+                                asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                             : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(col + u0));
                             } else if (VEC == 2) {
                                 const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
                                 w[0] = x.x; w[1] = x.y;
@@ -353,32 +343,27 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                             for (int e = 0; e < VEC; e++) w[e] = 0.0;
                         }
-                        int a[VEC];
 #pragma unroll
-                        for (int e = 0; e < VEC; e++) {
-                            const int r = c * VEC + e;
-                            h[r] = fma(d, w[e], h[r]);
-                            a[e] = (__double2hiint(h[r]) & ~1) ^ sw[r];
-                        }
-                        int* q = dst + u0;
-                        if (VEC == 4) *reinterpret_cast<int4*>(q) = make_int4(a[0], a[1], a[2], a[3]);
-                        else if (VEC == 2) *reinterpret_cast<int2*>(q) = make_int2(a[0], a[1]);
-                        else q[0] = a[0];
+                        for (int e = 0; e < VEC; e++) h[c * VEC + e] = fma(d, w[e], h[c * VEC + e]);
                     }
                 };
-                if (p.ldw == NU) {
-                    // default: 256-bit ld.global.nc.v4.f64 (measured 8% faster than two 128-bit loads; the
-                    // L1/LSU data pipe, not HBM, bounds this kernel: profiles/r01_relax_v3_ncu_summary.txt)
-                    const int lm = (p.variant >> 9) & 3;
-                    if (lm == 0) flip_pass(std::true_type{}, std::integral_constant<int, 3>{});
-                    else if (lm == 1) flip_pass(std::true_type{}, std::integral_constant<int, 1>{});
-                    else if (lm == 2) flip_pass(std::true_type{}, std::integral_constant<int, 2>{});
-                    else flip_pass(std::true_type{}, std::integral_constant<int, 0>{});
-                } else flip_pass(std::false_type{}, std::integral_constant<int, 0>{});
+                if (p.ldw == NU) flip_pass(std::true_type{}); else flip_pass(std::false_type{});
+                HN_TICK(3)
+                {
+                    const mask_t nm = cand_mask();
+                    mask_t ch = nm ^ cm;
+                    cm = nm;
+                    while (ch) {
+                        const int r = (sizeof(mask_t) == 8) ? (__ffsll((long long)ch) - 1) : (__ffs((int)ch) - 1);
+                        ch &= ch - 1;
+                        const int pos = s_inv[unit_of_r(r)];
+                        atomicXor(&s_cand[pos >> 5], 1u << (pos & 31));
+                    }
+                }
                 flips++;
-                long long tc2 = 0; if (timing) { tc2 = clock64(); t_flip += tc2 - tc1; }
-                __syncthreads();  // shadow[abuf] complete before anyone scans it
-                if (timing) { t_last = clock64(); t_bar += t_last - tc2; }
+                HN_TICK(4)
+                __syncthreads();  // bitmap complete before anyone scans it
+                HN_TICK(2)
             }
             sweeps++;
 
@@ -393,7 +378,7 @@ relax_kernel(RelaxParams p) {
             uint32_t cnt = 0;
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
-                const int a = __double2hiint(h[r]) ^ (sw[r] & (int)0x80000000);
+                const int a = __double2hiint(h[r]) ^ sw[r];
                 if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
             }
             cnt = block_sum(cnt);
@@ -402,13 +387,9 @@ relax_kernel(RelaxParams p) {
             for (;;) {
                 uint32_t cmin = RELAX_NONE;
 #pragma unroll
-                for (int c = 0; c < NCH; c++) {
-#pragma unroll
-                    for (int e = 0; e < VEC; e++) {
-                        const int r = c * VEC + e;
-                        const int u = unit_of(c, e);
-                        if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T && u > last) cmin = min(cmin, (uint32_t)u);
-                    }
+                for (int r = 0; r < UPT; r++) {
+                    const int u = unit_of_r(r);
+                    if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T && u > last) cmin = min(cmin, (uint32_t)u);
                 }
                 cmin = block_min(cmin);
                 if (cmin == RELAX_NONE) break;
@@ -439,13 +420,7 @@ relax_kernel(RelaxParams p) {
             if (p.flips) p.flips[pi] = flips;
             if (p.margin_hits) p.margin_hits[pi] = margin;
             if (p.serial_stream) { s_probe = pi + 1; s_rowbase = rowbase + sweeps; }
-            atomicAdd(&p.status[2], n_hit); atomicAdd(&p.status[3], n_pred);
-            if (timing) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 7), (unsigned long long)t_scan);
-                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 9), (unsigned long long)t_flip);
-                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 11), (unsigned long long)t_bar);
-                atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 13), (unsigned long long)t_other);
-            }
+            if (timing) for (int i = 0; i < 6; i++) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 7) + i, (unsigned long long)tph[i]);
         }
         // Manhattan distance with inversion to every target (DistanceMeasure.go:28-42):
         // bipolar 2*min(dH, N-dH), binary min(dH, N-dH); exact integers.

@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--dim", type=int, default=4096)
     ap.add_argument("--targets", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-delta", action="store_true", help="skip the Delta-rule epoch timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,6 +232,12 @@ def main():
                                       "dedup": float(np.mean(post_ms))},
                 "margin_hits_per_probe": out.total_margin_hits / b,
                 "unique_attractors": int(n_unique_global if n_unique_global is not None else out.n_unique)}
+        if not args.no_delta:
+            line["delta_epoch_ms"] = {
+                "config2_N1024_P100_inversion0.1": measure_delta_epoch(hn, local, 1024, 100, 5),
+                "config5_shape_N16384_P128_per_gpu": measure_delta_epoch(hn, local, 16384, 128, 2),
+                "note": "wall clock through hn_delta_epoch + hn_energy_profiles with host buffers (H2D of packed targets, "
+                        "noised copies and permutations inside the timed region); 1 GPU, no all-reduce"}
         if not args.no_cpu:
             from oracle import orc
             cores = os.cpu_count() or 1
@@ -251,6 +258,34 @@ def main():
     net.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_delta_epoch(hn, local, n, p, epochs, noise_scale=0.1):
+    """Second BASELINE metric: Delta-rule epoch time = one pass of `delta` (LearningRule.go:90-114) over all
+    targets + the per-epoch target diagnostics of fullSetLearningMethod (LearningMethod.go:45-58).
+    Noise / update orders are drawn host-side with the library's restated RNG before the timed region."""
+    rs = np.random.Generator(np.random.PCG64(0x5EED + 2))
+    w = (n + 63) // 64
+    targets = rs.integers(0, 2**63, size=(p, w), dtype=np.int64).astype(np.uint64) << np.uint64(1) | \
+        rs.integers(0, 2, size=(p, w), dtype=np.int64).astype(np.uint64)
+    net = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
+        hn.DeltaLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(2).SetDevice(local).Build()
+    k = int(n * noise_scale)
+    times = []
+    for ep in range(epochs + 2):
+        noised = targets.copy()
+        for s in range(p):      # MaximalInversion: int(N*ratio) units among 0..N-2 (NoiseApplication.go:64-75)
+            idx = rs.permutation(n - 1)[:k]
+            np.bitwise_xor.at(noised[s], idx // 64, np.uint64(1) << (idx % 64).astype(np.uint64))
+        perms = np.stack([rs.permutation(n).astype(np.uint16) for _ in range(p)])
+        t0 = time.perf_counter()
+        net.delta_epoch(targets, noised, perms)
+        net.energy_profiles(targets, want_energies=False)
+        dt = time.perf_counter() - t0
+        if ep >= 2:
+            times.append(dt * 1e3)
+    net.close()
+    return float(np.mean(times))
 
 
 if __name__ == "__main__":

@@ -113,3 +113,38 @@ def test_baseline_size_config3_sample(built):
     assert ((res.Stable == 1) | (res.NumSteps == 101)).all()
     assert (res.NumSteps >= 2).all() and (res.NumSteps <= 101).all()
     net.close()
+
+
+@pytest.mark.parametrize("n,p,b", [(8192, 24, 6), (16384, 16, 3), (5000, 60, 12)])
+def test_large_dimensions(built, n, p, b):
+    """UPT=32 / 64 register tilings (N up to 16384, BASELINE config 5 size) and a dimension that is not a
+    multiple of the tile, against the exact-integer oracle."""
+    onet, k2, pool, probes, targets = make_problem(n, p, b, 77, pool_rows=100)
+    ores = onet.relax_batch(probes.copy(), pool, threads=8, want_energies=False, fast_k2=k2)
+    net = gpu_net(n)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(targets))
+    res = net.relax_batch(probes, pool, dedup=True)
+    assert_relax_equal(res, ores, n)
+    assert np.array_equal(res.MarginHits, ores["margin_hits"])
+    net.close()
+
+
+def test_delta_epoch_config5_size(built):
+    """One Delta epoch at N=16384 (2 GiB W): relaxed copies and W bit-exact against the oracle."""
+    n, p = 16384, 6
+    rng = orc.Rng(78)
+    t = rng.generate_states(0, n, p)
+    noised = t.copy()
+    for s in range(p):
+        rng.apply_noise(1, 0.05, noised[s])
+    perms = rng.fresh_perms(n, p)
+    onet = orc.Net(n)
+    onet.hebbian(t)                      # a non-trivial W to sweep against
+    net = gpu_net(n)
+    net.hebbian_epoch(t)
+    rel_o = onet.delta(t, noised, perms)
+    rel_g = net.delta_epoch(t, noised, perms)
+    assert np.array_equal(rel_g, orc.pack(rel_o))
+    assert np.array_equal(net.GetMatrix(), onet.w)
+    net.close()

@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--targets", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-delta", action="store_true", help="skip the Delta-rule epoch timing")
+    ap.add_argument("--columns", default="f64", choices=["f64", "f32"], help="column stream of the relaxation kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -146,7 +147,8 @@ def main():
     _, probes, _ = synth(n, p, b, 0x5EED + 3 + 1000 * (rank + 1))
     targets, _, pool = synth(n, p, 1, 0x5EED + 3)  # same W / schedule on every rank
     net = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
-        hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).Build()
+        hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).SetColumnStream(
+        1 if args.columns == "f32" else 0).Build()
     net.LearnStates(targets)
     # pinned host staging for the e2e leg
     probes_pinned = torch.from_numpy(probes).pin_memory()

@@ -78,6 +78,9 @@ struct hn_handle_s {
     double* W = nullptr;
     double* WT = nullptr;
     double* dW = nullptr;
+    float* W32 = nullptr;       // float32 shadow of the column matrix (HN_COLUMNS_F32)
+    bool w32_valid = false;
+    double maxabs = 0;
     bool w_symmetric = true;   // W known symmetric -> column k == row k
     bool margin_valid = false;
     double tau_base = 0, tau_flip = 0;
@@ -128,12 +131,16 @@ int ensure_margin(hn_handle h) {
     if (h->margin_valid) return HN_OK;
     HN_TRY(h->small.reserve(256));
     unsigned long long* d = h->small.as<unsigned long long>();
-    HN_CUDA_TRY(cudaMemsetAsync(d, 0, 8, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(d, 0, 16, h->st));
     rowabs_max_kernel<<<h->N, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, d);
     HN_CUDA_TRY(cudaGetLastError());
-    double r = 0;
-    HN_CUDA_TRY(cudaMemcpyAsync(&r, d, 8, cudaMemcpyDeviceToHost, h->st));
+    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->W, h->N, h->ldw, d + 1);
+    HN_CUDA_TRY(cudaGetLastError());
+    double rr[2] = {0, 0};
+    HN_CUDA_TRY(cudaMemcpyAsync(rr, d, 16, cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    const double r = rr[0];
+    h->maxabs = rr[1];
     const double u = 1.1102230246251565e-16;  // 2^-53
     // |incremental field - fresh DotUnitary field| <= (N [GEMM] + N/4+3 [fresh] + flips) * u * R; x2 safety
     h->tau_base = 2.0 * (1.25 * h->N + 4.0) * u * r;
@@ -142,7 +149,7 @@ int ensure_margin(hn_handle h) {
     return HN_OK;
 }
 
-void weights_changed(hn_handle h) { h->margin_valid = false; }
+void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; }
 
 // exact symmetry test of the resident W (decides whether column k can be read as row k)
 int detect_symmetry(hn_handle h) {
@@ -167,9 +174,36 @@ int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H,
     return launch_gemm_f64(a, b, e, count, h->N, h->N, h->st);
 }
 
-template <int UPT>
+// float32 shadow of the column matrix (W if symmetric else W^T), rebuilt after any weight change
+int ensure_w32(hn_handle h) {
+    if (h->w32_valid) return HN_OK;
+    const int64_t total = (int64_t)h->N * h->ldw;
+    if (!h->W32) HN_CUDA_TRY(cudaMalloc(&h->W32, sizeof(float) * (size_t)total));
+    to_f32_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(h->w_symmetric ? h->W : h->WT, h->W32, total);
+    HN_CUDA_TRY(cudaGetLastError());
+    h->w32_valid = true;
+    return HN_OK;
+}
+
+// point p at the column stream selected by the configuration and set the matching per-flip margin growth
+int select_columns(hn_handle h, RelaxParams& p) {
+    const double dscale = h->cfg.domain == HN_DOMAIN_BINARY ? 1.0 : 2.0;
+    p.tau_base = h->tau_base;
+    p.tau_flip = h->tau_flip;
+    if (h->cfg.column_stream == HN_COLUMNS_F32) {
+        HN_TRY(ensure_w32(h));
+        p.Wcol = h->W32;
+        // |fl32(w) - w| <= 2^-24 |w| (+ a denormal floor): each flip perturbs a field by at most delta*max|W|*2^-24
+        p.tau_flip += 2.0 * dscale * (h->maxabs * 5.9604644775390625e-08 + 1.5e-45);
+    } else {
+        p.Wcol = h->w_symmetric ? (const void*)h->W : (const void*)h->WT;
+    }
+    return HN_OK;
+}
+
+template <int UPT, typename CT>
 int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
-    auto kern = relax_kernel<UPT>;
+    auto kern = relax_kernel<UPT, CT>;
     const size_t smem = relax_smem_bytes(h->N, h->ldp, UPT);
     HN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
@@ -182,17 +216,22 @@ int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }
-int launch_relax(hn_handle h, const RelaxParams& p) {
+template <typename CT>
+int launch_relax_c(hn_handle h, const RelaxParams& p) {
     const int n = h->N;
-    if (n <= 256) return launch_relax_t<1>(h, p, 0);
-    if (n <= 512) return launch_relax_t<2>(h, p, 0);
-    if (n <= 1024) return launch_relax_t<4>(h, p, 0);
-    if (n <= 2048) return launch_relax_t<8>(h, p, 0);
-    if (n <= 4096) return launch_relax_t<16>(h, p, 0);
-    if (n <= 8192) return launch_relax_t<32>(h, p, 0);
-    if (n <= 16384) return launch_relax_t<64>(h, p, 0);
+    if (n <= 256) return launch_relax_t<1, CT>(h, p, 0);
+    if (n <= 512) return launch_relax_t<2, CT>(h, p, 0);
+    if (n <= 1024) return launch_relax_t<4, CT>(h, p, 0);
+    if (n <= 2048) return launch_relax_t<8, CT>(h, p, 0);
+    if (n <= 4096) return launch_relax_t<16, CT>(h, p, 0);
+    if (n <= 8192) return launch_relax_t<32, CT>(h, p, 0);
+    if (n <= 16384) return launch_relax_t<64, CT>(h, p, 0);
     set_error("relaxation kernel supports dimension <= 16384 (got %d)", n);
     return HN_E_INVALID;
+}
+int launch_relax(hn_handle h, RelaxParams& p) {
+    HN_TRY(select_columns(h, p));
+    return h->cfg.column_stream == HN_COLUMNS_F32 ? launch_relax_c<float>(h, p) : launch_relax_c<double>(h, p);
 }
 
 // upload permutations [rows][N] (host, dense) into one device buffer:
@@ -255,13 +294,13 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
 
     RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
-    p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;
+    p.Wrow = h->W;
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
     p.probes = d_probes; p.perm_pool = d_pool; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n_pool;
     p.offsets = serial ? nullptr : d_offsets;
     p.B = B; p.max_iter = h->cfg.max_relax_iterations; p.max_unstable = h->cfg.max_relax_unstable_units;
     p.domain = h->cfg.domain; p.check_stability = 1; p.serial_stream = serial ? 1 : 0;
-    p.tau_base = h->tau_base; p.tau_flip = h->tau_flip;
+    
     p.final_states = h->finals.as<uint64_t>(); p.num_steps = h->steps.as<int32_t>();
     p.stable = h->stable.as<uint8_t>(); p.flips = h->flips.as<int32_t>(); p.margin_hits = h->margin.as<int32_t>();
     p.distances = (want_dist && h->P > 0) ? h->dist.as<int32_t>() : nullptr;
@@ -476,11 +515,11 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
     HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
     RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
-    p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;
+    p.Wrow = h->W;
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
     p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n;
     p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.max_unstable = 0; p.domain = h->cfg.domain;
-    p.check_stability = 0; p.serial_stream = 0; p.tau_base = h->tau_base; p.tau_flip = h->tau_flip;
+    p.check_stability = 0; p.serial_stream = 0; 
     p.final_states = h->bitsC.as<uint64_t>();
     p.work_counter = d_small; p.status = d_small + 1;
     HN_TRY(launch_relax(h, p));
@@ -564,7 +603,7 @@ void hn_default_config(hn_config* cfg) {
     cfg->max_relax_iterations = 100;
     cfg->learning_rate = 1.0;
     cfg->device = 0;
-    cfg->reserved = 0;
+    cfg->column_stream = HN_COLUMNS_F64;
 }
 
 int hn_create(const hn_config* cfg, hn_handle* out) {
@@ -578,6 +617,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     if (cfg->dimension > 65535) { set_error("dimension %d exceeds 65535 (uint16 unit indices)", cfg->dimension); return HN_E_INVALID; }
     if (cfg->domain != HN_DOMAIN_BIPOLAR && cfg->domain != HN_DOMAIN_BINARY) { set_error("unknown domain %d", cfg->domain); return HN_E_INVALID; }
     if (cfg->max_relax_iterations <= 0) { set_error("max_relax_iterations must be positive"); return HN_E_INVALID; }
+    if (cfg->column_stream != HN_COLUMNS_F64 && cfg->column_stream != HN_COLUMNS_F32) { set_error("unknown column_stream %d", cfg->column_stream); return HN_E_INVALID; }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev <= 0) {
@@ -635,6 +675,7 @@ int hn_destroy(hn_handle h) {
     for (DevBuf* b : bufs) b->release();
     if (h->W) cudaFree(h->W);
     if (h->WT) cudaFree(h->WT);
+    if (h->W32) cudaFree(h->W32);
     if (h->dW) cudaFree(h->dW);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
@@ -896,11 +937,11 @@ int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint
     HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
     RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
-    p.Wcol = h->w_symmetric ? h->W : h->WT; p.Wrow = h->W;
+    p.Wrow = h->W;
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
     p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv;
     p.ldp = h->ldp; p.n_pool = n; p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.domain = h->cfg.domain;
-    p.check_stability = 0; p.tau_base = h->tau_base; p.tau_flip = h->tau_flip;
+    p.check_stability = 0; 
     p.final_states = h->bitsC.as<uint64_t>(); p.work_counter = d_small; p.status = d_small + 1;
     HN_TRY(launch_relax(h, p));
     HN_CUDA_TRY(cudaMemcpyAsync(states_packed, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));

@@ -141,6 +141,21 @@ __global__ void rowabs_max_kernel(const double* __restrict__ w, int n, int ld, u
     if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(r));
 }
 
+// max_ij |W_ij| (per-flip rounding bound of the float32 column stream); atomicMax on the bits
+__global__ void maxabs_kernel(const double* __restrict__ w, int n, int ld, unsigned long long* out) {
+    double m = 0.0;
+    const int64_t total = (int64_t)n * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(w[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+// float32 (round-to-nearest) shadow of a padded float64 matrix, same leading dimension
+__global__ void to_f32_kernel(const double* __restrict__ w, float* __restrict__ w32, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        w32[i] = __double2float_rn(w[i]);
+}
+
 // ---- inverse permutations: inv[row][perm[row][i]] = i -----------------------
 __global__ void invert_perm_kernel(const uint16_t* __restrict__ perm, uint16_t* __restrict__ inv, int n,
                                    int ldp, int rows) {

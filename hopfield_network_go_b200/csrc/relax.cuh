@@ -32,7 +32,7 @@ struct RelaxParams {
     int N;               // dimension
     int ldw;             // leading dimension of W / WT (multiple of 16, zero padded)
     int words;           // 64-bit words per packed state
-    const double* Wcol;  // row k of this matrix == column k of W  (W if symmetric else W^T)
+    const void* Wcol;    // row k of this matrix == column k of W  (W if symmetric else W^T); float64 or float32 shadow
     const double* Wrow;  // W: row k . s gives h_k (exact recomputation)
     const double* H0;    // [B][ldh] initial fields (from the GEMM)
     int ldh;
@@ -48,7 +48,7 @@ struct RelaxParams {
     int domain;
     int check_stability;  // 0: UpdateState semantics (exactly max_iter sweeps, no test)
     int serial_stream;    // 1: one CTA walks the probes in order, offsets = running sweep count
-    double tau_base, tau_flip;
+    double tau_base, tau_flip;  // margin tau(F) = tau_base + tau_flip * F (tau_flip includes the float32 stream bound)
     // outputs (device)
     uint64_t* final_states;  // [B][words]
     int32_t* num_steps;      // [B]
@@ -106,6 +106,7 @@ constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
 #ifndef RELAX_MIN_CTAS
 #define RELAX_MIN_CTAS 3
 #endif
+constexpr int RELAX_TAU_STEP = 256;
 
 // Dynamic shared memory layout (see relax_smem_bytes):
 //   s_bits  [nbw, padded to 4]   uint32  packed state (exact path, outputs)
@@ -129,7 +130,7 @@ static inline size_t relax_smem_bytes(int N, int ldp, int upt) {
     return (size_t)((nbw + 3) / 4 * 4) * 4 * 2 + (size_t)((ldp + 7) / 8 * 8) * 2 * 2;
 }
 
-template <int UPT>
+template <int UPT, typename CT>
 __global__ void __launch_bounds__(RELAX_THREADS, (UPT <= 16 ? RELAX_MIN_CTAS : 1))
 relax_kernel(RelaxParams p) {
     constexpr int VEC = RelaxCfg<UPT>::VEC;
@@ -152,9 +153,10 @@ relax_kernel(RelaxParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N;
     const double dscale = p.domain == HN_DOMAIN_BINARY ? 1.0 : 2.0;
-    // constant margin for the whole relaxation: tau(flips) at its largest possible flip count
-    const double tau = p.tau_base + p.tau_flip * ((double)p.max_iter * (double)N);
-    const int T = __double2hiint(tau) + 1;
+    // Margin threshold on the hi word, valid for the next RELAX_TAU_STEP flips: T(F) = hi32(tau(F + STEP)) + 1.
+    // It is refreshed every RELAX_TAU_STEP flips (tau grows with the flip count).
+    auto thr = [&](int f) -> int { return __double2hiint(p.tau_base + p.tau_flip * (double)(f + RELAX_TAU_STEP)) + 1; };
+    int T = thr(0);
     int red_buf = 0;
 
     auto unit_of = [&](int c, int e) -> int { return (c * RELAX_THREADS + tid) * VEC + e; };
@@ -205,6 +207,7 @@ relax_kernel(RelaxParams p) {
         const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(p.probes + (size_t)pi * p.words);
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
+        T = thr(0);
         double h[UPT];     // true local fields of my units
         int sw[UPT];       // per unit: 0x80000000 when the bit is clear (v = -1), else 0: hi32(h) ^ sw = hi32(h*v)
 #pragma unroll
@@ -237,9 +240,6 @@ relax_kernel(RelaxParams p) {
         }
 
         int flips = 0, margin = 0, sweeps = 0, is_stable = 0, pool_fail = 0;
-        const bool timing = (p.variant & 256) != 0;
-        long long tph[6] = {0, 0, 0, 0, 0, 0}, tl = timing ? clock64() : 0;
-#define HN_TICK(i) if (timing) { const long long tn = clock64(); tph[i] += tn - tl; tl = tn; }
         for (int sweep = 0; sweep < p.max_iter; sweep++) {
             const long long row = rowbase + sweep;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
@@ -264,7 +264,6 @@ relax_kernel(RelaxParams p) {
             __syncthreads();
 
             int base = 0;  // next position of the sweep order to examine
-            HN_TICK(5)
             for (;;) {
                 // ---- scan ahead (every warp, redundantly): first set bit of the bitmap at position >= base ----
                 int found = -1;
@@ -280,7 +279,6 @@ relax_kernel(RelaxParams p) {
                         break;
                     }
                 }
-                HN_TICK(0)
                 if (found < 0) break;  // sweep finished
                 base = found + 1;
                 const int k = s_perm[found];
@@ -295,9 +293,7 @@ relax_kernel(RelaxParams p) {
                         s_flag = ((((a & 0x7FFFFFFF) < T) ? 2 : 0) | (sg ? 0 : 1));
                     }
                 }
-                HN_TICK(1)
                 __syncthreads();
-                HN_TICK(2)
                 const int fl = s_flag;
                 const uint32_t ob = (uint32_t)fl & 1u;
                 uint32_t nb = ob ^ 1u;
@@ -310,7 +306,6 @@ relax_kernel(RelaxParams p) {
 
                 // ---- flip unit k: h += d * W[:,k] over my units; toggle the bitmap where candidacy changed ----
                 const double d = nb ? dscale : -dscale;
-                const double* col = p.Wcol + (size_t)k * p.ldw;
                 {   // owner: new bit into its sign word and the packed state
                     const int ch = k / VEC, ke = k % VEC;
                     if ((ch % RELAX_THREADS) == tid) {
@@ -321,16 +316,26 @@ relax_kernel(RelaxParams p) {
                         s_bits[k >> 5] ^= 1u << (k & 31);
                     }
                 }
-                auto flip_pass = [&](auto full_tag) {
-                    constexpr bool FULL = decltype(full_tag)::value;  // every chunk lies inside the padded row
+                {   // one coalesced pass over column k (row k of Wcol), fused into the register-resident fields
+                    const CT* col = reinterpret_cast<const CT*>(p.Wcol) + (size_t)k * p.ldw;
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         const int u0 = unit_of(c, 0);
                         double w[VEC];
-                        if (FULL || u0 < p.ldw) {
-                            if (VEC == 4) {
-                                // 256-bit load: 8% faster than two 128-bit loads here; the column stream is
-                                // bounded by the L2->SM fabric (profiles/r01_relax_v4_ncu_summary.txt)
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) w[e] = 0.0;
+                        if (u0 < p.ldw) {
+                            if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
+                                if (VEC == 4) {
+                                    const float4 x = __ldg(reinterpret_cast<const float4*>(col + u0));
+                                    w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+                                } else if (VEC == 2) {
+                                    const float2 x = __ldg(reinterpret_cast<const float2*>(col + u0));
+                                    w[0] = x.x; w[1] = x.y;
+                                } else {
+                                    w[0] = __ldg(col + u0);
+                                }
+                            } else if (VEC == 4) {   // 256-bit loads (8% faster than two 128-bit loads here)
                                 asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
                                              : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(col + u0));
                             } else if (VEC == 2) {
@@ -339,16 +344,12 @@ relax_kernel(RelaxParams p) {
                             } else {
                                 w[0] = __ldg(col + u0);
                             }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < VEC; e++) w[e] = 0.0;
                         }
 #pragma unroll
                         for (int e = 0; e < VEC; e++) h[c * VEC + e] = fma(d, w[e], h[c * VEC + e]);
                     }
-                };
-                if (p.ldw == NU) flip_pass(std::true_type{}); else flip_pass(std::false_type{});
-                HN_TICK(3)
+                }
+                if (((flips + 1) & (RELAX_TAU_STEP - 1)) == 0) T = thr(flips + 1);  // candidacy below is re-derived with it
                 {
                     const mask_t nm = cand_mask();
                     mask_t ch = nm ^ cm;
@@ -361,9 +362,7 @@ relax_kernel(RelaxParams p) {
                     }
                 }
                 flips++;
-                HN_TICK(4)
                 __syncthreads();  // bitmap complete before anyone scans it
-                HN_TICK(2)
             }
             sweeps++;
 
@@ -420,7 +419,6 @@ relax_kernel(RelaxParams p) {
             if (p.flips) p.flips[pi] = flips;
             if (p.margin_hits) p.margin_hits[pi] = margin;
             if (p.serial_stream) { s_probe = pi + 1; s_rowbase = rowbase + sweeps; }
-            if (timing) for (int i = 0; i < 6; i++) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 7) + i, (unsigned long long)tph[i]);
         }
         // Manhattan distance with inversion to every target (DistanceMeasure.go:28-42):
         // bipolar 2*min(dH, N-dH), binary min(dH, N-dH); exact integers.

@@ -312,6 +312,7 @@ class HopfieldNetworkBuilder:
         self.allowIntensiveDataCollection = False
         self.seed = None     # additive: SetSeed
         self.device = 0      # additive: SetDevice
+        self.columnStream = capi.HN_COLUMNS_F64  # additive: SetColumnStream
 
     def SetRandMatrixInit(self, f): self.randMatrixInit = f; return self
     def SetNetworkDimension(self, d): self.dimension = d; return self
@@ -332,6 +333,7 @@ class HopfieldNetworkBuilder:
     def SetAllowIntensiveDataCollection(self, f): self.allowIntensiveDataCollection = f; return self
     def SetSeed(self, s): self.seed = s; return self
     def SetDevice(self, d): self.device = d; return self
+    def SetColumnStream(self, m): self.columnStream = m; return self
 
     def Build(self) -> HopfieldNetwork:
         # the four panics of HopfieldNetworkBuilder.go:215-229, as Python exceptions with the same text
@@ -345,7 +347,7 @@ class HopfieldNetworkBuilder:
             raise ValueError("HopfieldNetworkBuilder encountered an error during build! unitsUpdatedPerStep must be a positive integer that is smaller than the network dimension!")
         cfg = capi.HnConfig(self.dimension, self.domain, int(self.forceSymmetric), int(self.forceZeroDiagonal),
                             self.maximumRelaxationUnstableUnits, self.maximumRelaxationIterations,
-                            self.learningRate, self.device, 0)
+                            self.learningRate, self.device, self.columnStream)
         import time
         seed = self.seed if self.seed is not None else time.time_ns()  # :231 time-seeded unless SetSeed
         net = HopfieldNetwork(cfg, self.epochs, self.learningRule if self.learningRule is not None else 0,

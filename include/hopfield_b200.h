@@ -96,8 +96,19 @@ typedef struct hn_config {
     int32_t max_relax_iterations;      /* SetMaximumRelaxationIterations (default 100)        */
     double  learning_rate;             /* SetLearningRate (default 1.0)                       */
     int32_t device;                    /* CUDA device ordinal (additive extension)            */
-    int32_t reserved;
+    int32_t column_stream;             /* HN_COLUMNS_F64 (default) or HN_COLUMNS_F32, see below */
 } hn_config;
+
+/* Column stream of the relaxation kernel (additive extension; results are bit-identical in both modes).
+ * A flip of unit k adds +-delta*W[:,k] to the resident float64 fields.
+ *   HN_COLUMNS_F64  the column is read from the float64 matrix (8N bytes per flip).
+ *   HN_COLUMNS_F32  the column is read from a float32-rounded shadow copy of W (4N bytes per flip; the shadow of
+ *                   a 4096-unit network fits the L2).  The fields stay float64; the extra rounding error is
+ *                   bounded by flips * delta * max|W| * 2^-24 and added to the decision margin tau, and every
+ *                   decision inside the margin is re-evaluated exactly on the float64 matrix in the reference's
+ *                   summation order, so final states, step counts, flags and distances do not change.        */
+#define HN_COLUMNS_F64 0
+#define HN_COLUMNS_F32 1
 
 typedef struct hn_handle_s* hn_handle;
 

@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--targets", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-delta", action="store_true", help="skip the Delta-rule epoch timing")
+    ap.add_argument("--no-f32", action="store_true", help="skip the extra float32-column-stream measurement")
     ap.add_argument("--columns", default="f64", choices=["f64", "f32"], help="column stream of the relaxation kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -205,10 +206,23 @@ def main():
     h2d = probes_np.nbytes + pool.nbytes
     d2h = res.FinalStates.nbytes + res.NumSteps.nbytes + res.Stable.nbytes + res.DistancesToTargets.nbytes + \
         res.Flips.nbytes + res.MarginHits.nbytes + res.AttractorId.nbytes + 2 * 4 * len(res.UniqueFirst) + res.StateHash.nbytes
-    tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t))], device="cuda", dtype=torch.float64)
+    # the same step with the float32 column stream (bit-identical results, half the column bytes): reported beside
+    # the headline, never as the headline
+    f32_ms = None
+    if args.columns == "f64" and not args.no_f32:
+        net32 = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
+            hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).SetColumnStream(1).Build()
+        net32.SetMatrix(net.GetMatrix())
+        net32.SetLearnedStates(targets)
+        net32.upload_perm_pool(pool)
+        net32.upload_probes(probes_np)
+        net32.relax_resident(dedup=True)
+        f32_ms = net32.relax_resident(dedup=True)
+        net32.close()
+    tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t)), f32_ms or 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    step_ms_max, relax_ms_max, e2e_max = [float(x) for x in tmax.cpu()]
+    step_ms_max, relax_ms_max, e2e_max, f32_ms_max = [float(x) for x in tmax.cpu()]
     if rank == 0:
         peaks = {}
         try:
@@ -225,15 +239,26 @@ def main():
                 "e2e": {"value": world * b / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             "traffic": None, "kernel": "relax_kernel<16>",
+                             "traffic": None, "kernel": "relax_kernel<16,double>",
+                             "note": "per GPU; algorithmic bytes 8N per flip + 8N per sweep (SURVEY 8d) over the relaxation "
+                                     "kernel time; >1 because columns are served from L2 (see traffic); the kernel is bounded "
+                                     "by the L2->SM fabric (~8.5 TB/s), profiles/r01_relax_v4_ncu_summary.txt",
                              "peak_source": "measured" if peaks else "fallback",
                              "algorithmic_bytes_per_launch": int(alg_bytes), "flips_per_probe": flips / b,
                              "sweeps_per_probe": sweeps / b},
                 "clocks": sampler.summary(), "wall_s": wall,
                 "stage_ms_per_step": {"fields_gemm": float(np.mean(fields_ms)), "relax": float(np.mean(relax_ms)),
                                       "dedup": float(np.mean(post_ms))},
+                "value_f32_column_stream": (world * b / (f32_ms_max * 1e-3)) if f32_ms_max > 0 else None,
                 "margin_hits_per_probe": out.total_margin_hits / b,
                 "unique_attractors": int(n_unique_global if n_unique_global is not None else out.n_unique)}
+        try:   # DRAM bytes of the relaxation kernel from the committed ncu capture of this command (per launch)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_relax_traffic.json")))
+            if tr.get("probes_per_launch") == b and tr.get("N") == n:
+                line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+                line["roofline"]["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         if not args.no_delta:
             line["delta_epoch_ms"] = {
                 "config2_N1024_P100_inversion0.1": measure_delta_epoch(hn, local, 1024, 100, 5),

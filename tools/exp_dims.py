@@ -2,7 +2,7 @@
 import json, os, subprocess, sys
 for n, p, b in ((1024, 100, 65536), (2048, 200, 32768), (4096, 400, 16384), (8192, 800, 4096)):
     r = subprocess.run([sys.executable, "bench.py", "--dim", str(n), "--targets", str(p), "--probes", str(b), "--steps", "1",
-                        "--warmup", "1", "--no-cpu", "--no-delta"] + (["--columns", os.environ["COLS"]] if "COLS" in os.environ else []), capture_output=True, text=True, env=dict(os.environ, **{k: v for k, v in [a.split("=") for a in sys.argv[1:]]}))
+                        "--warmup", "1", "--no-cpu", "--no-delta", "--no-f32"] + (["--columns", os.environ["COLS"]] if "COLS" in os.environ else []), capture_output=True, text=True, env=dict(os.environ, **{k: v for k, v in [a.split("=") for a in sys.argv[1:]]}))
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
         ms = d["stage_ms_per_step"]["relax"]

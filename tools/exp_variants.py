@@ -4,7 +4,7 @@ variants = sys.argv[2:] or ["0"]
 probes = sys.argv[1] if len(sys.argv) > 1 else "16384"
 for v in variants:
     env = dict(os.environ, HN_RELAX_VARIANT=v)
-    r = subprocess.run([sys.executable, "bench.py", "--probes", probes, "--steps", "1", "--warmup", "1", "--no-cpu", "--no-delta"],
+    r = subprocess.run([sys.executable, "bench.py", "--probes", probes, "--steps", "1", "--warmup", "1", "--no-cpu", "--no-delta", "--no-f32"],
                        capture_output=True, text=True, env=env)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])

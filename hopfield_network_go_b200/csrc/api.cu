@@ -438,8 +438,8 @@ int contraction_hebbian(hn_handle h, const uint64_t* d_states, int n, ValueMap v
     return launch_gemm_f64(a, a, e, h->N, h->N, n, h->st);
 }
 
-struct OpBitsDiffG {  // scale * (val_a(bitA) - val_b(bitB))
-    const uint64_t* a; const uint64_t* b; int words; int rows; int K; double alo, ahi, blo, bhi, scale;
+struct OpBitsDiffG {  // scale * kscale[k] * (val_a(bitA) - val_b(bitB)); kscale == nullptr -> 1
+    const uint64_t* a; const uint64_t* b; int words; int rows; int K; double alo, ahi, blo, bhi, scale; const double* kscale;
     __device__ __forceinline__ void load8(int row, int k0, double (&v)[8]) const {
         unsigned ba = 0, bb = 0;
         if (row < rows && k0 < K) {
@@ -450,7 +450,7 @@ struct OpBitsDiffG {  // scale * (val_a(bitA) - val_b(bitB))
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const double va = ((ba >> e) & 1u) ? ahi : alo, vb = ((bb >> e) & 1u) ? bhi : blo;
-            v[e] = (row < rows && (k0 + e) < K) ? scale * (va - vb) : 0.0;
+            v[e] = (row < rows && (k0 + e) < K) ? (kscale ? scale * kscale[k0 + e] : scale) * (va - vb) : 0.0;
         }
     }
 };
@@ -491,7 +491,7 @@ int hebbian_epoch_impl(hn_handle h, const uint64_t* states, int n, ValueMap vm) 
 // tvm: value map of the target states as the rule sees them (mapped rules re-activate);
 // the relaxed copies always carry the network domain's values.
 int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised, const uint16_t* perms, int n,
-                     uint64_t* relaxed_out, ValueMap tvm) {
+                     uint64_t* relaxed_out, ValueMap tvm, bool thermal = false) {
     const int N = h->N, words = h->words;
     HN_TRY(ensure_margin(h));
     HN_TRY(refresh_wt(h));
@@ -534,7 +534,24 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
     transpose_bits_kernel<<<tg, 256, 0, h->st>>>(h->bitsC.as<uint64_t>(), h->bitsCT.as<uint64_t>(), N, words, n, pwords);
     HN_CUDA_TRY(cudaGetLastError());
     const ValueMap rvm = domain_values(h->cfg.domain);
-    OpBitsDiffG a{h->bitsAT.as<uint64_t>(), h->bitsCT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi, rvm.lo, rvm.hi, 0.5};
+    const double* kscale = nullptr;
+    if (thermal) {
+        // f_mu = exp(-||W t_mu||_2 / (1 + ||W||_F)) with the CURRENT W (LearningRule.go:134,149-150)
+        const int np = 1024;
+        HN_TRY(h->partial.reserve(sizeof(double) * (np + 2 + (size_t)n)));
+        double* part = h->partial.as<double>();
+        sumsq_partial_kernel<<<np, RED_THREADS, 0, h->st>>>(h->W, N, h->ldw, part);
+        sumsq_final_kernel<<<1, RED_THREADS, 0, h->st>>>(part, np, part + np);
+        OpBits ta{h->bitsA.as<uint64_t>(), words, n, N, tvm.lo, tvm.hi};
+        OpF64 tb{h->W, h->ldw, N};
+        EpiStore te{h->H.as<double>(), h->ldw, n, N};
+        HN_TRY(launch_gemm_f64(ta, tb, te, n, N, N, h->st));
+        thermal_factor_kernel<<<n, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, N, part + np, part + np + 2);
+        HN_CUDA_TRY(cudaGetLastError());
+        kscale = part + np + 2;
+    }
+    OpBitsDiffG a{h->bitsAT.as<uint64_t>(), h->bitsCT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi, rvm.lo, rvm.hi,
+                  thermal ? 1.0 : 0.5, kscale};
     OpBits b{h->bitsAT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi};
     EpiStore e{h->dW, h->ldw, N, N};
     HN_TRY(launch_gemm_f64(a, b, e, N, N, n, h->st));
@@ -746,6 +763,15 @@ int hn_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* n
     return delta_epoch_impl(h, states_packed, noised_packed, perms, n, relaxed_out, domain_values(h->cfg.domain));
 }
 
+int hn_thermal_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* noised_packed,
+                           const uint16_t* perms, int32_t n, uint64_t* relaxed_out) {
+    if (!check_handle(h, "hn_thermal_delta_epoch")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed || !noised_packed || !perms) { set_error("hn_thermal_delta_epoch: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    HN_TRY(validate_pool_host(h, perms, n));
+    return delta_epoch_impl(h, states_packed, noised_packed, perms, n, relaxed_out, domain_values(h->cfg.domain), true);
+}
+
 int hn_enforce_constraints(hn_handle h) {
     if (!check_handle(h, "hn_enforce_constraints")) return HN_E_INVALID;
     HN_TRY(set_device(h));
@@ -801,15 +827,12 @@ int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n, int32
         set_error("HopfieldNetworkBuilder encountered an error during build! learningNoiseRatio must be in range [0.0, 1.0]!");
         return HN_E_INVALID;
     }
-    if (rule == HN_RULE_THERMAL_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA) {
-        set_error("thermal delta rules are not implemented on the device path (SURVEY 8f #3)");
-        return HN_E_INVALID;
-    }
     if (rule < 0 || rule > 5 || (method != HN_METHOD_FULL_SET && method != HN_METHOD_ITERATIVE_BATCH)) {
         set_error("unknown learning rule %d / method %d", rule, method);
         return HN_E_INVALID;
     }
-    const bool is_delta = rule == HN_RULE_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_DELTA;
+    const bool is_thermal = rule == HN_RULE_THERMAL_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA;
+    const bool is_delta = rule == HN_RULE_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_DELTA || is_thermal;
     if (is_delta && !rng) { set_error("hn_learn_states: the delta rule needs an rng"); return HN_E_INVALID; }
     HN_TRY(set_device(h));
     const int N = h->N, words = h->words;
@@ -818,7 +841,7 @@ int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n, int32
     // LearningRule.go:80); bipolarMappedDelta with the Bipolar manager (:119).
     ValueMap tvm = domain_values(h->cfg.domain);
     if (rule == HN_RULE_BIPOLAR_MAPPED_HEBBIAN) tvm = ValueMap{0.0, 1.0};
-    if (rule == HN_RULE_BIPOLAR_MAPPED_DELTA) tvm = ValueMap{-1.0, 1.0};
+    if (rule == HN_RULE_BIPOLAR_MAPPED_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA) tvm = ValueMap{-1.0, 1.0};
     const ValueMap nvm = domain_values(h->cfg.domain);
     int produced = 0, last_epoch = 0;
     std::vector<uint64_t> noised;
@@ -844,7 +867,7 @@ int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n, int32
                     for (int i = 0; i < N; i++) pr[i] = (uint16_t)i;
                     HN_TRY(hn_rng_shuffle_u16(rng, pr, N));
                 }
-                HN_TRY(delta_epoch_impl(h, states_packed, noised.data(), perms.data(), cnt, nullptr, tvm));
+                HN_TRY(delta_epoch_impl(h, states_packed, noised.data(), perms.data(), cnt, nullptr, tvm, is_thermal));
             }
             // per-target diagnostics (LearningMethod.go:45-53) on the ORIGINAL states in the network domain
             stab.resize((size_t)cnt);

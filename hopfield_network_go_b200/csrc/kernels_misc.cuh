@@ -156,6 +156,18 @@ __global__ void to_f32_kernel(const double* __restrict__ w, float* __restrict__ 
         w32[i] = __double2float_rn(w[i]);
 }
 
+// thermal Delta factors (LearningRule.go:134,149-150): f[s] = exp(-wf * ||H[s,:]||_2), wf = 1/(1 + ||W||_F)
+// nrm[0] holds ||W||_F (sumsq_final_kernel). One CTA per state.
+__global__ void __launch_bounds__(RED_THREADS)
+thermal_factor_kernel(const double* __restrict__ H, int ldh, int n, const double* __restrict__ nrm, double* __restrict__ f) {
+    __shared__ double sm[RED_THREADS / 32];
+    const int s = blockIdx.x;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += RED_THREADS) { const double x = H[(size_t)s * ldh + i]; acc = fma(x, x, acc); }
+    const double r = block_reduce_sum_det(acc, sm);
+    if (threadIdx.x == 0) f[s] = exp(-1.0 * (1.0 / (1.0 + nrm[0])) * sqrt(r) / 1.0);
+}
+
 // ---- inverse permutations: inv[row][perm[row][i]] = i -----------------------
 __global__ void invert_perm_kernel(const uint16_t* __restrict__ perm, uint16_t* __restrict__ inv, int n,
                                    int ldp, int rows) {

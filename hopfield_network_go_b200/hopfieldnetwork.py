@@ -194,6 +194,13 @@ class HopfieldNetwork:
         check(capi.load().hn_delta_epoch(self._h, ptr(p), ptr(q), ptr(pm), p.shape[0], ptr(rel)))
         return rel
 
+    def thermal_delta_epoch(self, states, noised, perms) -> np.ndarray:
+        p, q = self._packed(states), self._packed(noised)
+        pm = np.ascontiguousarray(perms, dtype=np.uint16)
+        rel = np.empty_like(p)
+        check(capi.load().hn_thermal_delta_epoch(self._h, ptr(p), ptr(q), ptr(pm), p.shape[0], ptr(rel)))
+        return rel
+
     def enforce_constraints(self) -> None:
         check(capi.load().hn_enforce_constraints(self._h))
 

@@ -74,8 +74,8 @@ extern "C" {
 #define HN_RULE_BIPOLAR_MAPPED_HEBBIAN       1
 #define HN_RULE_DELTA                        2
 #define HN_RULE_BIPOLAR_MAPPED_DELTA         3
-#define HN_RULE_THERMAL_DELTA                4  /* not implemented on device */
-#define HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA 5  /* not implemented on device */
+#define HN_RULE_THERMAL_DELTA                4
+#define HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA 5
 /* LearningMethod.go:22-25 */
 #define HN_METHOD_FULL_SET        0
 #define HN_METHOD_ITERATIVE_BATCH 1
@@ -164,6 +164,12 @@ int hn_hebbian_epoch(hn_handle h, const uint64_t* states_packed, int32_t n);
  * enforceConstraints.                                                       */
 int hn_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* noised_packed,
                    const uint16_t* perms, int32_t n, uint64_t* relaxed_out);
+
+/* One application of the thermal Delta rule (LearningRule.go:129-158): as hn_delta_epoch, but every target's
+ * rank-one term is weighted by exp(-||W t||_2 / (1 + ||W||_F)) and the 0.5 factor is absent.  The weights are
+ * no longer integers: dW matches the reference within rounding of the summation order (1e-9 relative).       */
+int hn_thermal_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* noised_packed,
+                           const uint16_t* perms, int32_t n, uint64_t* relaxed_out);
 
 /* enforceConstraints (HopfieldNetwork.go:55-67) on the resident W. */
 int hn_enforce_constraints(hn_handle h);

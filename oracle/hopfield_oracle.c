@@ -328,6 +328,36 @@ void orc_delta(orc_net* net, const double* states, const double* noised, const u
     free(diff); free(relaxed); free(upd);
 }
 
+static void dlassq(int32_t n, const double* x, double* scale, double* sumsq);
+
+/* LearningRule.go:129-158.  mat.Norm(matrix, 2.0) = Frobenius (Dlange); MulVec = per-row DotUnitary (see header);
+ * mat.Norm(vector, 2) = Dnrm2 = scaled sum of squares. */
+void orc_thermal_delta(orc_net* net, const double* states, const double* noised, const uint16_t* perms,
+                       int32_t p, double* relaxed_out) {
+    int32_t n = net->n;
+    double* upd = (double*)calloc((size_t)n * n, sizeof(double));
+    double* relaxed = (double*)malloc(sizeof(double) * (size_t)p * n);
+    double* diff = (double*)malloc(sizeof(double) * n);
+    double* tv = (double*)malloc(sizeof(double) * n);
+    double weight_factor = 1 / (1 + orc_frobenius(net->w, n)); /* :134 */
+    memcpy(relaxed, noised, sizeof(double) * (size_t)p * n);
+    for (int32_t s = 0; s < p; s++) /* :138-144 */
+        orc_update_state(net, relaxed + (size_t)s * n, perms + (size_t)s * n);
+    for (int32_t s = 0; s < p; s++) { /* :146-153 */
+        const double* t = states + (size_t)s * n;
+        for (int32_t i = 0; i < n; i++) diff[i] = t[i] - relaxed[(size_t)s * n + i];
+        for (int32_t i = 0; i < n; i++) tv[i] = orc_dot_unitary(net->w + (size_t)i * n, t, n);
+        double scale = 0.0, ssq = 1.0;
+        dlassq(n, tv, &scale, &ssq);
+        double nrm = scale * sqrt(ssq);
+        double f = exp(-1.0 * weight_factor * nrm / (1.0));
+        rank_one(upd, n, f, diff, t);
+    }
+    apply_update(net, upd); /* :155-157 */
+    if (relaxed_out) memcpy(relaxed_out, relaxed, sizeof(double) * (size_t)p * n);
+    free(tv); free(diff); free(relaxed); free(upd);
+}
+
 /* gonum Dlassq (classic scaled sum of squares) */
 static void dlassq(int32_t n, const double* x, double* scale, double* sumsq) {
     for (int32_t i = 0; i < n; i++) {
@@ -391,9 +421,9 @@ static void apply_rule(orc_net* net, const double* states, int32_t p, int32_t ru
     int32_t n = net->n;
     double* mapped = NULL;
     const double* st = states;
-    if (rule == 1 || rule == 3) {
+    if (rule == 1 || rule == 3 || rule == 5) {
         /* bipolarMappedHebbian re-activates with the BINARY manager (sic, LearningRule.go:80),
-         * bipolarMappedDelta with the Bipolar manager (:119) */
+         * bipolarMappedDelta / bipolarMappedThermalDelta with the Bipolar manager (:119, :163) */
         mapped = (double*)malloc(sizeof(double) * (size_t)p * n);
         memcpy(mapped, states, sizeof(double) * (size_t)p * n);
         orc_activation(rule == 1 ? ORC_BINARY : ORC_BIPOLAR, mapped, p * n);
@@ -412,7 +442,8 @@ static void apply_rule(orc_net* net, const double* states, int32_t p, int32_t ru
             for (int32_t i = 0; i < n; i++) pr[i] = (uint16_t)i; /* getUnitIndices :71-77 */
             orc_rng_shuffle_u16(rng, pr, n);
         }
-        orc_delta(net, st, noised, perms, p, NULL);
+        if (rule >= 4) orc_thermal_delta(net, st, noised, perms, p, NULL);
+        else orc_delta(net, st, noised, perms, p, NULL);
         free(perms); free(noised);
     }
     free(mapped);

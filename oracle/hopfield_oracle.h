@@ -116,6 +116,10 @@ void orc_hebbian(orc_net* net, const double* states, int32_t p);
  *   relaxed_out: optional [p][n] */
 void orc_delta(orc_net* net, const double* states, const double* noised, const uint16_t* perms,
                int32_t p, double* relaxed_out);
+/* thermalDelta: LearningRule.go:129-158 with the RNG-derived inputs explicit (as orc_delta).
+ * weightFactor = 1/(1+||W||_F); per state f = exp(-weightFactor*||W t||_2 / 1.0); dW += f*(t-r) t^T (no 0.5). */
+void orc_thermal_delta(orc_net* net, const double* states, const double* noised, const uint16_t* perms,
+                       int32_t p, double* relaxed_out);
 /* Dense.Norm(2): Frobenius via Dlange/Dlassq */
 double orc_frobenius(const double* w, int32_t n);
 /* matrix.Scale(1/matrix.Norm(2), matrix): HopfieldNetwork.go:260; returns the norm */

@@ -207,6 +207,14 @@ class Net:
         lib().orc_delta(self.ref(), _p(s), _p(nz), _p(pm), C.c_int32(s.shape[0]), _p(rel))
         return rel
 
+    def thermal_delta(self, states, noised, perms):
+        s = np.ascontiguousarray(states, dtype=np.float64)
+        nz = np.ascontiguousarray(noised, dtype=np.float64)
+        pm = np.ascontiguousarray(perms, dtype=np.uint16)
+        rel = np.empty_like(s)
+        lib().orc_thermal_delta(self.ref(), _p(s), _p(nz), _p(pm), C.c_int32(s.shape[0]), _p(rel))
+        return rel
+
     def enforce_constraints(self):
         lib().orc_enforce_constraints(self.ref())
 

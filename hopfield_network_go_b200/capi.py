@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "hn_relax_resident", "hn_download_results", "hn_last_relax_timing", "hn_get_margin",
     "hn_pack_states_f64", "hn_unpack_states_f64", "hn_comm_unique_id", "hn_comm_attach", "hn_comm_detach",
     "hn_broadcast_weights", "hn_rng_create", "hn_rng_destroy", "hn_rng_uint64", "hn_rng_uint64n",
-    "hn_rng_float64", "hn_rng_norm_float64", "hn_rng_shuffle_u16", "hn_rng_perm_pool", "hn_rng_apply_noise",
+    "hn_rng_float64", "hn_rng_norm_float64", "hn_rng_shuffle_u16", "hn_rng_perm_pool", "hn_rng_apply_noise", "hn_rng_generate_states",
 ]
 
 
@@ -81,6 +81,7 @@ def load():
     L.hn_rng_shuffle_u16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hn_rng_perm_pool.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.hn_rng_apply_noise.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32]
+    L.hn_rng_generate_states.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p]
     L.hn_create.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_destroy.argtypes = [C.c_void_p]
     L.hn_set_weights.argtypes = [C.c_void_p, C.c_void_p]

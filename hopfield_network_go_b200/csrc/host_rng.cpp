@@ -169,4 +169,20 @@ int hn_rng_apply_noise(hn_rng r, int32_t noise_method, double noise_scale, doubl
     return HN_OK;
 }
 
+int hn_rng_generate_states(hn_rng r, int32_t dimension, int32_t count, double rand_min, double rand_max,
+                           uint64_t* packed_out) {
+    if (!r || !packed_out || dimension <= 0 || count < 0 || !(rand_min < rand_max)) {
+        hn::set_error("hn_rng_generate_states: bad argument");
+        return HN_E_INVALID;
+    }
+    const int words = (dimension + 63) / 64;
+    std::memset(packed_out, 0, sizeof(uint64_t) * (size_t)count * words);
+    for (int s = 0; s < count; s++)
+        for (int i = 0; i < dimension; i++) {
+            const double x = r->g.unit() * (rand_max - rand_min) + rand_min;  // distuv.Uniform.Rand
+            if (x > 0.0) packed_out[(size_t)s * words + (i >> 6)] |= 1ULL << (i & 63);  // activation: x <= 0 -> low
+        }
+    return HN_OK;
+}
+
 }  // extern "C"

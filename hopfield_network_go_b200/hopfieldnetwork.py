@@ -64,6 +64,12 @@ class Rand:
         assert state.dtype == np.float64 and state.flags.c_contiguous
         check(capi.load().hn_rng_apply_noise(self._h, method, scale, ptr(state), state.size))
 
+    def CreateStateCollection(self, dimension: int, count: int, rand_min=-1.0, rand_max=1.0) -> np.ndarray:
+        """states.StateGenerator.CreateStateCollection (states/StateGenerator.go:65-74), packed."""
+        out = np.zeros((count, words(dimension)), dtype=np.uint64)
+        check(capi.load().hn_rng_generate_states(self._h, dimension, count, rand_min, rand_max, ptr(out)))
+        return out
+
 
 @dataclass
 class LearnStateData:          # datacollector/LearnStateData.go:14-19

@@ -326,6 +326,11 @@ int      hn_rng_perm_pool(hn_rng r, int32_t dimension, int32_t n_rows, int32_t s
 int      hn_rng_apply_noise(hn_rng r, int32_t noise_method, double noise_scale,
                             double* state_f64, int32_t dimension);
 
+/* states.StateGenerator (states/StateGenerator.go:44-52, :65-74): `count` states whose elements are
+ * distuv.Uniform{min,max}.Rand() = Float64()*(max-min)+min followed by the domain activation, packed. */
+int      hn_rng_generate_states(hn_rng r, int32_t dimension, int32_t count, double rand_min, double rand_max,
+                                uint64_t* packed_out);
+
 #ifdef __cplusplus
 }
 #endif

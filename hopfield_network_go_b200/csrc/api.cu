@@ -201,18 +201,18 @@ int select_columns(hn_handle h, RelaxParams& p) {
     return HN_OK;
 }
 
-template <int UPT, typename CT>
+template <int UPT, typename CT, int THREADS = 256>
 int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
-    auto kern = relax_kernel<UPT, CT>;
+    auto kern = relax_kernel<UPT, CT, THREADS>;
     const size_t smem = relax_smem_bytes(h->N, h->ldp, UPT);
     HN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    HN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RELAX_THREADS, smem));
+    HN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
     if (occ < 1) occ = 1;
     int grid = p.serial_stream ? 1 : std::min(p.B, h->sms * occ);
     if (grid_cap > 0) grid = std::min(grid, grid_cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, RELAX_THREADS, smem, h->st>>>(p);
+    kern<<<grid, THREADS, smem, h->st>>>(p);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }
@@ -224,8 +224,8 @@ int launch_relax_c(hn_handle h, const RelaxParams& p) {
     if (n <= 1024) return launch_relax_t<4, CT>(h, p, 0);
     if (n <= 2048) return launch_relax_t<8, CT>(h, p, 0);
     if (n <= 4096) return launch_relax_t<16, CT>(h, p, 0);
-    if (n <= 8192) return launch_relax_t<32, CT>(h, p, 0);
-    if (n <= 16384) return launch_relax_t<64, CT>(h, p, 0);
+    if (n <= 8192) return launch_relax_t<16, CT, 512>(h, p, 0);     // more threads per probe, same 16 units each
+    if (n <= 16384) return launch_relax_t<16, CT, 1024>(h, p, 0);
     set_error("relaxation kernel supports dimension <= 16384 (got %d)", n);
     return HN_E_INVALID;
 }

@@ -100,11 +100,9 @@ __device__ __forceinline__ double exact_field_warp(const double* __restrict__ ro
     return __dadd_rn(pair, hi);
 }
 
-constexpr int RELAX_THREADS = 256;
-constexpr int RELAX_WARPS = RELAX_THREADS / 32;
 constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
 #ifndef RELAX_MIN_CTAS
-#define RELAX_MIN_CTAS 3
+#define RELAX_MIN_CTAS 4   // 64 registers per thread: +11% at N=4096, +18..26% at N<=2048 over 3 CTAs/SM
 #endif
 constexpr int RELAX_TAU_STEP = 256;
 
@@ -124,15 +122,17 @@ template <int UPT> struct RelaxCfg {
     static constexpr int VEC = UPT >= 4 ? 4 : UPT;   // contiguous units per ownership chunk
     static constexpr int NCH = UPT / VEC;            // chunks per thread
 };
-static inline size_t relax_smem_bytes(int N, int ldp, int upt) {
+static inline size_t relax_smem_bytes(int N, int ldp, int upt) {  // independent of the thread count
     const int nbw = (N + 31) / 32;
     (void)upt;
     return (size_t)((nbw + 3) / 4 * 4) * 4 * 2 + (size_t)((ldp + 7) / 8 * 8) * 2 * 2;
 }
 
-template <int UPT, typename CT>
-__global__ void __launch_bounds__(RELAX_THREADS, (UPT <= 16 ? RELAX_MIN_CTAS : 1))
+template <int UPT, typename CT, int THREADS>
+__global__ void __launch_bounds__(THREADS, (UPT <= 16 ? (RELAX_MIN_CTAS * 256) / THREADS : 1))
 relax_kernel(RelaxParams p) {
+    constexpr int RELAX_THREADS = THREADS;   // threads per probe: 256 up to N=4096, 512 / 1024 for N=8192 / 16384
+    constexpr int RELAX_WARPS = THREADS / 32;
     constexpr int VEC = RelaxCfg<UPT>::VEC;
     constexpr int NCH = RelaxCfg<UPT>::NCH;
     constexpr int NU = RELAX_THREADS * UPT;  // padded unit count
@@ -144,7 +144,7 @@ relax_kernel(RelaxParams p) {
     uint32_t* s_cand = s_bits + nbw4;
     uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_cand + nbw4);
     uint16_t* s_inv = s_perm + ldp8;
-    __shared__ __align__(16) uint32_t s_red[2][RELAX_WARPS];
+    __shared__ __align__(16) uint32_t s_red[2][32];
     __shared__ double s_exact[4];
     __shared__ int s_probe;
     __shared__ int s_flag;
@@ -166,10 +166,11 @@ relax_kernel(RelaxParams p) {
         x = __reduce_min_sync(0xFFFFFFFFu, x);
         if (lane == 0) s_red[red_buf][warp] = x;
         __syncthreads();
-        const uint4 a = *reinterpret_cast<const uint4*>(&s_red[red_buf][0]);
-        const uint4 b = *reinterpret_cast<const uint4*>(&s_red[red_buf][4]);
+        uint32_t m = s_red[red_buf][0];
+#pragma unroll
+        for (int w = 1; w < RELAX_WARPS; w++) m = min(m, s_red[red_buf][w]);
         red_buf ^= 1;
-        return min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
+        return m;
     };
     auto block_sum = [&](uint32_t x) -> uint32_t {
         x = __reduce_add_sync(0xFFFFFFFFu, x);
@@ -209,7 +210,8 @@ relax_kernel(RelaxParams p) {
         __syncthreads();
         T = thr(0);
         double h[UPT];     // true local fields of my units
-        int sw[UPT];       // per unit: 0x80000000 when the bit is clear (v = -1), else 0: hi32(h) ^ sw = hi32(h*v)
+        mask_t sbm = 0;    // my units' current bits; SIGNW(r) = 0x80000000 when the bit is clear (v = -1): hi32(h)^SIGNW = hi32(h*v)
+#define SIGNW(r) ((int)((uint32_t)((~sbm >> (r)) & 1u) << 31))
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
 #pragma unroll
@@ -217,10 +219,10 @@ relax_kernel(RelaxParams p) {
                 const int u = unit_of(c, e), r = c * VEC + e;
                 if (u < N) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
-                    sw[r] = b ? 0 : (int)0x80000000;
+                    sbm |= (mask_t)b << r;
                     h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited
-                    sw[r] = 0;
+                    sbm |= (mask_t)1 << r;
                     h[r] = __longlong_as_double(0x7FF0000000000000LL);
                 }
             }
@@ -230,7 +232,7 @@ relax_kernel(RelaxParams p) {
             mask_t m = 0;
 #pragma unroll
             for (int r = 0; r < UPT; r++)
-                if ((__double2hiint(h[r]) ^ sw[r]) < T) m |= (mask_t)1 << r;
+                if ((__double2hiint(h[r]) ^ SIGNW(r)) < T) m |= (mask_t)1 << r;
             return m;
         };
         mask_t cm = cand_mask();
@@ -289,7 +291,7 @@ relax_kernel(RelaxParams p) {
                         int a = 0, sg = 0;
 #pragma unroll
                         for (int r = 0; r < UPT; r++)
-                            if (r == rr) { a = __double2hiint(h[r]); sg = sw[r]; }
+                            if (r == rr) { a = __double2hiint(h[r]); sg = SIGNW(r); }
                         s_flag = ((((a & 0x7FFFFFFF) < T) ? 2 : 0) | (sg ? 0 : 1));
                     }
                 }
@@ -310,9 +312,7 @@ relax_kernel(RelaxParams p) {
                     const int ch = k / VEC, ke = k % VEC;
                     if ((ch % RELAX_THREADS) == tid) {
                         const int rr = (ch / RELAX_THREADS) * VEC + ke;
-#pragma unroll
-                        for (int r = 0; r < UPT; r++)
-                            if (r == rr) sw[r] ^= (int)0x80000000;
+                        sbm ^= (mask_t)1 << rr;
                         s_bits[k >> 5] ^= 1u << (k & 31);
                     }
                 }
@@ -377,7 +377,7 @@ relax_kernel(RelaxParams p) {
             uint32_t cnt = 0;
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
-                const int a = __double2hiint(h[r]) ^ sw[r];
+                const int a = __double2hiint(h[r]) ^ SIGNW(r);
                 if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
             }
             cnt = block_sum(cnt);

@@ -51,16 +51,24 @@ def merge_unique_tables(tables: List[dict]) -> dict:
     st = np.concatenate(states) if len(states) == len(tables) and states else None
     if first.size == 0:
         return {"first": first.astype(np.int32), "hits": hit.astype(np.int32), "rank_of": rk, "local_id": lid}
-    order = np.lexsort((first, hsh[:, 1], hsh[:, 0]))           # group by hash, earliest first inside a group
-    h_sorted = hsh[order]
+    # Every rank lists its attractors in ascending first index and ranks are concatenated in ascending offset, so
+    # `first` is already ascending: a STABLE sort on the low hash word keeps the earliest member first in a group.
+    h0, h1 = np.ascontiguousarray(hsh[:, 0]), np.ascontiguousarray(hsh[:, 1])
+    order = np.argsort(h0, kind="stable")
+    h0s, h1s = h0[order], h1[order]
+    same0 = h0s[1:] == h0s[:-1]
+    ascending = bool(np.all(first[1:] >= first[:-1]))
+    if not ascending or bool(np.any(same0 & (h1s[1:] != h1s[:-1]))):
+        order = np.lexsort((first, h1, h0))                      # general case: full sort, earliest first in a group
+        h0s, h1s = h0[order], h1[order]
+        same0 = h0s[1:] == h0s[:-1]
     new_group = np.ones(order.size, dtype=bool)
-    new_group[1:] = (h_sorted[1:] != h_sorted[:-1]).any(axis=1)
+    new_group[1:] = ~(same0 & (h1s[1:] == h1s[:-1]))
+    starts = np.flatnonzero(new_group)
     gid = np.cumsum(new_group) - 1
-    n_groups = int(gid[-1]) + 1
-    g_first = np.full(n_groups, np.iinfo(np.int64).max)
-    np.minimum.at(g_first, gid, first[order])
-    g_hits = np.zeros(n_groups, dtype=np.int64)
-    np.add.at(g_hits, gid, hit[order])
+    n_groups = starts.size
+    g_first = np.minimum.reduceat(first[order], starts)
+    g_hits = np.add.reduceat(hit[order], starts)
     rep = order[new_group]                                        # earliest member of each group
     if st is not None:
         same = (st[order] == st[rep][gid]).all(axis=1)

@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-delta", action="store_true", help="skip the Delta-rule epoch timing")
     ap.add_argument("--no-f32", action="store_true", help="skip the extra float32-column-stream measurement")
-    ap.add_argument("--columns", default="f64", choices=["f64", "f32"], help="column stream of the relaxation kernel")
+    ap.add_argument("--columns", default="f64", choices=["f64", "f32", "i16"], help="column stream of the relaxation kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,7 +149,7 @@ def main():
     targets, _, pool = synth(n, p, 1, 0x5EED + 3)  # same W / schedule on every rank
     net = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
         hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).SetColumnStream(
-        1 if args.columns == "f32" else 0).Build()
+        {"f64": 0, "f32": 1, "i16": 2}[args.columns]).Build()
     net.LearnStates(targets)
     # pinned host staging for the e2e leg
     probes_pinned = torch.from_numpy(probes).pin_memory()
@@ -206,23 +206,23 @@ def main():
     h2d = probes_np.nbytes + pool.nbytes
     d2h = res.FinalStates.nbytes + res.NumSteps.nbytes + res.Stable.nbytes + res.DistancesToTargets.nbytes + \
         res.Flips.nbytes + res.MarginHits.nbytes + res.AttractorId.nbytes + 2 * 4 * len(res.UniqueFirst) + res.StateHash.nbytes
-    # the same step with the float32 column stream (bit-identical results, half the column bytes): reported beside
-    # the headline, never as the headline
-    f32_ms = None
+    # the same step with the float32 / exact-int16 column streams (bit-identical results, 1/2 and 1/4 of the column
+    # bytes): reported beside the headline, never as the headline
+    alt_ms = {"f32": 0.0, "i16": 0.0}
     if args.columns == "f64" and not args.no_f32:
-        net32 = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
-            hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).SetColumnStream(1).Build()
-        net32.SetMatrix(net.GetMatrix())
-        net32.SetLearnedStates(targets)
-        net32.upload_perm_pool(pool)
-        net32.upload_probes(probes_np)
-        net32.relax_resident(dedup=True)
-        f32_ms = net32.relax_resident(dedup=True)
-        net32.close()
-    tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t)), f32_ms or 0.0], device="cuda", dtype=torch.float64)
+        for name, mode in (("f32", 1), ("i16", 2)):
+            alt = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
+                hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).SetColumnStream(mode).Build()
+            alt.LearnStates(targets)          # in-library learning: the integer structure is captured at normalisation
+            alt.upload_perm_pool(pool)
+            alt.upload_probes(probes_np)
+            alt.relax_resident(dedup=True)
+            alt_ms[name] = alt.relax_resident(dedup=True)
+            alt.close()
+    tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t)), alt_ms["f32"], alt_ms["i16"]], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    step_ms_max, relax_ms_max, e2e_max, f32_ms_max = [float(x) for x in tmax.cpu()]
+    step_ms_max, relax_ms_max, e2e_max, f32_ms_max, i16_ms_max = [float(x) for x in tmax.cpu()]
     if rank == 0:
         peaks = {}
         try:
@@ -250,6 +250,9 @@ def main():
                 "stage_ms_per_step": {"fields_gemm": float(np.mean(fields_ms)), "relax": float(np.mean(relax_ms)),
                                       "dedup": float(np.mean(post_ms))},
                 "value_f32_column_stream": (world * b / (f32_ms_max * 1e-3)) if f32_ms_max > 0 else None,
+                "value_i16_exact_integer_stream": (world * b / (i16_ms_max * 1e-3)) if i16_ms_max > 0 else None,
+                "alt_streams_note": "same step, same inputs, bit-identical results (tests/test_gpu_f32_columns.py, "
+                                    "tests/test_gpu_i16_columns.py); reported beside the float64 headline, not as it",
                 "margin_hits_per_probe": out.total_margin_hits / b,
                 "unique_attractors": int(n_unique_global if n_unique_global is not None else out.n_unique)}
         try:   # DRAM bytes of the relaxation kernel from the committed ncu capture of this command (per launch)

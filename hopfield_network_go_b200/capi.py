@@ -15,11 +15,11 @@ from . import build as _build
 HN_OK = 0
 HN_E_INVALID, HN_E_NO_DEVICE, HN_E_CUDA, HN_E_OOM, HN_E_POOL, HN_E_NCCL, HN_E_STATE = -1, -2, -3, -4, -5, -6, -7
 HN_RELAX_SERIAL_STREAM, HN_RELAX_DEDUP, HN_RELAX_HISTORY = 0x1, 0x2, 0x4
-HN_COLUMNS_F64, HN_COLUMNS_F32 = 0, 1
+HN_COLUMNS_F64, HN_COLUMNS_F32, HN_COLUMNS_I16 = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
     "hn_default_config", "hn_abi_version", "hn_last_error", "hn_create", "hn_destroy", "hn_set_weights",
-    "hn_get_weights", "hn_set_targets", "hn_num_targets", "hn_get_targets", "hn_hebbian_epoch",
+    "hn_get_weights", "hn_set_integer_structure", "hn_integer_stream_active", "hn_set_targets", "hn_num_targets", "hn_get_targets", "hn_hebbian_epoch",
     "hn_delta_epoch", "hn_thermal_delta_epoch", "hn_enforce_constraints", "hn_normalize_frobenius", "hn_energy_profiles",
     "hn_learn_states", "hn_relax_batch", "hn_update_states", "hn_upload_perm_pool", "hn_upload_probes",
     "hn_relax_resident", "hn_download_results", "hn_last_relax_timing", "hn_get_margin",
@@ -86,6 +86,8 @@ def load():
     L.hn_destroy.argtypes = [C.c_void_p]
     L.hn_set_weights.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_get_weights.argtypes = [C.c_void_p, C.c_void_p]
+    L.hn_set_integer_structure.argtypes = [C.c_void_p, C.c_void_p]
+    L.hn_integer_stream_active.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_set_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hn_num_targets.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_get_targets.argtypes = [C.c_void_p, C.c_void_p]

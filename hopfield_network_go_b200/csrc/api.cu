@@ -79,6 +79,10 @@ struct hn_handle_s {
     double* WT = nullptr;
     double* dW = nullptr;
     float* W32 = nullptr;       // float32 shadow of the column matrix (HN_COLUMNS_F32)
+    double* Wraw = nullptr;     // un-normalised W captured at normalisation (HN_COLUMNS_I16): W = c * Wraw
+    int16_t* K16 = nullptr;     // int16 image of 2*Wraw, column matrix layout
+    bool int_ok = false;        // the integer structure of the CURRENT W is known and fits int16
+    double int_scale = 2.0;     // K16 = int_scale * Wraw (2: Hebbian / bipolar Delta; 4: binary-domain Delta)
     bool w32_valid = false;
     double maxabs = 0;
     bool w_symmetric = true;   // W known symmetric -> column k == row k
@@ -149,7 +153,7 @@ int ensure_margin(hn_handle h) {
     return HN_OK;
 }
 
-void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; }
+void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; h->int_ok = false; }
 
 // exact symmetry test of the resident W (decides whether column k can be read as row k)
 int detect_symmetry(hn_handle h) {
@@ -167,11 +171,47 @@ int detect_symmetry(hn_handle h) {
 }
 
 // H[count][ldw] = S * W^T
-int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H, ValueMap vm) {
+int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H, ValueMap vm, const double* mat = nullptr) {
     OpBits a{d_states, h->words, count, h->N, vm.lo, vm.hi};
-    OpF64 b{h->W, h->ldw, h->N};
+    OpF64 b{mat ? mat : h->W, h->ldw, h->N};
     EpiStore e{d_H, h->ldw, count, h->N};
     return launch_gemm_f64(a, b, e, count, h->N, h->N, h->st);
+}
+
+// Integer structure for HN_COLUMNS_I16 from h->Wraw (already on the device): K16 = int16(2*Wraw) in column-matrix
+// layout; int_ok only if every entry is an exact integer within int16 and the exactness bound of the field holds.
+int build_integer_structure(hn_handle h, bool symmetric) {
+    const int64_t total = (int64_t)h->N * h->ldw;
+    if (!h->K16) HN_CUDA_TRY(cudaMalloc(&h->K16, sizeof(int16_t) * (size_t)total));
+    HN_TRY(h->small.reserve(256));
+    int32_t* flag = h->small.as<int32_t>() + 10;
+    unsigned long long* mx = h->small.as<unsigned long long>() + 6;
+    HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(mx, 0, 8, h->st));
+    const double* src = h->Wraw;
+    if (!symmetric) {  // column k of Wraw must be contiguous: transpose into dW (free outside learning epochs)
+        HN_CUDA_TRY(cudaMemsetAsync(h->dW, 0, sizeof(double) * (size_t)total, h->st));
+        dim3 g((h->N + SYM_T - 1) / SYM_T, (h->N + SYM_T - 1) / SYM_T), b(SYM_T, 8);
+        transpose_kernel<<<g, b, 0, h->st>>>(h->Wraw, h->dW, h->N, h->ldw);
+        src = h->dW;
+    }
+    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->Wraw, h->N, h->ldw, mx);
+    HN_CUDA_TRY(cudaGetLastError());
+    int32_t f = 1; double m = 0;
+    for (double scale : {2.0, 4.0}) {   // half-integers (Hebbian, bipolar Delta) or quarter-integers (binary Delta)
+        HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
+        to_i16_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(src, h->K16, total, scale, flag);
+        HN_CUDA_TRY(cudaGetLastError());
+        HN_CUDA_TRY(cudaMemcpyAsync(&f, flag, 4, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaMemcpyAsync(&m, mx, 8, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        h->int_scale = scale;
+        if (f == 0) break;
+    }
+    // fresh-dot rounding error << c  <=>  N^2 * max|2 Wraw| * 2^-50 < 0.5   (same precondition as oracle_fast.c)
+    const bool exact = (double)h->N * (double)h->N * (h->int_scale * m) * 8.881784197001252e-16 < 0.5;
+    h->int_ok = (f == 0) && exact && m > 0.0;
+    return HN_OK;
 }
 
 // float32 shadow of the column matrix (W if symmetric else W^T), rebuilt after any weight change
@@ -195,11 +235,15 @@ int select_columns(hn_handle h, RelaxParams& p) {
         p.Wcol = h->W32;
         // |fl32(w) - w| <= 2^-24 |w| (+ a denormal floor): each flip perturbs a field by at most delta*max|W|*2^-24
         p.tau_flip += 2.0 * dscale * (h->maxabs * 5.9604644775390625e-08 + 1.5e-45);
+    } else if (h->cfg.column_stream == HN_COLUMNS_I16 && h->int_ok) {
+        p.Wcol = h->K16;
+        p.int_scale = h->int_scale;
     } else {
         p.Wcol = h->w_symmetric ? (const void*)h->W : (const void*)h->WT;
     }
     return HN_OK;
 }
+bool integer_stream(hn_handle h) { return h->cfg.column_stream == HN_COLUMNS_I16 && h->int_ok; }
 
 template <int UPT, typename CT, int THREADS = 256>
 int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
@@ -231,6 +275,7 @@ int launch_relax_c(hn_handle h, const RelaxParams& p) {
 }
 int launch_relax(hn_handle h, RelaxParams& p) {
     HN_TRY(select_columns(h, p));
+    if (integer_stream(h)) return launch_relax_c<int16_t>(h, p);
     return h->cfg.column_stream == HN_COLUMNS_F32 ? launch_relax_c<float>(h, p) : launch_relax_c<double>(h, p);
 }
 
@@ -288,7 +333,8 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
 
     HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
-    HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain)));
+    // initial fields: S * W^T, or — exact integer stream — S * Wraw^T (half-integers, exact in float64)
+    HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
     launches++;
     HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
 
@@ -308,7 +354,6 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     p.hash = dedup ? h->hash.as<uint64_t>() : nullptr;
     p.history = hist ? h->history.as<uint64_t>() : nullptr;
     p.work_counter = d_small; p.status = d_small + 1;
-    { const char* ev = getenv("HN_RELAX_VARIANT"); p.variant = ev ? atoi(ev) : 0; }
     HN_TRY(launch_relax(h, p));
     launches++;
     HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
@@ -353,7 +398,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         launches += 5;
     }
     HN_CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
-    int32_t small_host[24];
+    int32_t small_host[8];
     HN_CUDA_TRY(cudaMemcpyAsync(small_host, d_small, sizeof(small_host), cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     if (small_host[1]) {
@@ -361,11 +406,6 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         return HN_E_POOL;
     }
     h->result_unique = dedup ? small_host[6] : 0;
-    if (getenv("HN_RELAX_VARIANT")) {
-        long long tt[6]; memcpy(tt, small_host + 8, sizeof(tt));
-        fprintf(stderr, "[hn] variant=%s cycles(thread0) scan %lld owner %lld barriers %lld load+fma %lld cand+atomics %lld sweepsetup+stability %lld\n",
-                getenv("HN_RELAX_VARIANT"), tt[0], tt[1], tt[2], tt[3], tt[4], tt[5]);
-    }
     float f = 0, r = 0, q = 0;
     cudaEventElapsedTime(&f, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&r, h->ev[1], h->ev[2]);
@@ -634,7 +674,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     if (cfg->dimension > 65535) { set_error("dimension %d exceeds 65535 (uint16 unit indices)", cfg->dimension); return HN_E_INVALID; }
     if (cfg->domain != HN_DOMAIN_BIPOLAR && cfg->domain != HN_DOMAIN_BINARY) { set_error("unknown domain %d", cfg->domain); return HN_E_INVALID; }
     if (cfg->max_relax_iterations <= 0) { set_error("max_relax_iterations must be positive"); return HN_E_INVALID; }
-    if (cfg->column_stream != HN_COLUMNS_F64 && cfg->column_stream != HN_COLUMNS_F32) { set_error("unknown column_stream %d", cfg->column_stream); return HN_E_INVALID; }
+    if (cfg->column_stream < HN_COLUMNS_F64 || cfg->column_stream > HN_COLUMNS_I16) { set_error("unknown column_stream %d", cfg->column_stream); return HN_E_INVALID; }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev <= 0) {
@@ -693,6 +733,8 @@ int hn_destroy(hn_handle h) {
     if (h->W) cudaFree(h->W);
     if (h->WT) cudaFree(h->WT);
     if (h->W32) cudaFree(h->W32);
+    if (h->Wraw) cudaFree(h->Wraw);
+    if (h->K16) cudaFree(h->K16);
     if (h->dW) cudaFree(h->dW);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
@@ -718,6 +760,37 @@ int hn_get_weights(hn_handle h, double* w_host) {
     HN_CUDA_TRY(cudaMemcpy2DAsync(w_host, sizeof(double) * h->N, h->W, sizeof(double) * h->ldw, sizeof(double) * h->N, h->N,
                                   cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int hn_set_integer_structure(hn_handle h, const double* w_raw) {
+    if (!check_handle(h, "hn_set_integer_structure") || !w_raw) { if (h) set_error("hn_set_integer_structure: NULL matrix"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    const int N = h->N;
+    // proportionality W = c * w_raw, c > 0, checked on the host against a copy of the resident weights
+    std::vector<double> w((size_t)N * N);
+    HN_TRY(hn_get_weights(h, w.data()));
+    size_t imax = 0;
+    for (size_t i = 1; i < w.size(); i++) if (std::fabs(w_raw[i]) > std::fabs(w_raw[imax])) imax = i;
+    const double c = w_raw[imax] != 0.0 ? w[imax] / w_raw[imax] : 0.0;   // W = fl(c * Wraw): one rounding per element
+    if (!(c > 0.0)) { set_error("hn_set_integer_structure: weights are not a positive multiple of the given matrix"); return HN_E_INVALID; }
+    for (size_t i = 0; i < w.size(); i++)
+        if (std::fabs(w[i] - c * w_raw[i]) > 1e-13 * std::fabs(c * w_raw[i])) {
+            set_error("hn_set_integer_structure: weights are not proportional to the given matrix (element %zu)", i);
+            return HN_E_INVALID;
+        }
+    const size_t wb = sizeof(double) * (size_t)N * h->ldw;
+    if (!h->Wraw) HN_CUDA_TRY(cudaMalloc(&h->Wraw, wb));
+    HN_CUDA_TRY(cudaMemsetAsync(h->Wraw, 0, wb, h->st));
+    HN_CUDA_TRY(cudaMemcpy2DAsync(h->Wraw, sizeof(double) * h->ldw, w_raw, sizeof(double) * N, sizeof(double) * N, N,
+                                  cudaMemcpyHostToDevice, h->st));
+    HN_TRY(build_integer_structure(h, h->w_symmetric));
+    if (!h->int_ok) { set_error("hn_set_integer_structure: 4*matrix is not integer valued within int16"); return HN_E_INVALID; }
+    return HN_OK;
+}
+int hn_integer_stream_active(hn_handle h, int32_t* active) {
+    if (!check_handle(h, "hn_integer_stream_active") || !active) return HN_E_INVALID;
+    *active = integer_stream(h) ? 1 : 0;
     return HN_OK;
 }
 
@@ -792,6 +865,12 @@ int hn_normalize_frobenius(hn_handle h, double* norm_out) {
     const int np = 1024;
     HN_TRY(h->partial.reserve(sizeof(double) * (np + 2)));
     double* part = h->partial.as<double>();
+    const bool capture = h->cfg.column_stream == HN_COLUMNS_I16;
+    if (capture) {  // keep the un-normalised matrix: W = (1/norm) * Wraw is the integer structure of the new weights
+        const size_t wb = sizeof(double) * (size_t)h->N * h->ldw;
+        if (!h->Wraw) HN_CUDA_TRY(cudaMalloc(&h->Wraw, wb));
+        HN_CUDA_TRY(cudaMemcpyAsync(h->Wraw, h->W, wb, cudaMemcpyDeviceToDevice, h->st));
+    }
     sumsq_partial_kernel<<<np, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, part);
     sumsq_final_kernel<<<1, RED_THREADS, 0, h->st>>>(part, np, part + np);
     scale_kernel<<<grid_for((int64_t)h->N * h->ldw, 256, h->sms), 256, 0, h->st>>>(h->W, h->N, h->ldw, part + np);
@@ -801,6 +880,7 @@ int hn_normalize_frobenius(hn_handle h, double* norm_out) {
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     if (norm_out) *norm_out = nrm[0];
     weights_changed(h);
+    if (capture && nrm[0] > 0.0 && std::isfinite(nrm[0])) HN_TRY(build_integer_structure(h, h->w_symmetric));
     return HN_OK;
 }
 

@@ -168,6 +168,16 @@ thermal_factor_kernel(const double* __restrict__ H, int ldh, int n, const double
     if (threadIdx.x == 0) f[s] = exp(-1.0 * (1.0 / (1.0 + nrm[0])) * sqrt(r) / 1.0);
 }
 
+// int16 image of scale*Wraw (exact integer stream); flag <- 1 if some scale*w is not an integer within int16
+__global__ void to_i16_kernel(const double* __restrict__ w, int16_t* __restrict__ k16, int64_t total, double scale, int32_t* flag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = scale * w[i];
+        const double r = rint(x);
+        if (r != x || fabs(r) > 32767.0) *flag = 1;
+        k16[i] = (int16_t)(long long)r;
+    }
+}
+
 // ---- inverse permutations: inv[row][perm[row][i]] = i -----------------------
 __global__ void invert_perm_kernel(const uint16_t* __restrict__ perm, uint16_t* __restrict__ inv, int n,
                                    int ldp, int rows) {

@@ -48,6 +48,7 @@ struct RelaxParams {
     int domain;
     int check_stability;  // 0: UpdateState semantics (exactly max_iter sweeps, no test)
     int serial_stream;    // 1: one CTA walks the probes in order, offsets = running sweep count
+    double int_scale;    // exact integer stream: fields g = int_scale * (Wraw s)
     double tau_base, tau_flip;  // margin tau(F) = tau_base + tau_flip * F (tau_flip includes the float32 stream bound)
     // outputs (device)
     uint64_t* final_states;  // [B][words]
@@ -61,8 +62,7 @@ struct RelaxParams {
     uint64_t* hash;          // [B][2] canonical-state hash or nullptr
     uint64_t* history;       // [B][max_iter+1][words] or nullptr
     int32_t* work_counter;   // dynamic probe scheduler
-    int32_t* status;         // [0]: set to 1 when the pool was exhausted; [1]: rows needed; [2],[3]: prediction hits / made
-    int variant;             // tuning knob (HN_RELAX_VARIANT): bit0 L2 prefetch, bit1 L1 prefetch, bits 4..7 spec windows
+    int32_t* status;         // [0]: set to 1 when the pool was exhausted; [1]: rows needed
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -104,6 +104,9 @@ constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
 #ifndef RELAX_MIN_CTAS
 #define RELAX_MIN_CTAS 4   // 64 registers per thread: +11% at N=4096, +18..26% at N<=2048 over 3 CTAs/SM
 #endif
+#ifndef RELAX_MIN_CTAS_INT
+#define RELAX_MIN_CTAS_INT 6   // the integer stream holds int32 fields: half the registers
+#endif
 constexpr int RELAX_TAU_STEP = 256;
 
 // Dynamic shared memory layout (see relax_smem_bytes):
@@ -129,7 +132,7 @@ static inline size_t relax_smem_bytes(int N, int ldp, int upt) {  // independent
 }
 
 template <int UPT, typename CT, int THREADS>
-__global__ void __launch_bounds__(THREADS, (UPT <= 16 ? (RELAX_MIN_CTAS * 256) / THREADS : 1))
+__global__ void __launch_bounds__(THREADS, (UPT <= 16 ? ((std::is_same<CT, int16_t>::value ? RELAX_MIN_CTAS_INT : RELAX_MIN_CTAS) * 256) / THREADS : 1))
 relax_kernel(RelaxParams p) {
     constexpr int RELAX_THREADS = THREADS;   // threads per probe: 256 up to N=4096, 512 / 1024 for N=8192 / 16384
     constexpr int RELAX_WARPS = THREADS / 32;
@@ -137,6 +140,11 @@ relax_kernel(RelaxParams p) {
     constexpr int NCH = RelaxCfg<UPT>::NCH;
     constexpr int NU = RELAX_THREADS * UPT;  // padded unit count
     using mask_t = typename std::conditional<(UPT > 32), uint64_t, uint32_t>::type;
+    // Field type: float64 local fields, or — CT = int16_t, the exact-integer stream — int32 fields g = 2*(Wraw s) with
+    // Wraw the un-normalised dyadic matrix (W = c*Wraw, c > 0): sign(g) is the sign of the reference's field wherever
+    // g != 0, and g == 0 is an exact tie that is re-evaluated on the float64 matrix (as oracle/oracle_fast.c does).
+    constexpr bool INTF = std::is_same<CT, int16_t>::value;
+    using FT = typename std::conditional<INTF, int, double>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbw = (p.N + 31) / 32;
     const int nbw4 = (nbw + 3) / 4 * 4, ldp8 = (p.ldp + 7) / 8 * 8;
@@ -209,7 +217,7 @@ relax_kernel(RelaxParams p) {
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
         T = thr(0);
-        double h[UPT];     // true local fields of my units
+        FT h[UPT];         // local fields of my units (float64 h, or exact int32 g = 2*Wraw*s)
         mask_t sbm = 0;    // my units' current bits; SIGNW(r) = 0x80000000 when the bit is clear (v = -1): hi32(h)^SIGNW = hi32(h*v)
 #define SIGNW(r) ((int)((uint32_t)((~sbm >> (r)) & 1u) << 31))
 #pragma unroll
@@ -220,10 +228,11 @@ relax_kernel(RelaxParams p) {
                 if (u < N) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
                     sbm |= (mask_t)b << r;
-                    h[r] = p.H0[(size_t)pi * p.ldh + u];
+                    if constexpr (INTF) h[r] = (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);   // H0 = S * Wraw^T, exact
+                    else h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited
                     sbm |= (mask_t)1 << r;
-                    h[r] = __longlong_as_double(0x7FF0000000000000LL);
+                    if constexpr (INTF) h[r] = 0x7FFFFFFF; else h[r] = __longlong_as_double(0x7FF0000000000000LL);
                 }
             }
         }
@@ -231,8 +240,12 @@ relax_kernel(RelaxParams p) {
         auto cand_mask = [&]() -> mask_t {
             mask_t m = 0;
 #pragma unroll
-            for (int r = 0; r < UPT; r++)
-                if ((__double2hiint(h[r]) ^ SIGNW(r)) < T) m |= (mask_t)1 << r;
+            for (int r = 0; r < UPT; r++) {
+                bool c;
+                if constexpr (INTF) c = (((sbm >> r) & 1u) ? h[r] : -h[r]) <= 0;   // wants to flip (aligned < 0) or exact tie (g == 0)
+                else c = (__double2hiint(h[r]) ^ SIGNW(r)) < T;
+                if (c) m |= (mask_t)1 << r;
+            }
             return m;
         };
         mask_t cm = cand_mask();
@@ -288,11 +301,12 @@ relax_kernel(RelaxParams p) {
                     const int ch = k / VEC, ke = k % VEC;
                     if ((ch % RELAX_THREADS) == tid) {
                         const int rr = (ch / RELAX_THREADS) * VEC + ke;
-                        int a = 0, sg = 0;
+                        int a = 0;
 #pragma unroll
                         for (int r = 0; r < UPT; r++)
-                            if (r == rr) { a = __double2hiint(h[r]); sg = SIGNW(r); }
-                        s_flag = ((((a & 0x7FFFFFFF) < T) ? 2 : 0) | (sg ? 0 : 1));
+                            if (r == rr) { if constexpr (INTF) a = h[r]; else a = __double2hiint(h[r]); }
+                        const bool inside = INTF ? (a == 0) : ((a & 0x7FFFFFFF) < T);
+                        s_flag = (inside ? 2 : 0) | (int)((sbm >> rr) & 1u);
                     }
                 }
                 __syncthreads();
@@ -307,8 +321,7 @@ relax_kernel(RelaxParams p) {
                 if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
                 // ---- flip unit k: h += d * W[:,k] over my units; toggle the bitmap where candidacy changed ----
-                const double d = nb ? dscale : -dscale;
-                {   // owner: new bit into its sign word and the packed state
+                {   // owner: new bit into its sign mask and the packed state
                     const int ch = k / VEC, ke = k % VEC;
                     if ((ch % RELAX_THREADS) == tid) {
                         const int rr = (ch / RELAX_THREADS) * VEC + ke;
@@ -318,14 +331,25 @@ relax_kernel(RelaxParams p) {
                 }
                 {   // one coalesced pass over column k (row k of Wcol), fused into the register-resident fields
                     const CT* col = reinterpret_cast<const CT*>(p.Wcol) + (size_t)k * p.ldw;
+                    const FT d = nb ? (FT)dscale : (FT)(-dscale);
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         const int u0 = unit_of(c, 0);
-                        double w[VEC];
+                        FT w[VEC];
 #pragma unroll
-                        for (int e = 0; e < VEC; e++) w[e] = 0.0;
+                        for (int e = 0; e < VEC; e++) w[e] = (FT)0;
                         if (u0 < p.ldw) {
-                            if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
+                            if constexpr (INTF) {              // exact int16 column stream: 2N bytes per flip
+                                if (VEC == 4) {
+                                    const int2 x = __ldg(reinterpret_cast<const int2*>(col + u0));
+                                    w[0] = (short)(x.x & 0xFFFF); w[1] = x.x >> 16; w[2] = (short)(x.y & 0xFFFF); w[3] = x.y >> 16;
+                                } else if (VEC == 2) {
+                                    const int x = __ldg(reinterpret_cast<const int*>(col + u0));
+                                    w[0] = (short)(x & 0xFFFF); w[1] = x >> 16;
+                                } else {
+                                    w[0] = __ldg(col + u0);
+                                }
+                            } else if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
                                 if (VEC == 4) {
                                     const float4 x = __ldg(reinterpret_cast<const float4*>(col + u0));
                                     w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
@@ -346,10 +370,13 @@ relax_kernel(RelaxParams p) {
                             }
                         }
 #pragma unroll
-                        for (int e = 0; e < VEC; e++) h[c * VEC + e] = fma(d, w[e], h[c * VEC + e]);
+                        for (int e = 0; e < VEC; e++) {
+                            if constexpr (INTF) h[c * VEC + e] += d * w[e];
+                            else h[c * VEC + e] = fma(d, w[e], h[c * VEC + e]);
+                        }
                     }
                 }
-                if (((flips + 1) & (RELAX_TAU_STEP - 1)) == 0) T = thr(flips + 1);  // candidacy below is re-derived with it
+                if (!INTF && ((flips + 1) & (RELAX_TAU_STEP - 1)) == 0) T = thr(flips + 1);  // candidacy below is re-derived with it
                 {
                     const mask_t nm = cand_mask();
                     mask_t ch = nm ^ cm;
@@ -377,8 +404,12 @@ relax_kernel(RelaxParams p) {
             uint32_t cnt = 0;
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
-                const int a = __double2hiint(h[r]) ^ SIGNW(r);
-                if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
+                if constexpr (INTF) {
+                    if ((((sbm >> r) & 1u) ? h[r] : -h[r]) < 0) cnt++;           // g != 0 and misaligned: certainly unstable
+                } else {
+                    const int a = __double2hiint(h[r]) ^ SIGNW(r);
+                    if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
+                }
             }
             cnt = block_sum(cnt);
             // units inside the margin: exact recomputation, in increasing unit index
@@ -388,7 +419,9 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                 for (int r = 0; r < UPT; r++) {
                     const int u = unit_of_r(r);
-                    if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T && u > last) cmin = min(cmin, (uint32_t)u);
+                    bool inside;
+                    if constexpr (INTF) inside = h[r] == 0; else inside = (__double2hiint(h[r]) & 0x7FFFFFFF) < T;
+                    if (inside && u > last) cmin = min(cmin, (uint32_t)u);
                 }
                 cmin = block_min(cmin);
                 if (cmin == RELAX_NONE) break;

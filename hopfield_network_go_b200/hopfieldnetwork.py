@@ -136,6 +136,16 @@ class HopfieldNetwork:
         assert w.shape == (self.dimension, self.dimension)
         check(capi.load().hn_set_weights(self._h, ptr(w)))
 
+    def SetIntegerStructure(self, w_unnormalized: np.ndarray) -> None:
+        """Declare W = c * w_unnormalized (2*w_unnormalized integer) for the exact integer column stream."""
+        w = np.ascontiguousarray(w_unnormalized, dtype=np.float64)
+        check(capi.load().hn_set_integer_structure(self._h, ptr(w)))
+
+    def integer_stream_active(self) -> bool:
+        a = C.c_int32()
+        check(capi.load().hn_integer_stream_active(self._h, C.byref(a)))
+        return bool(a.value)
+
     def GetDimension(self) -> int:
         return self.dimension
 

@@ -105,7 +105,7 @@ constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
 #define RELAX_MIN_CTAS 4   // 64 registers per thread: +11% at N=4096, +18..26% at N<=2048 over 3 CTAs/SM
 #endif
 #ifndef RELAX_MIN_CTAS_INT
-#define RELAX_MIN_CTAS_INT 6   // the integer stream holds int32 fields: half the registers
+#define RELAX_MIN_CTAS_INT 5   // int32 aligned fields + int sign words: 48 registers
 #endif
 constexpr int RELAX_TAU_STEP = 256;
 
@@ -217,7 +217,9 @@ relax_kernel(RelaxParams p) {
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
         T = thr(0);
-        FT h[UPT];         // local fields of my units (float64 h, or exact int32 g = 2*Wraw*s)
+        FT h[UPT];         // float64: local fields h of my units.  Integer stream: ALIGNED exact fields a = g*v
+                           // (g = scale*Wraw*s, v = +-1 by the unit's bit): candidate <=> a <= 0, exact tie <=> a == 0
+        int sv[INTF ? UPT : 1];   // integer stream: v * delta of my units (the sign a column entry enters a with)
         mask_t sbm = 0;    // my units' current bits; SIGNW(r) = 0x80000000 when the bit is clear (v = -1): hi32(h)^SIGNW = hi32(h*v)
 #define SIGNW(r) ((int)((uint32_t)((~sbm >> (r)) & 1u) << 31))
 #pragma unroll
@@ -228,11 +230,14 @@ relax_kernel(RelaxParams p) {
                 if (u < N) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
                     sbm |= (mask_t)b << r;
-                    if constexpr (INTF) h[r] = (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);   // H0 = S * Wraw^T, exact
-                    else h[r] = p.H0[(size_t)pi * p.ldh + u];
+                    if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
+                        const int g = (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
+                        h[r] = b ? g : -g;
+                        sv[r] = b ? (int)dscale : -(int)dscale;
+                    } else h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited
                     sbm |= (mask_t)1 << r;
-                    if constexpr (INTF) h[r] = 0x7FFFFFFF; else h[r] = __longlong_as_double(0x7FF0000000000000LL);
+                    if constexpr (INTF) { h[r] = 0x7FFFFFFF; sv[r] = 0; } else h[r] = __longlong_as_double(0x7FF0000000000000LL);
                 }
             }
         }
@@ -242,7 +247,7 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
                 bool c;
-                if constexpr (INTF) c = (((sbm >> r) & 1u) ? h[r] : -h[r]) <= 0;   // wants to flip (aligned < 0) or exact tie (g == 0)
+                if constexpr (INTF) c = h[r] <= 0;   // wants to flip (aligned < 0) or exact tie (== 0)
                 else c = (__double2hiint(h[r]) ^ SIGNW(r)) < T;
                 if (c) m |= (mask_t)1 << r;
             }
@@ -321,7 +326,7 @@ relax_kernel(RelaxParams p) {
                 if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
                 // ---- flip unit k: h += d * W[:,k] over my units; toggle the bitmap where candidacy changed ----
-                {   // owner: new bit into its sign mask and the packed state
+                if constexpr (!INTF) {   // owner: new bit into its sign mask and the packed state
                     const int ch = k / VEC, ke = k % VEC;
                     if ((ch % RELAX_THREADS) == tid) {
                         const int rr = (ch / RELAX_THREADS) * VEC + ke;
@@ -332,48 +337,66 @@ relax_kernel(RelaxParams p) {
                 {   // one coalesced pass over column k (row k of Wcol), fused into the register-resident fields
                     const CT* col = reinterpret_cast<const CT*>(p.Wcol) + (size_t)k * p.ldw;
                     const FT d = nb ? (FT)dscale : (FT)(-dscale);
+                    auto pass = [&](auto full_tag, auto up_tag) {
+                        constexpr bool FULL = decltype(full_tag)::value;   // every chunk lies inside the padded row
+                        constexpr bool UP = decltype(up_tag)::value;       // integer stream: the flipped unit goes 0 -> 1
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) {
-                        const int u0 = unit_of(c, 0);
-                        FT w[VEC];
+                        for (int c = 0; c < NCH; c++) {
+                            const int u0 = unit_of(c, 0);
+                            FT w[VEC];
 #pragma unroll
-                        for (int e = 0; e < VEC; e++) w[e] = (FT)0;
-                        if (u0 < p.ldw) {
-                            if constexpr (INTF) {              // exact int16 column stream: 2N bytes per flip
-                                if (VEC == 4) {
-                                    const int2 x = __ldg(reinterpret_cast<const int2*>(col + u0));
-                                    w[0] = (short)(x.x & 0xFFFF); w[1] = x.x >> 16; w[2] = (short)(x.y & 0xFFFF); w[3] = x.y >> 16;
+                            for (int e = 0; e < VEC; e++) w[e] = (FT)0;
+                            if (FULL || u0 < p.ldw) {
+                                if constexpr (INTF) {              // exact int16 column stream: 2N bytes per flip
+                                    if (VEC == 4) {
+                                        const int2 x = __ldg(reinterpret_cast<const int2*>(col + u0));
+                                        w[0] = (short)(x.x & 0xFFFF); w[1] = x.x >> 16; w[2] = (short)(x.y & 0xFFFF); w[3] = x.y >> 16;
+                                    } else if (VEC == 2) {
+                                        const int x = __ldg(reinterpret_cast<const int*>(col + u0));
+                                        w[0] = (short)(x & 0xFFFF); w[1] = x >> 16;
+                                    } else {
+                                        w[0] = __ldg(col + u0);
+                                    }
+                                } else if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
+                                    if (VEC == 4) {
+                                        const float4 x = __ldg(reinterpret_cast<const float4*>(col + u0));
+                                        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+                                    } else if (VEC == 2) {
+                                        const float2 x = __ldg(reinterpret_cast<const float2*>(col + u0));
+                                        w[0] = x.x; w[1] = x.y;
+                                    } else {
+                                        w[0] = __ldg(col + u0);
+                                    }
+                                } else if (VEC == 4) {   // 256-bit loads (8% faster than two 128-bit loads here)
+                                    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                                 : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(col + u0));
                                 } else if (VEC == 2) {
-                                    const int x = __ldg(reinterpret_cast<const int*>(col + u0));
-                                    w[0] = (short)(x & 0xFFFF); w[1] = x >> 16;
-                                } else {
-                                    w[0] = __ldg(col + u0);
-                                }
-                            } else if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
-                                if (VEC == 4) {
-                                    const float4 x = __ldg(reinterpret_cast<const float4*>(col + u0));
-                                    w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
-                                } else if (VEC == 2) {
-                                    const float2 x = __ldg(reinterpret_cast<const float2*>(col + u0));
+                                    const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
                                     w[0] = x.x; w[1] = x.y;
                                 } else {
                                     w[0] = __ldg(col + u0);
                                 }
-                            } else if (VEC == 4) {   // 256-bit loads (8% faster than two 128-bit loads here)
-                                asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                                             : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(col + u0));
-                            } else if (VEC == 2) {
-                                const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
-                                w[0] = x.x; w[1] = x.y;
-                            } else {
-                                w[0] = __ldg(col + u0);
+                            }
+#pragma unroll
+                            for (int e = 0; e < VEC; e++) {
+                                const int r = c * VEC + e;
+                                if constexpr (INTF) { if (UP) h[r] += sv[r] * w[e]; else h[r] -= sv[r] * w[e]; }   // a += v*(+-delta)*K
+                                else h[r] = fma(d, w[e], h[r]);
                             }
                         }
+                    };
+                    if (p.ldw == NU) { if (nb) pass(std::true_type{}, std::true_type{}); else pass(std::true_type{}, std::false_type{}); }
+                    else { if (nb) pass(std::false_type{}, std::true_type{}); else pass(std::false_type{}, std::false_type{}); }
+                }
+                if constexpr (INTF) {   // owner: its own sign changed -> negate its aligned field and its column sign
+                    const int ch = k / VEC, ke = k % VEC;
+                    if ((ch % RELAX_THREADS) == tid) {
+                        const int rr = (ch / RELAX_THREADS) * VEC + ke;
 #pragma unroll
-                        for (int e = 0; e < VEC; e++) {
-                            if constexpr (INTF) h[c * VEC + e] += d * w[e];
-                            else h[c * VEC + e] = fma(d, w[e], h[c * VEC + e]);
-                        }
+                        for (int r = 0; r < UPT; r++)
+                            if (r == rr) { h[r] = -h[r]; sv[r] = -sv[r]; }
+                        sbm ^= (mask_t)1 << rr;
+                        s_bits[k >> 5] ^= 1u << (k & 31);
                     }
                 }
                 if (!INTF && ((flips + 1) & (RELAX_TAU_STEP - 1)) == 0) T = thr(flips + 1);  // candidacy below is re-derived with it
@@ -405,7 +428,7 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
                 if constexpr (INTF) {
-                    if ((((sbm >> r) & 1u) ? h[r] : -h[r]) < 0) cnt++;           // g != 0 and misaligned: certainly unstable
+                    if (h[r] < 0) cnt++;           // aligned field negative: certainly unstable
                 } else {
                     const int a = __double2hiint(h[r]) ^ SIGNW(r);
                     if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;

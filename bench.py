@@ -223,6 +223,12 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     step_ms_max, relax_ms_max, e2e_max, f32_ms_max, i16_ms_max = [float(x) for x in tmax.cpu()]
+    delta_ms = {}
+    if not args.no_delta:   # collective when world > 1: every rank takes part
+        if world == 1:
+            delta_ms["config2_N1024_P100_inversion0.1"] = measure_delta_epoch(hn, local, 1024, 100, 5)
+        delta_ms[f"config5_N16384_P{128 * world}_sharded_128_per_gpu"] = measure_delta_epoch(
+            hn, local, 16384, 128, 2, dist=dist if world > 1 else None, rank=rank, world=world)
     if rank == 0:
         peaks = {}
         try:
@@ -263,11 +269,10 @@ def main():
         except Exception:
             pass
         if not args.no_delta:
-            line["delta_epoch_ms"] = {
-                "config2_N1024_P100_inversion0.1": measure_delta_epoch(hn, local, 1024, 100, 5),
-                "config5_shape_N16384_P128_per_gpu": measure_delta_epoch(hn, local, 16384, 128, 2),
-                "note": "wall clock through hn_delta_epoch + hn_energy_profiles with host buffers (H2D of packed targets, "
-                        "noised copies and permutations inside the timed region); 1 GPU, no all-reduce"}
+            line["delta_epoch_ms"] = dict(delta_ms, note="wall clock (max over ranks) through hn_delta_epoch + hn_energy_profiles "
+                                          "with host buffers (H2D of packed targets, noised copies and permutations inside the timed "
+                                          "region); with n_gpus > 1 the config-5 targets are sharded 128 per GPU and dW (2 GiB) is "
+                                          "all-reduced over NCCL every epoch")
         if not args.no_cpu:
             from oracle import orc
             cores = os.cpu_count() or 1
@@ -290,32 +295,54 @@ def main():
         dist.destroy_process_group()
 
 
-def measure_delta_epoch(hn, local, n, p, epochs, noise_scale=0.1):
+def measure_delta_epoch(hn, local, n, p, epochs, noise_scale=0.1, dist=None, rank=0, world=1):
     """Second BASELINE metric: Delta-rule epoch time = one pass of `delta` (LearningRule.go:90-114) over all
     targets + the per-epoch target diagnostics of fullSetLearningMethod (LearningMethod.go:45-58).
-    Noise / update orders are drawn host-side with the library's restated RNG before the timed region."""
+    Noise / update orders are drawn host-side before the timed region.  With world > 1 the p*world targets are
+    sharded (p per GPU) and the library all-reduces dW over NCCL inside hn_delta_epoch."""
+    import ctypes as C
+    from hopfield_network_go_b200 import capi
     rs = np.random.Generator(np.random.PCG64(0x5EED + 2))
     w = (n + 63) // 64
-    targets = rs.integers(0, 2**63, size=(p, w), dtype=np.int64).astype(np.uint64) << np.uint64(1) | \
-        rs.integers(0, 2, size=(p, w), dtype=np.int64).astype(np.uint64)
+    ptot = p * world
+    targets = rs.integers(0, 2**63, size=(ptot, w), dtype=np.int64).astype(np.uint64) << np.uint64(1) | \
+        rs.integers(0, 2, size=(ptot, w), dtype=np.int64).astype(np.uint64)
     net = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
         hn.DeltaLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(2).SetDevice(local).Build()
+    if world > 1:
+        uid = (C.c_uint8 * 128)()
+        if rank == 0:
+            capi.check(capi.load().hn_comm_unique_id(uid))
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=0)
+        uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        capi.check(capi.load().hn_comm_attach(net._h, uid, rank, world))
+    lo, hi = rank * p, (rank + 1) * p
     k = int(n * noise_scale)
     times = []
     for ep in range(epochs + 2):
-        noised = targets.copy()
+        noised = targets[lo:hi].copy()
         for s in range(p):      # MaximalInversion: int(N*ratio) units among 0..N-2 (NoiseApplication.go:64-75)
             idx = rs.permutation(n - 1)[:k]
             np.bitwise_xor.at(noised[s], idx // 64, np.uint64(1) << (idx % 64).astype(np.uint64))
         perms = np.stack([rs.permutation(n).astype(np.uint16) for _ in range(p)])
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        net.delta_epoch(targets, noised, perms)
-        net.energy_profiles(targets, want_energies=False)
+        net.delta_epoch(targets[lo:hi], noised, perms)
+        net.energy_profiles(targets[lo:hi], want_energies=False)
         dt = time.perf_counter() - t0
         if ep >= 2:
             times.append(dt * 1e3)
+    ms = float(np.mean(times))
+    if world > 1:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        capi.check(capi.load().hn_comm_detach(net._h))
     net.close()
-    return float(np.mean(times))
+    return ms
 
 
 if __name__ == "__main__":

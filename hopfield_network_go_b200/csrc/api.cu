@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "gemm_f64.cuh"
+#include "igemm_s8.cuh"
 #include "kernels_misc.cuh"
 #include "relax.cuh"
 
@@ -333,8 +334,14 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
 
     HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
-    // initial fields: S * W^T, or — exact integer stream — S * Wraw^T (half-integers, exact in float64)
-    HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
+    // initial fields: S * W^T (FP64 tensor pipe); exact integer stream: G = S * K^T on the integer tensor pipe when W is
+    // symmetric (K's rows are its columns), else S * Wraw^T in float64 (half/quarter-integers: exact)
+    const bool int_fields = integer_stream(h) && h->w_symmetric;
+    if (int_fields)
+        HN_TRY(launch_igemm_fields(d_probes, h->words, B, h->K16, h->ldw, N, h->cfg.domain == HN_DOMAIN_BIPOLAR,
+                                   reinterpret_cast<int32_t*>(h->H.as<double>()), h->ldw, h->st));
+    else
+        HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
     launches++;
     HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
 
@@ -342,6 +349,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wrow = h->W;
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
+    p.H0i = int_fields ? reinterpret_cast<const int32_t*>(h->H.as<double>()) : nullptr;
     p.probes = d_probes; p.perm_pool = d_pool; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n_pool;
     p.offsets = serial ? nullptr : d_offsets;
     p.B = B; p.max_iter = h->cfg.max_relax_iterations; p.max_unstable = h->cfg.max_relax_unstable_units;

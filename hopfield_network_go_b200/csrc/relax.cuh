@@ -35,6 +35,7 @@ struct RelaxParams {
     const void* Wcol;    // row k of this matrix == column k of W  (W if symmetric else W^T); float64 or float32 shadow
     const double* Wrow;  // W: row k . s gives h_k (exact recomputation)
     const double* H0;    // [B][ldh] initial fields (from the GEMM)
+    const int32_t* H0i;  // integer stream: [B][ldh] exact int32 fields g = scale*Wraw*s from the integer GEMM (or nullptr)
     int ldh;
     const uint64_t* probes;     // [B][words]
     const uint16_t* perm_pool;  // [n_pool][ldp]
@@ -231,7 +232,7 @@ relax_kernel(RelaxParams p) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
                     sbm |= (mask_t)b << r;
                     if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
-                        const int g = (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
+                        const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
                         h[r] = b ? g : -g;
                         sv[r] = b ? (int)dscale : -(int)dscale;
                     } else h[r] = p.H0[(size_t)pi * p.ldh + u];

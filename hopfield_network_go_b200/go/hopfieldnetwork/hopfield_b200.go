@@ -71,6 +71,8 @@ func check(rc C.int) {
 func newDeviceNetwork(net *HopfieldNetwork, device int, initial []float64) *HopfieldNetwork {
 	var cfg C.hn_config
 	C.hn_default_config(&cfg)
+	// cfg.column_stream: C.HN_COLUMNS_F64 (default), C.HN_COLUMNS_F32 or C.HN_COLUMNS_I16 — results are identical,
+	// see include/hopfield_b200.h; a SetColumnStream builder option can expose it.
 	cfg.dimension = C.int32_t(net.dimension)
 	cfg.domain = C.int32_t(net.domain)
 	cfg.force_symmetric = boolToC(net.forceSymmetric)
@@ -212,7 +214,7 @@ func (network *HopfieldNetwork) learnEpoch(states []*mat.VecDense) {
 	switch network.learningRuleEnum {
 	case HebbianLearningRule:
 		check(C.hn_hebbian_epoch(network.handle, sp, C.int32_t(len(states))))
-	case DeltaLearningRule:
+	case DeltaLearningRule, ThermalDeltaLearningRule:
 		noised := make([]*mat.VecDense, len(states))
 		perms := make([]uint16, len(states)*network.dimension)
 		for i, s := range states {
@@ -229,8 +231,13 @@ func (network *HopfieldNetwork) learnEpoch(states []*mat.VecDense) {
 			}
 		}
 		np := network.pack(noised)
-		check(C.hn_delta_epoch(network.handle, sp, (*C.uint64_t)(unsafe.Pointer(&np[0])),
-			(*C.uint16_t)(unsafe.Pointer(&perms[0])), C.int32_t(len(states)), nil))
+		if network.learningRuleEnum == ThermalDeltaLearningRule { // LearningRule.go:129-158
+			check(C.hn_thermal_delta_epoch(network.handle, sp, (*C.uint64_t)(unsafe.Pointer(&np[0])),
+				(*C.uint16_t)(unsafe.Pointer(&perms[0])), C.int32_t(len(states)), nil))
+		} else {
+			check(C.hn_delta_epoch(network.handle, sp, (*C.uint64_t)(unsafe.Pointer(&np[0])),
+				(*C.uint16_t)(unsafe.Pointer(&perms[0])), C.int32_t(len(states)), nil))
+		}
 	default:
 		panic("learning rule not available on the device path")
 	}

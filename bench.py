@@ -248,7 +248,7 @@ def main():
                              "traffic": None, "kernel": "relax_kernel<16,double>",
                              "note": "per GPU; algorithmic bytes 8N per flip + 8N per sweep (SURVEY 8d) over the relaxation "
                                      "kernel time; >1 because columns are served from L2 (see traffic); the kernel is bounded "
-                                     "by the L2->SM fabric (~8.5 TB/s), profiles/r01_relax_v4_ncu_summary.txt",
+                                     "by the L2->SM fabric (every flip moves its 8N-byte column L2->SM: ~9.7 TB/s, ~33 B/clk/SM), profiles/r01_relax_final_ncu_summary.txt",
                              "peak_source": "measured" if peaks else "fallback",
                              "algorithmic_bytes_per_launch": int(alg_bytes), "flips_per_probe": flips / b,
                              "sweeps_per_probe": sweeps / b},

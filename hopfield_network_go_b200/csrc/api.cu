@@ -72,6 +72,19 @@ constexpr int NCCL_FLOAT64 = 8, NCCL_INT32 = 2, NCCL_SUM = 0, NCCL_MIN = 4;
 
 using namespace hn;
 
+// Small device scratch block of a handle (one allocation, h->small): every kernel-side counter / flag lives here.
+struct Scratch {
+    int32_t work_counter;              // relax: dynamic probe scheduler
+    int32_t status[2];                 // relax: [0] pool exhausted, [1] rows needed
+    int32_t unique_total;              // dedup: number of unique attractors
+    int32_t asym_flag;                 // detect_symmetry
+    int32_t int_flag;                  // build_integer_structure: scale*Wraw not an int16 integer somewhere
+    int32_t pad[2];
+    unsigned long long rowabs_bits;    // ensure_margin: max_i sum_k |W_ik| (double bits)
+    unsigned long long maxabs_bits;    // ensure_margin: max |W_ij|
+    unsigned long long maxabs_raw_bits;  // build_integer_structure: max |Wraw_ij|
+};
+
 struct hn_handle_s {
     hn_config cfg;
     int N = 0, ldw = 0, words = 0, ldp = 0, sms = 0;
@@ -103,6 +116,7 @@ struct hn_handle_s {
     hn_relax_timing timing = {};
     int64_t tot_flips = 0, tot_sweeps = 0, tot_margin = 0;
     void* comm = nullptr;
+    Scratch* scratch() const { return small.as<Scratch>(); }
     int rank_id = 0, n_ranks = 1;
 };
 
@@ -134,15 +148,15 @@ int refresh_wt(hn_handle h) {
 
 int ensure_margin(hn_handle h) {
     if (h->margin_valid) return HN_OK;
-    HN_TRY(h->small.reserve(256));
-    unsigned long long* d = h->small.as<unsigned long long>();
-    HN_CUDA_TRY(cudaMemsetAsync(d, 0, 16, h->st));
-    rowabs_max_kernel<<<h->N, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, d);
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    Scratch* sc = h->scratch();
+    HN_CUDA_TRY(cudaMemsetAsync(&sc->rowabs_bits, 0, 16, h->st));
+    rowabs_max_kernel<<<h->N, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, &sc->rowabs_bits);
     HN_CUDA_TRY(cudaGetLastError());
-    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->W, h->N, h->ldw, d + 1);
+    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->W, h->N, h->ldw, &sc->maxabs_bits);
     HN_CUDA_TRY(cudaGetLastError());
     double rr[2] = {0, 0};
-    HN_CUDA_TRY(cudaMemcpyAsync(rr, d, 16, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync(rr, &sc->rowabs_bits, 16, cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     const double r = rr[0];
     h->maxabs = rr[1];
@@ -158,8 +172,8 @@ void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = fals
 
 // exact symmetry test of the resident W (decides whether column k can be read as row k)
 int detect_symmetry(hn_handle h) {
-    HN_TRY(h->small.reserve(256));
-    int32_t* flag = h->small.as<int32_t>() + 8;
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    int32_t* flag = &h->scratch()->asym_flag;
     HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
     dim3 g((h->N + SYM_T - 1) / SYM_T, (h->N + SYM_T - 1) / SYM_T), b(SYM_T, 8);
     asymmetry_kernel<<<g, b, 0, h->st>>>(h->W, h->N, h->ldw, flag);
@@ -184,9 +198,9 @@ int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H,
 int build_integer_structure(hn_handle h, bool symmetric) {
     const int64_t total = (int64_t)h->N * h->ldw;
     if (!h->K16) HN_CUDA_TRY(cudaMalloc(&h->K16, sizeof(int16_t) * (size_t)total));
-    HN_TRY(h->small.reserve(256));
-    int32_t* flag = h->small.as<int32_t>() + 10;
-    unsigned long long* mx = h->small.as<unsigned long long>() + 6;
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    int32_t* flag = &h->scratch()->int_flag;
+    unsigned long long* mx = &h->scratch()->maxabs_raw_bits;
     HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(mx, 0, 8, h->st));
     const double* src = h->Wraw;
@@ -323,14 +337,14 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     HN_TRY(h->stable.reserve((size_t)B));
     HN_TRY(h->flips.reserve(sizeof(int32_t) * (size_t)B));
     HN_TRY(h->margin.reserve(sizeof(int32_t) * (size_t)B));
-    HN_TRY(h->small.reserve(256));
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
     if (want_dist && h->P > 0) HN_TRY(h->dist.reserve(sizeof(int32_t) * (size_t)B * h->P));
     if (dedup) HN_TRY(h->hash.reserve(sizeof(uint64_t) * 2 * (size_t)B));
     if (hist) HN_TRY(h->history.reserve(sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
 
     int launches = 0;
-    int32_t* d_small = h->small.as<int32_t>();  // [0] work counter, [1..4] status, [6] unique total
-    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
+    Scratch* sc = h->scratch();
+    HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));   // work counter, status, unique total
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
 
     HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
@@ -361,7 +375,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     p.targets = h->targets.as<uint64_t>(); p.P = h->P;
     p.hash = dedup ? h->hash.as<uint64_t>() : nullptr;
     p.history = hist ? h->history.as<uint64_t>() : nullptr;
-    p.work_counter = d_small; p.status = d_small + 1;
+    p.work_counter = &sc->work_counter; p.status = sc->status;
     HN_TRY(launch_relax(h, p));
     launches++;
     HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
@@ -398,7 +412,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
                                                  h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>());
         dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), B, h->first.as<int32_t>(), h->hits.as<int32_t>());
         dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), B, h->flag.as<int32_t>());
-        scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), d_small + 6);
+        scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), &sc->unique_total);
         dedup_finalize_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), h->hits.as<int32_t>(),
                                                    h->rank.as<int32_t>(), B, h->attractor.as<int32_t>(),
                                                    h->ufirst.as<int32_t>(), h->uhits.as<int32_t>());
@@ -406,14 +420,14 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         launches += 5;
     }
     HN_CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
-    int32_t small_host[8];
-    HN_CUDA_TRY(cudaMemcpyAsync(small_host, d_small, sizeof(small_host), cudaMemcpyDeviceToHost, h->st));
+    Scratch host_sc;
+    HN_CUDA_TRY(cudaMemcpyAsync(&host_sc, sc, offsetof(Scratch, asym_flag), cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
-    if (small_host[1]) {
-        set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, small_host[2]);
+    if (host_sc.status[0]) {
+        set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, host_sc.status[1]);
         return HN_E_POOL;
     }
-    h->result_unique = dedup ? small_host[6] : 0;
+    h->result_unique = dedup ? host_sc.unique_total : 0;
     float f = 0, r = 0, q = 0;
     cudaEventElapsedTime(&f, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&r, h->ev[1], h->ev[2]);
@@ -558,9 +572,9 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
     // fields of the noised copies, then ONE sweep each without stability test (UpdateState)
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
     HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
-    HN_TRY(h->small.reserve(256));
-    int32_t* d_small = h->small.as<int32_t>();
-    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    Scratch* sc = h->scratch();
+    HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));
     RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wrow = h->W;
@@ -569,7 +583,7 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
     p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.max_unstable = 0; p.domain = h->cfg.domain;
     p.check_stability = 0; p.serial_stream = 0; 
     p.final_states = h->bitsC.as<uint64_t>();
-    p.work_counter = d_small; p.status = d_small + 1;
+    p.work_counter = &sc->work_counter; p.status = sc->status;
     HN_TRY(launch_relax(h, p));
     if (relaxed_out)
         HN_CUDA_TRY(cudaMemcpyAsync(relaxed_out, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));
@@ -1043,9 +1057,9 @@ int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
     HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
-    HN_TRY(h->small.reserve(256));
-    int32_t* d_small = h->small.as<int32_t>();
-    HN_CUDA_TRY(cudaMemsetAsync(d_small, 0, 128, h->st));
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    Scratch* sc = h->scratch();
+    HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));
     RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wrow = h->W;
@@ -1053,7 +1067,7 @@ int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint
     p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv;
     p.ldp = h->ldp; p.n_pool = n; p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.domain = h->cfg.domain;
     p.check_stability = 0; 
-    p.final_states = h->bitsC.as<uint64_t>(); p.work_counter = d_small; p.status = d_small + 1;
+    p.final_states = h->bitsC.as<uint64_t>(); p.work_counter = &sc->work_counter; p.status = sc->status;
     HN_TRY(launch_relax(h, p));
     HN_CUDA_TRY(cudaMemcpyAsync(states_packed, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));

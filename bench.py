@@ -122,8 +122,9 @@ def main():
     ap.add_argument("--targets", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-delta", action="store_true", help="skip the Delta-rule epoch timing")
-    ap.add_argument("--no-f32", action="store_true", help="skip the extra float32-column-stream measurement")
-    ap.add_argument("--columns", default="f64", choices=["f64", "f32", "i16"], help="column stream of the relaxation kernel")
+    ap.add_argument("--no-f32", action="store_true", help="skip the extra measurements of the other column streams")
+    ap.add_argument("--columns", default="auto", choices=["auto", "f64", "f32", "i16"],
+                    help="column stream of the relaxation kernel (auto = library default: exact int16 stream when available)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,8 +150,9 @@ def main():
     targets, _, pool = synth(n, p, 1, 0x5EED + 3)  # same W / schedule on every rank
     net = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
         hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).SetColumnStream(
-        {"f64": 0, "f32": 1, "i16": 2}[args.columns]).Build()
+        {"f64": 0, "f32": 1, "i16": 2, "auto": 3}[args.columns]).Build()
     net.LearnStates(targets)
+    stream = "i16" if net.integer_stream_active() else ("f32" if args.columns == "f32" else "f64")
     # pinned host staging for the e2e leg
     probes_pinned = torch.from_numpy(probes).pin_memory()
     probes_np = probes_pinned.numpy()
@@ -208,9 +210,12 @@ def main():
         res.Flips.nbytes + res.MarginHits.nbytes + res.AttractorId.nbytes + 2 * 4 * len(res.UniqueFirst) + res.StateHash.nbytes
     # the same step with the float32 / exact-int16 column streams (bit-identical results, 1/2 and 1/4 of the column
     # bytes): reported beside the headline, never as the headline
-    alt_ms = {"f32": 0.0, "i16": 0.0}
-    if args.columns == "f64" and not args.no_f32:
-        for name, mode in (("f32", 1), ("i16", 2)):
+    alt_ms = {"f64": 0.0, "f32": 0.0, "i16": 0.0}
+    alt_relax_ms = dict(alt_ms)
+    if not args.no_f32:
+        for name, mode in (("f64", 0), ("f32", 1), ("i16", 2)):
+            if name == stream:
+                continue
             alt = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetEpochs(1).SetNetworkLearningRule(
                 hn.HebbianLearningRule).SetNetworkLearningMethod(hn.FullSetMethod).SetSeed(1).SetDevice(local).SetColumnStream(mode).Build()
             alt.LearnStates(targets)          # in-library learning: the integer structure is captured at normalisation
@@ -218,11 +223,13 @@ def main():
             alt.upload_probes(probes_np)
             alt.relax_resident(dedup=True)
             alt_ms[name] = alt.relax_resident(dedup=True)
+            alt_relax_ms[name] = alt.last_timing().relax_ms
             alt.close()
-    tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t)), alt_ms["f32"], alt_ms["i16"]], device="cuda", dtype=torch.float64)
+    tmax = torch.tensor([step_ms, float(np.sum(relax_ms)), float(np.mean(e2e_t)), alt_ms["f64"], alt_ms["f32"], alt_ms["i16"],
+                         alt_relax_ms["f64"]], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    step_ms_max, relax_ms_max, e2e_max, f32_ms_max, i16_ms_max = [float(x) for x in tmax.cpu()]
+    step_ms_max, relax_ms_max, e2e_max, f64_ms_max, f32_ms_max, i16_ms_max, f64_relax_ms_max = [float(x) for x in tmax.cpu()]
     delta_ms = {}
     if not args.no_delta:   # collective when world > 1: every rank takes part
         if world == 1:
@@ -237,37 +244,59 @@ def main():
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
         achieved = alg_bytes * args.steps / (relax_ms_max * 1e-3) / 1e9
+        col_bytes = {"f64": 8, "f32": 4, "i16": 2}[stream]
+        field_bytes = 4 if stream == "i16" else 8
+        streamed = col_bytes * n * flips + field_bytes * n * sweeps     # what this stream really moves L2->SM per launch
+        kernel = {"f64": "relax_kernel<16,double,256>", "f32": "relax_kernel<16,float,256>", "i16": "relax_kernel<16,short,256>"}[stream]
+        notes = {
+            "f64": "bounded by the L2->SM fabric: every flip moves its 8N-byte column L2->SM (~9.7 TB/s, ~33 B/clk/SM)",
+            "f32": "float32 shadow of W: 4N bytes per flip, float64 fields, exact re-evaluation inside the grown margin",
+            "i16": "exact integer stream: int32 fields and int16 columns (2N bytes per flip) give the reference's float64 "
+                   "decisions bit for bit; exact ties are re-evaluated in float64 in the reference's summation order"}
         line = {"metric": METRIC, "value": world * b * args.steps / (step_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": cfg["name"], "N": n, "P": p, "probes_per_gpu": b,
-                           "l2": "inputs larger than L2 (W 128 MiB + 4 GiB of initial fields streamed per step)"},
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64" if stream != "i16" else "f64 (decisions taken on an exact int32 image of the float64 fields)",
+                "data": "synthetic",
+                "config": {"workload": cfg["name"], "N": n, "P": p, "probes_per_gpu": b, "column_stream": f"{args.columns} -> {stream}",
+                           "l2": "inputs larger than L2 (W 128 MiB + 2-4 GiB of initial fields streamed per step)"},
                 "e2e": {"value": world * b / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             "traffic": None, "kernel": "relax_kernel<16,double>",
-                             "note": "per GPU; algorithmic bytes 8N per flip + 8N per sweep (SURVEY 8d) over the relaxation "
-                                     "kernel time; >1 because columns are served from L2 (see traffic); the kernel is bounded "
-                                     "by the L2->SM fabric (every flip moves its 8N-byte column L2->SM: ~9.7 TB/s, ~33 B/clk/SM), profiles/r01_relax_final_ncu_summary.txt",
+                             "traffic": None, "kernel": kernel,
+                             "note": "per GPU; achieved = ALGORITHMIC bytes of the reference algorithm (8N per flip + 8N per sweep, "
+                                     "SURVEY 8d) over the relaxation kernel time; >1 because W stays in L2 (see traffic) and "
+                                     "this stream moves fewer bytes than the algorithm names (streamed_bytes_per_launch); "
+                                     + notes[stream] + "; profiles/r01_relax_final_ncu_summary.txt",
                              "peak_source": "measured" if peaks else "fallback",
-                             "algorithmic_bytes_per_launch": int(alg_bytes), "flips_per_probe": flips / b,
-                             "sweeps_per_probe": sweeps / b},
+                             "algorithmic_bytes_per_launch": int(alg_bytes), "streamed_bytes_per_launch": int(streamed),
+                             "streamed_gbs": streamed * args.steps / (relax_ms_max * 1e-3) / 1e9,
+                             "flips_per_probe": flips / b, "sweeps_per_probe": sweeps / b},
                 "clocks": sampler.summary(), "wall_s": wall,
                 "stage_ms_per_step": {"fields_gemm": float(np.mean(fields_ms)), "relax": float(np.mean(relax_ms)),
                                       "dedup": float(np.mean(post_ms))},
-                "value_f32_column_stream": (world * b / (f32_ms_max * 1e-3)) if f32_ms_max > 0 else None,
-                "value_i16_exact_integer_stream": (world * b / (i16_ms_max * 1e-3)) if i16_ms_max > 0 else None,
                 "alt_streams_note": "same step, same inputs, bit-identical results (tests/test_gpu_f32_columns.py, "
-                                    "tests/test_gpu_i16_columns.py); reported beside the float64 headline, not as it",
+                                    "tests/test_gpu_i16_columns.py, tests/test_gpu_auto_columns.py)",
                 "margin_hits_per_probe": out.total_margin_hits / b,
                 "unique_attractors": int(n_unique_global if n_unique_global is not None else out.n_unique)}
-        try:   # DRAM bytes of the relaxation kernel from the committed ncu capture of this command (per launch)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_relax_traffic.json")))
-            if tr.get("probes_per_launch") == b and tr.get("N") == n:
-                line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
-                line["roofline"]["traffic_source"] = tr["source"]
+        for name, ms in (("f64", f64_ms_max), ("f32", f32_ms_max), ("i16", i16_ms_max)):
+            if ms > 0:
+                line[f"value_{name}_column_stream"] = world * b / (ms * 1e-3)
+        traffic = {}
+        try:   # DRAM bytes of the relaxation kernels from the committed ncu captures of this command (per launch)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_relax_traffic.json")))
         except Exception:
             pass
+        tr = traffic.get(stream, {})
+        if tr.get("probes_per_launch") == b and tr.get("N") == n:
+            line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+            line["roofline"]["traffic_source"] = tr["source"]
+        if stream != "f64" and f64_relax_ms_max > 0:   # the float64 stream's own roofline beside the headline
+            ach64 = alg_bytes / (f64_relax_ms_max * 1e-3) / 1e9
+            t64 = traffic.get("f64", {})
+            line["roofline_f64_stream"] = {"bound": "hbm", "achieved": ach64, "peak": hbm, "unit": "GB/s", "frac": ach64 / hbm,
+                                           "traffic": t64.get("dram_bytes_per_launch") if t64.get("probes_per_launch") == b and t64.get("N") == n else None,
+                                           "kernel": "relax_kernel<16,double,256>", "note": notes["f64"]}
         if not args.no_delta:
             line["delta_epoch_ms"] = dict(delta_ms, note="wall clock (max over ranks) through hn_delta_epoch + hn_energy_profiles "
                                           "with host buffers (H2D of packed targets, noised copies and permutations inside the timed "

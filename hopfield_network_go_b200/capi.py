@@ -15,7 +15,7 @@ from . import build as _build
 HN_OK = 0
 HN_E_INVALID, HN_E_NO_DEVICE, HN_E_CUDA, HN_E_OOM, HN_E_POOL, HN_E_NCCL, HN_E_STATE = -1, -2, -3, -4, -5, -6, -7
 HN_RELAX_SERIAL_STREAM, HN_RELAX_DEDUP, HN_RELAX_HISTORY = 0x1, 0x2, 0x4
-HN_COLUMNS_F64, HN_COLUMNS_F32, HN_COLUMNS_I16 = 0, 1, 2
+HN_COLUMNS_F64, HN_COLUMNS_F32, HN_COLUMNS_I16, HN_COLUMNS_AUTO = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
     "hn_default_config", "hn_abi_version", "hn_last_error", "hn_create", "hn_destroy", "hn_set_weights",

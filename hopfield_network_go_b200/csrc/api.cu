@@ -241,6 +241,7 @@ int ensure_w32(hn_handle h) {
 }
 
 // point p at the column stream selected by the configuration and set the matching per-flip margin growth
+bool integer_stream(hn_handle h);
 int select_columns(hn_handle h, RelaxParams& p) {
     const double dscale = h->cfg.domain == HN_DOMAIN_BINARY ? 1.0 : 2.0;
     p.tau_base = h->tau_base;
@@ -250,7 +251,7 @@ int select_columns(hn_handle h, RelaxParams& p) {
         p.Wcol = h->W32;
         // |fl32(w) - w| <= 2^-24 |w| (+ a denormal floor): each flip perturbs a field by at most delta*max|W|*2^-24
         p.tau_flip += 2.0 * dscale * (h->maxabs * 5.9604644775390625e-08 + 1.5e-45);
-    } else if (h->cfg.column_stream == HN_COLUMNS_I16 && h->int_ok) {
+    } else if (integer_stream(h)) {
         p.Wcol = h->K16;
         p.int_scale = h->int_scale;
     } else {
@@ -258,7 +259,8 @@ int select_columns(hn_handle h, RelaxParams& p) {
     }
     return HN_OK;
 }
-bool integer_stream(hn_handle h) { return h->cfg.column_stream == HN_COLUMNS_I16 && h->int_ok; }
+bool wants_integer_stream(hn_handle h) { return h->cfg.column_stream == HN_COLUMNS_I16 || h->cfg.column_stream == HN_COLUMNS_AUTO; }
+bool integer_stream(hn_handle h) { return wants_integer_stream(h) && h->int_ok; }
 
 template <int UPT, typename CT, int THREADS = 256>
 int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
@@ -682,7 +684,7 @@ void hn_default_config(hn_config* cfg) {
     cfg->max_relax_iterations = 100;
     cfg->learning_rate = 1.0;
     cfg->device = 0;
-    cfg->column_stream = HN_COLUMNS_F64;
+    cfg->column_stream = HN_COLUMNS_AUTO;
 }
 
 int hn_create(const hn_config* cfg, hn_handle* out) {
@@ -696,7 +698,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     if (cfg->dimension > 65535) { set_error("dimension %d exceeds 65535 (uint16 unit indices)", cfg->dimension); return HN_E_INVALID; }
     if (cfg->domain != HN_DOMAIN_BIPOLAR && cfg->domain != HN_DOMAIN_BINARY) { set_error("unknown domain %d", cfg->domain); return HN_E_INVALID; }
     if (cfg->max_relax_iterations <= 0) { set_error("max_relax_iterations must be positive"); return HN_E_INVALID; }
-    if (cfg->column_stream < HN_COLUMNS_F64 || cfg->column_stream > HN_COLUMNS_I16) { set_error("unknown column_stream %d", cfg->column_stream); return HN_E_INVALID; }
+    if (cfg->column_stream < HN_COLUMNS_F64 || cfg->column_stream > HN_COLUMNS_AUTO) { set_error("unknown column_stream %d", cfg->column_stream); return HN_E_INVALID; }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev <= 0) {
@@ -887,7 +889,7 @@ int hn_normalize_frobenius(hn_handle h, double* norm_out) {
     const int np = 1024;
     HN_TRY(h->partial.reserve(sizeof(double) * (np + 2)));
     double* part = h->partial.as<double>();
-    const bool capture = h->cfg.column_stream == HN_COLUMNS_I16;
+    const bool capture = wants_integer_stream(h);
     if (capture) {  // keep the un-normalised matrix: W = (1/norm) * Wraw is the integer structure of the new weights
         const size_t wb = sizeof(double) * (size_t)h->N * h->ldw;
         if (!h->Wraw) HN_CUDA_TRY(cudaMalloc(&h->Wraw, wb));

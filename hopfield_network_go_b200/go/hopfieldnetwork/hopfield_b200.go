@@ -71,7 +71,7 @@ func check(rc C.int) {
 func newDeviceNetwork(net *HopfieldNetwork, device int, initial []float64) *HopfieldNetwork {
 	var cfg C.hn_config
 	C.hn_default_config(&cfg)
-	// cfg.column_stream: C.HN_COLUMNS_F64 (default), C.HN_COLUMNS_F32 or C.HN_COLUMNS_I16 — results are identical,
+	// cfg.column_stream: C.HN_COLUMNS_AUTO (default), C.HN_COLUMNS_F64, C.HN_COLUMNS_F32 or C.HN_COLUMNS_I16 — results are identical,
 	// see include/hopfield_b200.h; a SetColumnStream builder option can expose it.
 	cfg.dimension = C.int32_t(net.dimension)
 	cfg.domain = C.int32_t(net.domain)

@@ -335,7 +335,7 @@ class HopfieldNetworkBuilder:
         self.allowIntensiveDataCollection = False
         self.seed = None     # additive: SetSeed
         self.device = 0      # additive: SetDevice
-        self.columnStream = capi.HN_COLUMNS_F64  # additive: SetColumnStream
+        self.columnStream = capi.HN_COLUMNS_AUTO  # additive: SetColumnStream
 
     def SetRandMatrixInit(self, f): self.randMatrixInit = f; return self
     def SetNetworkDimension(self, d): self.dimension = d; return self

@@ -96,10 +96,10 @@ typedef struct hn_config {
     int32_t max_relax_iterations;      /* SetMaximumRelaxationIterations (default 100)        */
     double  learning_rate;             /* SetLearningRate (default 1.0)                       */
     int32_t device;                    /* CUDA device ordinal (additive extension)            */
-    int32_t column_stream;             /* HN_COLUMNS_F64 (default) or HN_COLUMNS_F32, see below */
+    int32_t column_stream;             /* HN_COLUMNS_AUTO (default), _F64, _F32 or _I16, see below */
 } hn_config;
 
-/* Column stream of the relaxation kernel (additive extension; results are bit-identical in both modes).
+/* Column stream of the relaxation kernel (additive extension; results are bit-identical in every mode).
  * A flip of unit k adds +-delta*W[:,k] to the resident float64 fields.
  *   HN_COLUMNS_F64  the column is read from the float64 matrix (8N bytes per flip).
  *   HN_COLUMNS_F32  the column is read from a float32-rounded shadow copy of W (4N bytes per flip; the shadow of
@@ -117,6 +117,11 @@ typedef struct hn_config {
 #define HN_COLUMNS_F64 0
 #define HN_COLUMNS_F32 1
 #define HN_COLUMNS_I16 2
+/*   HN_COLUMNS_AUTO the default: HN_COLUMNS_I16 whenever the integer structure of the current weights is known and
+ *                   passes its exactness checks, HN_COLUMNS_F64 otherwise (random initial matrix, hn_set_weights,
+ *                   thermal rules, non-dyadic learning rate).  Results are bit-identical either way;
+ *                   hn_integer_stream_active tells which one the next relaxation uses.                           */
+#define HN_COLUMNS_AUTO 3
 
 typedef struct hn_handle_s* hn_handle;
 

@@ -30,6 +30,7 @@ def gpu_net(n, domain=0, **kw):
     b = hn.NewHopfieldNetworkBuilder().SetNetworkDimension(n).SetNetworkDomain(domain).SetEpochs(kw.pop("epochs", 1))
     b.SetNetworkLearningRule(kw.pop("rule", hn.HebbianLearningRule)).SetNetworkLearningMethod(kw.pop("method", hn.FullSetMethod))
     b.SetSeed(kw.pop("seed", 1))
+    kw.setdefault("SetColumnStream", 0)   # HN_COLUMNS_F64 unless a test asks for another stream (AUTO: test_gpu_auto_columns.py)
     for k, v in kw.items():
         getattr(b, k)(v)
     return b.Build()

@@ -39,6 +39,7 @@ def test_struct_layouts_match_header(built):
     capi.load().hn_default_config(C.byref(cfg))
     assert (cfg.domain, cfg.force_symmetric, cfg.force_zero_diagonal, cfg.max_relax_unstable_units,
             cfg.max_relax_iterations, cfg.learning_rate) == (0, 1, 1, 0, 100, 1.0)   # HopfieldNetworkBuilder.go:40-55
+    assert cfg.column_stream == capi.HN_COLUMNS_AUTO == 3
 
 
 def test_no_cpu_fallback(built):

@@ -126,10 +126,11 @@ template <int UPT> struct RelaxCfg {
     static constexpr int VEC = UPT >= 4 ? 4 : UPT;   // contiguous units per ownership chunk
     static constexpr int NCH = UPT / VEC;            // chunks per thread
 };
+static inline int relax_cand_words(int nbw) { return (nbw + 31) / 32 * 32 + 32; }   // scan reads 32 words from any word < nbw
 static inline size_t relax_smem_bytes(int N, int ldp, int upt) {  // independent of the thread count
     const int nbw = (N + 31) / 32;
     (void)upt;
-    return (size_t)((nbw + 3) / 4 * 4) * 4 * 2 + (size_t)((ldp + 7) / 8 * 8) * 2 * 2;
+    return (size_t)((nbw + 3) / 4 * 4 + relax_cand_words(nbw)) * 4 + (size_t)((ldp + 7) / 8 * 8) * 2 * 2;
 }
 
 template <int UPT, typename CT, int THREADS>
@@ -150,8 +151,9 @@ relax_kernel(RelaxParams p) {
     const int nbw = (p.N + 31) / 32;
     const int nbw4 = (nbw + 3) / 4 * 4, ldp8 = (p.ldp + 7) / 8 * 8;
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);
+    const int ncw = ((nbw + 31) / 32) * 32 + 32;   // relax_cand_words(nbw); words >= nbw stay zero
     uint32_t* s_cand = s_bits + nbw4;
-    uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_cand + nbw4);
+    uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_cand + ncw);
     uint16_t* s_inv = s_perm + ldp8;
     __shared__ __align__(16) uint32_t s_red[2][32];
     __shared__ double s_exact[4];
@@ -218,9 +220,16 @@ relax_kernel(RelaxParams p) {
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
         T = thr(0);
-        FT h[UPT];         // float64: local fields h of my units.  Integer stream: ALIGNED exact fields a = g*v
-                           // (g = scale*Wraw*s, v = +-1 by the unit's bit): candidate <=> a <= 0, exact tie <=> a == 0
-        int sv[INTF ? UPT : 1];   // integer stream: v * delta of my units (the sign a column entry enters a with)
+        FT h[UPT];         // float64: local fields h of my units.  Integer stream: ALIGNED exact fields minus one,
+                           // a' = g*v - 1 (g = scale*Wraw*s, v = +-1 by the unit's bit): candidate <=> a' < 0 (one
+                           // funnel shift per unit collects the sign bits), exact tie <=> a' == -1
+        int q[INTF ? (UPT + 1) / 2 : 1];   // integer stream: v * delta of my units as signed bytes, two units per word
+                                           // (even unit: byte 0, odd unit: byte 3) = the multipliers of dp2a.lo / dp2a.hi
+        const int qneg = p.domain == HN_DOMAIN_BINARY ? 0xFE : 0xFC;   // byte ^ qneg negates +-1 (binary) / +-2 (bipolar)
+        if constexpr (INTF) {
+#pragma unroll
+            for (int j = 0; j < (UPT + 1) / 2; j++) q[j] = 0;
+        }
         mask_t sbm = 0;    // my units' current bits; SIGNW(r) = 0x80000000 when the bit is clear (v = -1): hi32(h)^SIGNW = hi32(h*v)
 #define SIGNW(r) ((int)((uint32_t)((~sbm >> (r)) & 1u) << 31))
 #pragma unroll
@@ -233,26 +242,38 @@ relax_kernel(RelaxParams p) {
                     sbm |= (mask_t)b << r;
                     if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
                         const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
-                        h[r] = b ? g : -g;
-                        sv[r] = b ? (int)dscale : -(int)dscale;
+                        h[r] = (b ? g : -g) - 1;
+                        q[r >> 1] |= ((b ? (int)dscale : -(int)dscale) & 0xFF) << ((r & 1) ? 24 : 0);
                     } else h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited
                     sbm |= (mask_t)1 << r;
-                    if constexpr (INTF) { h[r] = 0x7FFFFFFF; sv[r] = 0; } else h[r] = __longlong_as_double(0x7FF0000000000000LL);
+                    if constexpr (INTF) h[r] = 0x7FFFFFFF; else h[r] = __longlong_as_double(0x7FF0000000000000LL);   // (its column entries are 0)
                 }
             }
         }
         // candidacy of my units: bit r set iff hi32(h*v) < T   (aligned field below tau)
         auto cand_mask = [&]() -> mask_t {
             mask_t m = 0;
+            if constexpr (INTF) {   // sign bit of a': wants to flip (aligned < 0) or exact tie (== 0)
 #pragma unroll
-            for (int r = 0; r < UPT; r++) {
-                bool c;
-                if constexpr (INTF) c = h[r] <= 0;   // wants to flip (aligned < 0) or exact tie (== 0)
-                else c = (__double2hiint(h[r]) ^ SIGNW(r)) < T;
-                if (c) m |= (mask_t)1 << r;
+                for (int r = UPT - 1; r >= 0; r--) m = (mask_t)__funnelshift_l((uint32_t)h[r], (uint32_t)m, 1);
+            } else {
+#pragma unroll
+                for (int r = 0; r < UPT; r++)
+                    if ((__double2hiint(h[r]) ^ SIGNW(r)) < T) m |= (mask_t)1 << r;
             }
             return m;
+        };
+        // integer stream, owner of a flipping unit: its own sign changes, so its aligned field and its column sign
+        // are negated (a -> -a  <=>  a' -> ~a' - 1).  Commutes with the column update of the same flip.
+        auto owner_flip = [&](int rr, int k) {
+            if constexpr (INTF) {
+#pragma unroll
+                for (int r = 0; r < UPT; r++)
+                    if (r == rr) { h[r] = ~h[r] - 1; q[r >> 1] ^= qneg << ((r & 1) ? 24 : 0); }
+                sbm ^= (mask_t)1 << rr;
+                s_bits[k >> 5] ^= 1u << (k & 31);
+            }
         };
         mask_t cm = cand_mask();
         if (p.history) {
@@ -271,7 +292,7 @@ relax_kernel(RelaxParams p) {
                 reinterpret_cast<uint32_t*>(s_perm)[i] = reinterpret_cast<const uint32_t*>(permrow)[i];
                 reinterpret_cast<uint32_t*>(s_inv)[i] = reinterpret_cast<const uint32_t*>(invrow)[i];
             }
-            for (int w = tid; w < nbw4; w += RELAX_THREADS) s_cand[w] = 0u;
+            for (int w = tid; w < ncw; w += RELAX_THREADS) s_cand[w] = 0u;
             __syncthreads();
             {   // bitmap of this sweep's order from the candidacy masks held in registers
                 mask_t m = cm;
@@ -288,16 +309,15 @@ relax_kernel(RelaxParams p) {
             for (;;) {
                 // ---- scan ahead (every warp, redundantly): first set bit of the bitmap at position >= base ----
                 int found = -1;
-                for (int w0 = base >> 5; w0 < nbw; w0 += 32) {
-                    const int wi = w0 + lane;
-                    uint32_t word = wi < nbw ? s_cand[wi] : 0u;
-                    if (wi == (base >> 5)) word &= 0xFFFFFFFFu << (base & 31);
-                    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0u);
-                    if (nz) {
-                        const int l = __ffs(nz) - 1;
-                        const uint32_t wsel = __shfl_sync(0xFFFFFFFFu, word, l);
-                        found = (w0 + l) * 32 + __ffs(wsel) - 1;
-                        break;
+                {
+                    uint32_t first = lane == 0 ? 0xFFFFFFFFu << (base & 31) : 0xFFFFFFFFu;   // positions < base are done
+                    for (int w0 = base >> 5; w0 < nbw; w0 += 32) {
+                        const int wi = w0 + lane;
+                        const uint32_t word = s_cand[wi] & first;            // padded with zero words: no bounds check
+                        uint32_t pos = word ? (uint32_t)(wi * 32 + __ffs((int)word) - 1) : RELAX_NONE;
+                        pos = __reduce_min_sync(0xFFFFFFFFu, pos);
+                        if (pos != RELAX_NONE) { found = (int)pos; break; }
+                        first = 0xFFFFFFFFu;
                     }
                 }
                 if (found < 0) break;  // sweep finished
@@ -311,8 +331,9 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                         for (int r = 0; r < UPT; r++)
                             if (r == rr) { if constexpr (INTF) a = h[r]; else a = __double2hiint(h[r]); }
-                        const bool inside = INTF ? (a == 0) : ((a & 0x7FFFFFFF) < T);
+                        const bool inside = INTF ? (a == -1) : ((a & 0x7FFFFFFF) < T);
                         s_flag = (inside ? 2 : 0) | (int)((sbm >> rr) & 1u);
+                        if constexpr (INTF) { if (!inside) owner_flip(rr, k); }   // a' < -1: the flip is certain
                     }
                 }
                 __syncthreads();
@@ -323,6 +344,12 @@ relax_kernel(RelaxParams p) {
                     const double hx = exact_field(k);
                     margin++;
                     nb = hx > 0.0 ? 1u : 0u;
+                    if constexpr (INTF) {
+                        if (nb != ob) {
+                            const int ch = k / VEC, ke = k % VEC;
+                            if ((ch % RELAX_THREADS) == tid) owner_flip((ch / RELAX_THREADS) * VEC + ke, k);
+                        }
+                    }
                 }
                 if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
@@ -337,28 +364,39 @@ relax_kernel(RelaxParams p) {
                 }
                 {   // one coalesced pass over column k (row k of Wcol), fused into the register-resident fields
                     const CT* col = reinterpret_cast<const CT*>(p.Wcol) + (size_t)k * p.ldw;
-                    const FT d = nb ? (FT)dscale : (FT)(-dscale);
-                    auto pass = [&](auto full_tag, auto up_tag) {
+                    const double d = nb ? dscale : -dscale;
+                    const int qdir = nb ? 0 : (qneg | (qneg << 24));   // integer stream: 1 -> 0 enters with the opposite sign
+                    auto pass = [&](auto full_tag) {
                         constexpr bool FULL = decltype(full_tag)::value;   // every chunk lies inside the padded row
-                        constexpr bool UP = decltype(up_tag)::value;       // integer stream: the flipped unit goes 0 -> 1
 #pragma unroll
                         for (int c = 0; c < NCH; c++) {
                             const int u0 = unit_of(c, 0);
-                            FT w[VEC];
+                            if constexpr (INTF) {   // exact int16 column stream, 2N bytes per flip: a' += (v*(+-delta)) * K by dp2a
+                                int x[(VEC + 1) / 2];
 #pragma unroll
-                            for (int e = 0; e < VEC; e++) w[e] = (FT)0;
-                            if (FULL || u0 < p.ldw) {
-                                if constexpr (INTF) {              // exact int16 column stream: 2N bytes per flip
+                                for (int e = 0; e < (VEC + 1) / 2; e++) x[e] = 0;
+                                if (FULL || u0 < p.ldw) {
                                     if (VEC == 4) {
-                                        const int2 x = __ldg(reinterpret_cast<const int2*>(col + u0));
-                                        w[0] = (short)(x.x & 0xFFFF); w[1] = x.x >> 16; w[2] = (short)(x.y & 0xFFFF); w[3] = x.y >> 16;
+                                        const int2 t = __ldg(reinterpret_cast<const int2*>(col + u0));
+                                        x[0] = t.x; x[(VEC + 1) / 2 - 1] = t.y;
                                     } else if (VEC == 2) {
-                                        const int x = __ldg(reinterpret_cast<const int*>(col + u0));
-                                        w[0] = (short)(x & 0xFFFF); w[1] = x >> 16;
+                                        x[0] = __ldg(reinterpret_cast<const int*>(col + u0));
                                     } else {
-                                        w[0] = __ldg(col + u0);
+                                        x[0] = (int)__ldg(col + u0);   // hi half = sign bits, multiplied by byte 1 = 0
                                     }
-                                } else if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
+                                }
+#pragma unroll
+                                for (int e = 0; e < VEC; e++) {
+                                    const int r = c * VEC + e;
+                                    const int qd = q[r >> 1] ^ qdir;
+                                    h[r] = (r & 1) ? __dp2a_hi(x[e >> 1], qd, h[r]) : __dp2a_lo(x[e >> 1], qd, h[r]);
+                                }
+                            } else {
+                            double w[VEC];
+#pragma unroll
+                            for (int e = 0; e < VEC; e++) w[e] = 0.0;
+                            if (FULL || u0 < p.ldw) {
+                                if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
                                     if (VEC == 4) {
                                         const float4 x = __ldg(reinterpret_cast<const float4*>(col + u0));
                                         w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
@@ -381,24 +419,13 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                             for (int e = 0; e < VEC; e++) {
                                 const int r = c * VEC + e;
-                                if constexpr (INTF) { if (UP) h[r] += sv[r] * w[e]; else h[r] -= sv[r] * w[e]; }   // a += v*(+-delta)*K
-                                else h[r] = fma(d, w[e], h[r]);
+                                h[r] = fma(d, w[e], h[r]);
+                            }
                             }
                         }
                     };
-                    if (p.ldw == NU) { if (nb) pass(std::true_type{}, std::true_type{}); else pass(std::true_type{}, std::false_type{}); }
-                    else { if (nb) pass(std::false_type{}, std::true_type{}); else pass(std::false_type{}, std::false_type{}); }
-                }
-                if constexpr (INTF) {   // owner: its own sign changed -> negate its aligned field and its column sign
-                    const int ch = k / VEC, ke = k % VEC;
-                    if ((ch % RELAX_THREADS) == tid) {
-                        const int rr = (ch / RELAX_THREADS) * VEC + ke;
-#pragma unroll
-                        for (int r = 0; r < UPT; r++)
-                            if (r == rr) { h[r] = -h[r]; sv[r] = -sv[r]; }
-                        sbm ^= (mask_t)1 << rr;
-                        s_bits[k >> 5] ^= 1u << (k & 31);
-                    }
+                    (void)qdir; (void)d;
+                    if (p.ldw == NU) pass(std::true_type{}); else pass(std::false_type{});
                 }
                 if (!INTF && ((flips + 1) & (RELAX_TAU_STEP - 1)) == 0) T = thr(flips + 1);  // candidacy below is re-derived with it
                 {
@@ -429,7 +456,7 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
                 if constexpr (INTF) {
-                    if (h[r] < 0) cnt++;           // aligned field negative: certainly unstable
+                    if (h[r] < -1) cnt++;          // aligned field negative: certainly unstable
                 } else {
                     const int a = __double2hiint(h[r]) ^ SIGNW(r);
                     if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
@@ -444,7 +471,7 @@ relax_kernel(RelaxParams p) {
                 for (int r = 0; r < UPT; r++) {
                     const int u = unit_of_r(r);
                     bool inside;
-                    if constexpr (INTF) inside = h[r] == 0; else inside = (__double2hiint(h[r]) & 0x7FFFFFFF) < T;
+                    if constexpr (INTF) inside = h[r] == -1; else inside = (__double2hiint(h[r]) & 0x7FFFFFFF) < T;
                     if (inside && u > last) cmin = min(cmin, (uint32_t)u);
                 }
                 cmin = block_min(cmin);

@@ -133,6 +133,22 @@ static inline size_t relax_smem_bytes(int N, int ldp, int upt) {  // independent
     return (size_t)((nbw + 3) / 4 * 4 + relax_cand_words(nbw)) * 4 + (size_t)((ldp + 7) / 8 * 8) * 2 * 2;
 }
 
+// v[idx] for a register-resident array and a run-time index: a binary tree of selects (N-1 selects, log2 N deep)
+// instead of the N-long dependent compare/select chain a loop would give.
+template <int N_>
+__device__ __forceinline__ int tree_select(const int (&v)[N_], int idx) {
+    int t[N_];
+#pragma unroll
+    for (int i = 0; i < N_; i++) t[i] = v[i];
+#pragma unroll
+    for (int s = 1; s < N_; s <<= 1) {
+        const bool up = (idx & s) != 0;
+#pragma unroll
+        for (int i = 0; i + s < N_; i += 2 * s) t[i] = up ? t[i + s] : t[i];
+    }
+    return t[0];
+}
+
 template <int UPT, typename CT, int THREADS>
 __global__ void __launch_bounds__(THREADS, (UPT <= 16 ? ((std::is_same<CT, int16_t>::value ? RELAX_MIN_CTAS_INT : RELAX_MIN_CTAS) * 256) / THREADS : 1))
 relax_kernel(RelaxParams p) {
@@ -161,7 +177,10 @@ relax_kernel(RelaxParams p) {
     __shared__ int s_flag;
     __shared__ long long s_rowbase;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tid = threadIdx.x;
+    asm volatile("" : "+r"(tid));   // keep the thread index in a register (the compiler would re-read SR_TID every flip)
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool full_rows = p.ldw == NU;   // every ownership chunk lies inside the padded row: unpredicated column pass
     const int N = p.N;
     const double dscale = p.domain == HN_DOMAIN_BINARY ? 1.0 : 2.0;
     // Margin threshold on the hi word, valid for the next RELAX_TAU_STEP flips: T(F) = hi32(tau(F + STEP)) + 1.
@@ -239,7 +258,7 @@ relax_kernel(RelaxParams p) {
                 const int u = unit_of(c, e), r = c * VEC + e;
                 if (u < N) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
-                    sbm |= (mask_t)b << r;
+                    if constexpr (!INTF) sbm |= (mask_t)b << r;
                     if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
                         const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
                         h[r] = (b ? g : -g) - 1;
@@ -255,8 +274,18 @@ relax_kernel(RelaxParams p) {
         auto cand_mask = [&]() -> mask_t {
             mask_t m = 0;
             if constexpr (INTF) {   // sign bit of a': wants to flip (aligned < 0) or exact tie (== 0)
+                if constexpr (UPT >= 8) {   // two independent chains halve the dependent latency
+                    uint32_t hi = 0, lo = 0;
 #pragma unroll
-                for (int r = UPT - 1; r >= 0; r--) m = (mask_t)__funnelshift_l((uint32_t)h[r], (uint32_t)m, 1);
+                    for (int r = UPT / 2 - 1; r >= 0; r--) {
+                        hi = __funnelshift_l((uint32_t)h[r + UPT / 2], hi, 1);
+                        lo = __funnelshift_l((uint32_t)h[r], lo, 1);
+                    }
+                    m = (mask_t)((hi << (UPT / 2)) | lo);
+                } else {
+#pragma unroll
+                    for (int r = UPT - 1; r >= 0; r--) m = (mask_t)__funnelshift_l((uint32_t)h[r], (uint32_t)m, 1);
+                }
             } else {
 #pragma unroll
                 for (int r = 0; r < UPT; r++)
@@ -271,9 +300,8 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                 for (int r = 0; r < UPT; r++)
                     if (r == rr) { h[r] = ~h[r] - 1; q[r >> 1] ^= qneg << ((r & 1) ? 24 : 0); }
-                sbm ^= (mask_t)1 << rr;
-                s_bits[k >> 5] ^= 1u << (k & 31);
-            }
+            } else sbm ^= (mask_t)1 << rr;
+            s_bits[k >> 5] ^= 1u << (k & 31);
         };
         mask_t cm = cand_mask();
         if (p.history) {
@@ -323,18 +351,19 @@ relax_kernel(RelaxParams p) {
                 if (found < 0) break;  // sweep finished
                 base = found + 1;
                 const int k = s_perm[found];
-                {   // owner of k publishes: bit1 = inside the margin, bit0 = current (old) bit
-                    const int ch = k / VEC, ke = k % VEC;
-                    if ((ch % RELAX_THREADS) == tid) {
-                        const int rr = (ch / RELAX_THREADS) * VEC + ke;
-                        int a = 0;
+                const int kch = k / VEC;
+                const bool owner = (kch % RELAX_THREADS) == tid;
+                if (owner) {   // publishes: bit1 = inside the margin (integer stream: exact tie), bit0 = current (old) bit
+                    const int rr = (kch / RELAX_THREADS) * VEC + k % VEC;   // register slot of unit k
+                    int hw[UPT];
 #pragma unroll
-                        for (int r = 0; r < UPT; r++)
-                            if (r == rr) { if constexpr (INTF) a = h[r]; else a = __double2hiint(h[r]); }
-                        const bool inside = INTF ? (a == -1) : ((a & 0x7FFFFFFF) < T);
-                        s_flag = (inside ? 2 : 0) | (int)((sbm >> rr) & 1u);
-                        if constexpr (INTF) { if (!inside) owner_flip(rr, k); }   // a' < -1: the flip is certain
-                    }
+                    for (int r = 0; r < UPT; r++) { if constexpr (INTF) hw[r] = h[r]; else hw[r] = __double2hiint(h[r]); }
+                    const int a = tree_select(hw, rr);
+                    const bool inside = INTF ? (a == -1) : ((a & 0x7FFFFFFF) < T);
+                    const uint32_t obit = (s_bits[k >> 5] >> (k & 31)) & 1u;
+                    s_flag = (inside ? 2 : 0) | (int)obit;
+                    if (!inside) owner_flip(rr, k);   // outside the margin the flip is certain: new bit into the packed state
+                                                      // and the sign mask (integer stream: negate the aligned field)
                 }
                 __syncthreads();
                 const int fl = s_flag;
@@ -344,26 +373,13 @@ relax_kernel(RelaxParams p) {
                     const double hx = exact_field(k);
                     margin++;
                     nb = hx > 0.0 ? 1u : 0u;
-                    if constexpr (INTF) {
-                        if (nb != ob) {
-                            const int ch = k / VEC, ke = k % VEC;
-                            if ((ch % RELAX_THREADS) == tid) owner_flip((ch / RELAX_THREADS) * VEC + ke, k);
-                        }
-                    }
+                    if (nb != ob && owner) owner_flip((kch / RELAX_THREADS) * VEC + k % VEC, k);
                 }
                 if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
                 // ---- flip unit k: h += d * W[:,k] over my units; toggle the bitmap where candidacy changed ----
-                if constexpr (!INTF) {   // owner: new bit into its sign mask and the packed state
-                    const int ch = k / VEC, ke = k % VEC;
-                    if ((ch % RELAX_THREADS) == tid) {
-                        const int rr = (ch / RELAX_THREADS) * VEC + ke;
-                        sbm ^= (mask_t)1 << rr;
-                        s_bits[k >> 5] ^= 1u << (k & 31);
-                    }
-                }
                 {   // one coalesced pass over column k (row k of Wcol), fused into the register-resident fields
-                    const CT* col = reinterpret_cast<const CT*>(p.Wcol) + (size_t)k * p.ldw;
+                    const CT* mycol = reinterpret_cast<const CT*>(p.Wcol) + ((unsigned)k * (unsigned)p.ldw + (unsigned)(tid * VEC));   // my chunk 0 of column k (N*ldw < 2^32)
                     const double d = nb ? dscale : -dscale;
                     const int qdir = nb ? 0 : (qneg | (qneg << 24));   // integer stream: 1 -> 0 enters with the opposite sign
                     auto pass = [&](auto full_tag) {
@@ -377,12 +393,12 @@ relax_kernel(RelaxParams p) {
                                 for (int e = 0; e < (VEC + 1) / 2; e++) x[e] = 0;
                                 if (FULL || u0 < p.ldw) {
                                     if (VEC == 4) {
-                                        const int2 t = __ldg(reinterpret_cast<const int2*>(col + u0));
+                                        const int2 t = __ldg(reinterpret_cast<const int2*>(mycol + c * (RELAX_THREADS * VEC)));
                                         x[0] = t.x; x[(VEC + 1) / 2 - 1] = t.y;
                                     } else if (VEC == 2) {
-                                        x[0] = __ldg(reinterpret_cast<const int*>(col + u0));
+                                        x[0] = __ldg(reinterpret_cast<const int*>(mycol + c * (RELAX_THREADS * VEC)));
                                     } else {
-                                        x[0] = (int)__ldg(col + u0);   // hi half = sign bits, multiplied by byte 1 = 0
+                                        x[0] = (int)__ldg(mycol + c * (RELAX_THREADS * VEC));   // hi half = sign bits, multiplied by byte 1 = 0
                                     }
                                 }
 #pragma unroll
@@ -398,22 +414,22 @@ relax_kernel(RelaxParams p) {
                             if (FULL || u0 < p.ldw) {
                                 if constexpr (sizeof(CT) == 4) {   // float32 column stream: 4N bytes per flip
                                     if (VEC == 4) {
-                                        const float4 x = __ldg(reinterpret_cast<const float4*>(col + u0));
+                                        const float4 x = __ldg(reinterpret_cast<const float4*>(mycol + c * (RELAX_THREADS * VEC)));
                                         w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
                                     } else if (VEC == 2) {
-                                        const float2 x = __ldg(reinterpret_cast<const float2*>(col + u0));
+                                        const float2 x = __ldg(reinterpret_cast<const float2*>(mycol + c * (RELAX_THREADS * VEC)));
                                         w[0] = x.x; w[1] = x.y;
                                     } else {
-                                        w[0] = __ldg(col + u0);
+                                        w[0] = __ldg(mycol + c * (RELAX_THREADS * VEC));
                                     }
                                 } else if (VEC == 4) {   // 256-bit loads (8% faster than two 128-bit loads here)
                                     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                                                 : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(col + u0));
+                                                 : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(mycol + c * (RELAX_THREADS * VEC)));
                                 } else if (VEC == 2) {
-                                    const double2 x = __ldg(reinterpret_cast<const double2*>(col + u0));
+                                    const double2 x = __ldg(reinterpret_cast<const double2*>(mycol + c * (RELAX_THREADS * VEC)));
                                     w[0] = x.x; w[1] = x.y;
                                 } else {
-                                    w[0] = __ldg(col + u0);
+                                    w[0] = __ldg(mycol + c * (RELAX_THREADS * VEC));
                                 }
                             }
 #pragma unroll
@@ -425,7 +441,7 @@ relax_kernel(RelaxParams p) {
                         }
                     };
                     (void)qdir; (void)d;
-                    if (p.ldw == NU) pass(std::true_type{}); else pass(std::false_type{});
+                    if (full_rows) pass(std::true_type{}); else pass(std::false_type{});
                 }
                 if (!INTF && ((flips + 1) & (RELAX_TAU_STEP - 1)) == 0) T = thr(flips + 1);  // candidacy below is re-derived with it
                 {

@@ -122,8 +122,9 @@ constexpr int RELAX_TAU_STEP = 256;
 // changed; __syncthreads; every warp finds the next candidate position with one coalesced read of the bitmap
 // (32 words = 1024 positions per step) + ballot/ffs; the unit's owner publishes (inside-margin?, old bit);
 // __syncthreads.  The L1/LSU data pipe carries the column and almost nothing else.
-template <int UPT> struct RelaxCfg {
-    static constexpr int VEC = UPT >= 4 ? 4 : UPT;   // contiguous units per ownership chunk
+template <int UPT, typename CT> struct RelaxCfg {
+    static constexpr int VMAX = std::is_same<CT, int16_t>::value ? 8 : 4;   // one 128-bit load of int16 / float32, one 256-bit load of float64
+    static constexpr int VEC = UPT >= VMAX ? VMAX : UPT;   // contiguous units per ownership chunk
     static constexpr int NCH = UPT / VEC;            // chunks per thread
 };
 static inline int relax_cand_words(int nbw) { return (nbw + 31) / 32 * 32 + 32; }   // scan reads 32 words from any word < nbw
@@ -149,13 +150,14 @@ __device__ __forceinline__ int tree_select(const int (&v)[N_], int idx) {
     return t[0];
 }
 
-template <int UPT, typename CT, int THREADS>
-__global__ void __launch_bounds__(THREADS, (UPT <= 16 ? ((std::is_same<CT, int16_t>::value ? RELAX_MIN_CTAS_INT : RELAX_MIN_CTAS) * 256) / THREADS : 1))
+// MINB = CTAs per SM the register allocation must allow (0: the default for 256-thread-equivalent occupancy)
+template <int UPT, typename CT, int THREADS, int MINB = 0>
+__global__ void __launch_bounds__(THREADS, MINB > 0 ? MINB : ((std::is_same<CT, int16_t>::value ? RELAX_MIN_CTAS_INT : RELAX_MIN_CTAS) * 256) / THREADS)
 relax_kernel(RelaxParams p) {
     constexpr int RELAX_THREADS = THREADS;   // threads per probe: 256 up to N=4096, 512 / 1024 for N=8192 / 16384
     constexpr int RELAX_WARPS = THREADS / 32;
-    constexpr int VEC = RelaxCfg<UPT>::VEC;
-    constexpr int NCH = RelaxCfg<UPT>::NCH;
+    constexpr int VEC = RelaxCfg<UPT, CT>::VEC;
+    constexpr int NCH = RelaxCfg<UPT, CT>::NCH;
     constexpr int NU = RELAX_THREADS * UPT;  // padded unit count
     using mask_t = typename std::conditional<(UPT > 32), uint64_t, uint32_t>::type;
     // Field type: float64 local fields, or — CT = int16_t, the exact-integer stream — int32 fields g = 2*(Wraw s) with
@@ -281,7 +283,7 @@ relax_kernel(RelaxParams p) {
                         hi = __funnelshift_l((uint32_t)h[r + UPT / 2], hi, 1);
                         lo = __funnelshift_l((uint32_t)h[r], lo, 1);
                     }
-                    m = (mask_t)((hi << (UPT / 2)) | lo);
+                    m = ((mask_t)hi << (UPT / 2)) | (mask_t)lo;
                 } else {
 #pragma unroll
                     for (int r = UPT - 1; r >= 0; r--) m = (mask_t)__funnelshift_l((uint32_t)h[r], (uint32_t)m, 1);
@@ -392,7 +394,10 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                                 for (int e = 0; e < (VEC + 1) / 2; e++) x[e] = 0;
                                 if (FULL || u0 < p.ldw) {
-                                    if (VEC == 4) {
+                                    if (VEC == 8) {
+                                        const int4 t = __ldg(reinterpret_cast<const int4*>(mycol + c * (RELAX_THREADS * VEC)));
+                                        x[0] = t.x; x[1 % ((VEC + 1) / 2)] = t.y; x[2 % ((VEC + 1) / 2)] = t.z; x[3 % ((VEC + 1) / 2)] = t.w;
+                                    } else if (VEC == 4) {
                                         const int2 t = __ldg(reinterpret_cast<const int2*>(mycol + c * (RELAX_THREADS * VEC)));
                                         x[0] = t.x; x[(VEC + 1) / 2 - 1] = t.y;
                                     } else if (VEC == 2) {

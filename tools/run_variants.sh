@@ -8,6 +8,7 @@ args=$1; shift
 for v in "$@"; do
   cp $L/variants/$v.so $L/libhopfield_b200.so
   python bench.py $args > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
+  if [ -n "$VERIFY" ]; then python -m pytest $VERIFY -q 2>&1 | tail -1; fi
   python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]

@@ -72,3 +72,20 @@ def test_i16_rejects_wrong_structure(built):
         net.SetIntegerStructure(onet.w)                   # proportional, but 4*matrix is not integer valued
     assert not net.integer_stream_active()
     net.close()
+
+
+@pytest.mark.parametrize("n,p,b", [(2048, 100, 24), (1500, 40, 24), (5000, 60, 12), (8192, 24, 6), (16384, 16, 3)])
+def test_i16_stream_thread_geometries(built, n, p, b):
+    """Every thread geometry of the integer stream (32 units per thread; 64 / 128 / 256 / 512 threads per probe) and
+    dimensions that are not a multiple of the tile, against the exact-integer oracle."""
+    onet, k2, pool, probes, targets = make_problem(n, p, b, 91, pool_rows=100)
+    ores = onet.relax_batch(probes.copy(), pool, threads=8, want_energies=False, fast_k2=k2)
+    net = gpu_net(n, SetColumnStream=I16)
+    net.SetMatrix(onet.w)
+    net.SetIntegerStructure(k2 * 0.5)
+    assert net.integer_stream_active()
+    net.SetLearnedStates(orc.pack(targets))
+    res = net.relax_batch(probes, pool, dedup=True)
+    assert_relax_equal(res, ores, n)
+    assert np.array_equal(res.MarginHits, ores["margin_hits"])
+    net.close()

@@ -280,13 +280,15 @@ int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
 template <typename CT>
 int launch_relax_c(hn_handle h, const RelaxParams& p) {
     const int n = h->N;
-    if (n <= 256) return launch_relax_t<1, CT>(h, p, 0);
-    if (n <= 512) return launch_relax_t<2, CT>(h, p, 0);
-    if (n <= 1024) return launch_relax_t<4, CT>(h, p, 0);
-    if (n <= 2048) return launch_relax_t<8, CT>(h, p, 0);
-    if (n <= 4096) return launch_relax_t<16, CT>(h, p, 0);
-    if (n <= 8192) return launch_relax_t<16, CT, 512>(h, p, 0);     // more threads per probe, same 16 units each
-    if (n <= 16384) return launch_relax_t<16, CT, 1024>(h, p, 0);
+    // few, fat threads per probe (what every warp repeats per flip dominates): one warp up to N = 1024 (no block barrier
+    // worth the name), 32 float64 fields per thread: 2.5x at N=1024, 3.8x at N=256, +33% at N=2048 over 256 threads
+    if (n <= 256) return launch_relax_t<8, CT, 32, 32>(h, p, 0);
+    if (n <= 512) return launch_relax_t<16, CT, 32, 24>(h, p, 0);
+    if (n <= 1024) return launch_relax_t<32, CT, 32, 16>(h, p, 0);
+    if (n <= 2048) return launch_relax_t<32, CT, 64, 8>(h, p, 0);
+    if (n <= 4096) return launch_relax_t<32, CT, 128, 4>(h, p, 0);
+    if (n <= 8192) return launch_relax_t<32, CT, 256, 2>(h, p, 0);
+    if (n <= 16384) return launch_relax_t<32, CT, 512, 1>(h, p, 0);
     set_error("relaxation kernel supports dimension <= 16384 (got %d)", n);
     return HN_E_INVALID;
 }

@@ -247,6 +247,7 @@ relax_kernel(RelaxParams p) {
         int q[INTF ? (UPT + 1) / 2 : 1];   // integer stream: v * delta of my units as signed bytes, two units per word
                                            // (even unit: byte 0, odd unit: byte 3) = the multipliers of dp2a.lo / dp2a.hi
         const int qneg = p.domain == HN_DOMAIN_BINARY ? 0xFE : 0xFC;   // byte ^ qneg negates +-1 (binary) / +-2 (bipolar)
+        uint32_t qdir_up = 1u;   // direction the sign bytes are currently multiplied with (1: a flip 0 -> 1)
         if constexpr (INTF) {
 #pragma unroll
             for (int j = 0; j < (UPT + 1) / 2; j++) q[j] = 0;
@@ -364,8 +365,6 @@ relax_kernel(RelaxParams p) {
                     const bool inside = INTF ? (a == -1) : ((a & 0x7FFFFFFF) < T);
                     const uint32_t obit = (s_bits[k >> 5] >> (k & 31)) & 1u;
                     s_flag = (inside ? 2 : 0) | (int)obit;
-                    if (!inside) owner_flip(rr, k);   // outside the margin the flip is certain: new bit into the packed state
-                                                      // and the sign mask (integer stream: negate the aligned field)
                 }
                 __syncthreads();
                 const int fl = s_flag;
@@ -375,7 +374,6 @@ relax_kernel(RelaxParams p) {
                     const double hx = exact_field(k);
                     margin++;
                     nb = hx > 0.0 ? 1u : 0u;
-                    if (nb != ob && owner) owner_flip((kch / RELAX_THREADS) * VEC + k % VEC, k);
                 }
                 if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
@@ -383,36 +381,57 @@ relax_kernel(RelaxParams p) {
                 {   // one coalesced pass over column k (row k of Wcol), fused into the register-resident fields
                     const CT* mycol = reinterpret_cast<const CT*>(p.Wcol) + ((unsigned)k * (unsigned)p.ldw + (unsigned)(tid * VEC));   // my chunk 0 of column k (N*ldw < 2^32)
                     const double d = nb ? dscale : -dscale;
-                    const int qdir = nb ? 0 : (qneg | (qneg << 24));   // integer stream: 1 -> 0 enters with the opposite sign
+                    if constexpr (INTF) {
+                        // exact int16 column stream, 2N bytes per flip: a' += (v*(+-delta)) * K by dp2a.  The sign bytes are
+                        // kept pre-multiplied by the direction of the last flip and turned over only when it changes.
+                        if (nb != qdir_up) {
+#pragma unroll
+                            for (int j = 0; j < (UPT + 1) / 2; j++) q[j] ^= qneg | (qneg << 24);
+                            qdir_up = nb;
+                        }
+                        auto ipass = [&](auto full_tag) {
+                        constexpr bool FULL = decltype(full_tag)::value;   // every chunk lies inside the padded row
+                        constexpr int XW = (VEC + 1) / 2;
+                        int x[NCH][XW];
+#pragma unroll
+                        for (int c = 0; c < NCH; c++) {
+#pragma unroll
+                            for (int e = 0; e < XW; e++) x[c][e] = 0;
+                            if (FULL || unit_of(c, 0) < p.ldw) {
+                                const CT* src = mycol + c * (RELAX_THREADS * VEC);
+                                if constexpr (VEC == 8) {
+                                    const int4 t = __ldg(reinterpret_cast<const int4*>(src));
+                                    x[c][0] = t.x; x[c][1 % XW] = t.y; x[c][2 % XW] = t.z; x[c][3 % XW] = t.w;
+                                } else if constexpr (VEC == 4) {
+                                    const int2 t = __ldg(reinterpret_cast<const int2*>(src));
+                                    x[c][0] = t.x; x[c][1 % XW] = t.y;
+                                } else if constexpr (VEC == 2) {
+                                    x[c][0] = __ldg(reinterpret_cast<const int*>(src));
+                                } else {
+                                    x[c][0] = (int)__ldg(src);   // hi half = sign bits, multiplied by byte 1 = 0
+                                }
+                            }
+                        }
+                        // owner, in the shadow of the loads: its own sign changes (commutes with the column update)
+                        if (owner) owner_flip((kch / RELAX_THREADS) * VEC + k % VEC, k);
+#pragma unroll
+                        for (int c = 0; c < NCH; c++) {
+#pragma unroll
+                            for (int e = 0; e < VEC; e++) {
+                                const int r = c * VEC + e;
+                                h[r] = (r & 1) ? __dp2a_hi(x[c][e >> 1], q[r >> 1], h[r]) : __dp2a_lo(x[c][e >> 1], q[r >> 1], h[r]);
+                            }
+                        }
+                        };
+                        if (full_rows) ipass(std::true_type{}); else ipass(std::false_type{});
+                    } else {
+                    if (owner) owner_flip((kch / RELAX_THREADS) * VEC + k % VEC, k);
                     auto pass = [&](auto full_tag) {
                         constexpr bool FULL = decltype(full_tag)::value;   // every chunk lies inside the padded row
 #pragma unroll
                         for (int c = 0; c < NCH; c++) {
                             const int u0 = unit_of(c, 0);
-                            if constexpr (INTF) {   // exact int16 column stream, 2N bytes per flip: a' += (v*(+-delta)) * K by dp2a
-                                int x[(VEC + 1) / 2];
-#pragma unroll
-                                for (int e = 0; e < (VEC + 1) / 2; e++) x[e] = 0;
-                                if (FULL || u0 < p.ldw) {
-                                    if (VEC == 8) {
-                                        const int4 t = __ldg(reinterpret_cast<const int4*>(mycol + c * (RELAX_THREADS * VEC)));
-                                        x[0] = t.x; x[1 % ((VEC + 1) / 2)] = t.y; x[2 % ((VEC + 1) / 2)] = t.z; x[3 % ((VEC + 1) / 2)] = t.w;
-                                    } else if (VEC == 4) {
-                                        const int2 t = __ldg(reinterpret_cast<const int2*>(mycol + c * (RELAX_THREADS * VEC)));
-                                        x[0] = t.x; x[(VEC + 1) / 2 - 1] = t.y;
-                                    } else if (VEC == 2) {
-                                        x[0] = __ldg(reinterpret_cast<const int*>(mycol + c * (RELAX_THREADS * VEC)));
-                                    } else {
-                                        x[0] = (int)__ldg(mycol + c * (RELAX_THREADS * VEC));   // hi half = sign bits, multiplied by byte 1 = 0
-                                    }
-                                }
-#pragma unroll
-                                for (int e = 0; e < VEC; e++) {
-                                    const int r = c * VEC + e;
-                                    const int qd = q[r >> 1] ^ qdir;
-                                    h[r] = (r & 1) ? __dp2a_hi(x[e >> 1], qd, h[r]) : __dp2a_lo(x[e >> 1], qd, h[r]);
-                                }
-                            } else {
+                            {
                             double w[VEC];
 #pragma unroll
                             for (int e = 0; e < VEC; e++) w[e] = 0.0;
@@ -445,8 +464,8 @@ relax_kernel(RelaxParams p) {
                             }
                         }
                     };
-                    (void)qdir; (void)d;
                     if (full_rows) pass(std::true_type{}); else pass(std::false_type{});
+                    }
                 }
                 if (!INTF && ((flips + 1) & (RELAX_TAU_STEP - 1)) == 0) T = thr(flips + 1);  // candidacy below is re-derived with it
                 {

@@ -195,7 +195,7 @@ def main():
     for it in range(1 + min(args.steps, 2)):
         barrier()
         t1 = time.perf_counter()
-        res = net.relax_batch(probes_np, pool, dedup=True)
+        res = net.relax_batch(probes_np, pool, dedup=True, reuse_pinned_buffers=True)   # page-locked result buffers of the network
         if world > 1:   # host-side merge of the per-GPU unique-attractor tables (first-seen order, hits)
             from hopfield_network_go_b200 import multigpu
             merged = multigpu.gather_unique_tables({"offset": rank * b, "first": res.UniqueFirst, "hits": res.UniqueHits,
@@ -247,7 +247,7 @@ def main():
         col_bytes = {"f64": 8, "f32": 4, "i16": 2}[stream]
         field_bytes = 4 if stream == "i16" else 8
         streamed = col_bytes * n * flips + field_bytes * n * sweeps     # what this stream really moves L2->SM per launch
-        kernel = {"f64": "relax_kernel<16,double,256>", "f32": "relax_kernel<16,float,256>", "i16": "relax_kernel<16,short,256>"}[stream]
+        kernel = {"f64": "relax_kernel<32,double,128,4>", "f32": "relax_kernel<32,float,128,4>", "i16": "relax_kernel<32,short,128,7>"}[stream]
         notes = {
             "f64": "bounded by the L2->SM fabric: every flip moves its 8N-byte column L2->SM (~9.7 TB/s, ~33 B/clk/SM)",
             "f32": "float32 shadow of W: 4N bytes per flip, float64 fields, exact re-evaluation inside the grown margin",
@@ -296,7 +296,7 @@ def main():
             t64 = traffic.get("f64", {})
             line["roofline_f64_stream"] = {"bound": "hbm", "achieved": ach64, "peak": hbm, "unit": "GB/s", "frac": ach64 / hbm,
                                            "traffic": t64.get("dram_bytes_per_launch") if t64.get("probes_per_launch") == b and t64.get("N") == n else None,
-                                           "kernel": "relax_kernel<16,double,256>", "note": notes["f64"]}
+                                           "kernel": "relax_kernel<32,double,128,4>", "note": notes["f64"]}
         if not args.no_delta:
             line["delta_epoch_ms"] = dict(delta_ms, note="wall clock (max over ranks) through hn_delta_epoch + hn_energy_profiles "
                                           "with host buffers (H2D of packed targets, noised copies and permutations inside the timed "

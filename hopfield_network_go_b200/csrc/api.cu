@@ -1144,6 +1144,22 @@ int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip) {
     return HN_OK;
 }
 
+int hn_host_alloc(void** ptr_out, size_t bytes) {
+    if (!ptr_out || bytes == 0) { set_error("hn_host_alloc: bad argument"); return HN_E_INVALID; }
+    *ptr_out = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr_out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        set_error("hn_host_alloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? HN_E_OOM : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? HN_E_NO_DEVICE : HN_E_CUDA);
+    }
+    return HN_OK;
+}
+int hn_host_free(void* ptr) {
+    if (ptr) HN_CUDA_TRY(cudaFreeHost(ptr));
+    return HN_OK;
+}
+
 int hn_pack_states_f64(int32_t dimension, int32_t n, const double* states_f64, uint64_t* packed) {
     if (dimension <= 0 || n < 0 || !states_f64 || !packed) { set_error("hn_pack_states_f64: bad argument"); return HN_E_INVALID; }
     const int words = hn_words(dimension);

@@ -115,9 +115,32 @@ class HopfieldNetwork:
         self.randomGenerator = Rand(seed)
 
     def close(self):
+        for addr, _ in getattr(self, "_pinned", {}).values():
+            capi.load().hn_host_free(C.c_void_p(addr))
+        self._pinned = {}
         if self._h:
             capi.load().hn_destroy(self._h)
             self._h = C.c_void_p()
+
+    def _result_buffer(self, name, shape, dtype, pinned):
+        """Result array: a fresh numpy array, or (pinned=True) a view of a page-locked buffer of this network that
+        is REUSED by the next call with pinned=True (hn_host_alloc: results arrive at PCIe speed, no page faults)."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        if not pinned:
+            return np.zeros(shape, dtype=dtype)
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        addr, cap = self._pinned.get(name, (0, 0))
+        if cap < nbytes:
+            if addr:
+                check(capi.load().hn_host_free(C.c_void_p(addr)))
+            p = C.c_void_p()
+            check(capi.load().hn_host_alloc(C.byref(p), nbytes))
+            addr, cap = p.value, nbytes
+            self._pinned[name] = (addr, cap)
+        raw = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(addr))
+        return raw[:int(np.prod(shape)) * dtype.itemsize].view(dtype).reshape(shape)
 
     def __del__(self):
         try:
@@ -252,31 +275,34 @@ class HopfieldNetwork:
         return p
 
     def relax_batch(self, probes, perm_pool, offsets=None, serial_stream=False, dedup=False, history=False,
-                    want_energies=False, want_distances=True) -> RelaxationBatchResult:
+                    want_energies=False, want_distances=True, reuse_pinned_buffers=False) -> RelaxationBatchResult:
+        """hn_relax_batch with host buffers.  reuse_pinned_buffers=True returns views of page-locked buffers owned by
+        this network; they are overwritten by the next such call (copy what must outlive it)."""
         p = self._packed(probes)
         b = p.shape[0]
         pool = np.ascontiguousarray(perm_pool, dtype=np.uint16).reshape(-1, self.dimension)
         nt = C.c_int32()
         check(capi.load().hn_num_targets(self._h, C.byref(nt)))
         w = words(self.dimension)
-        finals = np.zeros((b, w), dtype=np.uint64)
-        steps = np.zeros(b, dtype=np.int32)
-        stable = np.zeros(b, dtype=np.uint8)
-        flips = np.zeros(b, dtype=np.int32)
-        margin = np.zeros(b, dtype=np.int32)
-        dist = np.zeros((b, nt.value), dtype=np.int32) if (want_distances and nt.value) else None
-        en = np.zeros((b, self.dimension)) if want_energies else None
-        aid = np.zeros(b, dtype=np.int32) if dedup else None
-        uf = np.zeros(max(b, 1), dtype=np.int32) if dedup else None
-        uh = np.zeros(max(b, 1), dtype=np.int32) if dedup else None
-        hist = np.zeros((b, self._cfg.max_relax_iterations + 1, w), dtype=np.uint64) if history else None
+        buf = lambda name, shape, dtype: self._result_buffer(name, shape, dtype, reuse_pinned_buffers)
+        finals = buf("finals", (b, w), np.uint64)
+        steps = buf("steps", (b,), np.int32)
+        stable = buf("stable", (b,), np.uint8)
+        flips = buf("flips", (b,), np.int32)
+        margin = buf("margin", (b,), np.int32)
+        dist = buf("dist", (b, nt.value), np.int32) if (want_distances and nt.value) else None
+        en = buf("energies", (b, self.dimension), np.float64) if want_energies else None
+        aid = buf("aid", (b,), np.int32) if dedup else None
+        uf = buf("uf", (max(b, 1),), np.int32) if dedup else None
+        uh = buf("uh", (max(b, 1),), np.int32) if dedup else None
+        hist = buf("history", (b, self._cfg.max_relax_iterations + 1, w), np.uint64) if history else None
         out = capi.HnRelaxOut()
         out.final_states, out.num_steps, out.stable = ptr(finals), ptr(steps), ptr(stable)
         out.distances, out.energies, out.flips, out.margin_hits = ptr(dist), ptr(en), ptr(flips), ptr(margin)
         out.attractor_id, out.unique_first, out.unique_hits = ptr(aid), ptr(uf), ptr(uh)
         out.unique_cap = b if dedup else 0
         out.history = ptr(hist)
-        sh = np.zeros((b, 2), dtype=np.uint64) if dedup else None
+        sh = buf("hash", (b, 2), np.uint64) if dedup else None
         out.state_hash = ptr(sh)
         flags = (capi.HN_RELAX_SERIAL_STREAM if serial_stream else 0) | (capi.HN_RELAX_DEDUP if dedup else 0) | \
                 (capi.HN_RELAX_HISTORY if history else 0)

@@ -305,6 +305,13 @@ int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip);
 /* ---- conversions -------------------------------------------------------
  * f64 rows -> packed with the domain activation function applied. Host-side
  * helpers for hosts that hold gonum-style float64 state vectors.             */
+/* Page-locked host staging buffers (additive extension): every host pointer of this API may be pageable, but
+ * probes / results in buffers from hn_host_alloc move at PCIe speed and without a staging copy (a Go binding
+ * keeps its flattened []float64 / []uint64 slices in such buffers; reference: the [] *mat.VecDense results of
+ * ConcurrentRelaxStates, HopfieldNetwork.go:461-490).  Freed with hn_host_free only.                          */
+int hn_host_alloc(void** ptr_out, size_t bytes);
+int hn_host_free(void* ptr);
+
 int hn_pack_states_f64(int32_t dimension, int32_t n, const double* states_f64, uint64_t* packed);
 int hn_unpack_states_f64(int32_t dimension, int32_t domain, int32_t n, const uint64_t* packed,
                          double* states_f64);

@@ -85,3 +85,22 @@ def test_offsets_and_pool_exhaustion(built):
         net.relax_batch(probes[:4], pool[:10])
     assert ei.value.code == capi.HN_E_POOL
     net.close()
+
+
+def test_pinned_result_buffers_match_pageable(built):
+    """hn_host_alloc staging: the same results arrive in the network's page-locked buffers, which are reused."""
+    n, p, b = 320, 24, 128
+    onet, _, pool, probes, targets = make_problem(n, p, b, 58)
+    net = gpu_net(n)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(targets))
+    ref = net.relax_batch(probes, pool, dedup=True, want_energies=True)
+    a = net.relax_batch(probes, pool, dedup=True, want_energies=True, reuse_pinned_buffers=True)
+    for name in ("FinalStates", "NumSteps", "Stable", "DistancesToTargets", "Flips", "AttractorId", "UniqueFirst",
+                 "UniqueHits", "StateHash", "EnergyProfiles"):
+        assert np.array_equal(getattr(a, name), getattr(ref, name)), name
+    addr = a.FinalStates.ctypes.data
+    b2 = net.relax_batch(probes[:64], pool, dedup=True, reuse_pinned_buffers=True)      # smaller batch: same buffers
+    assert b2.FinalStates.ctypes.data == addr
+    assert np.array_equal(b2.FinalStates, ref.FinalStates[:64])
+    net.close()

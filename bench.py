@@ -249,7 +249,7 @@ def main():
         streamed = col_bytes * n * flips + field_bytes * n * sweeps     # what this stream really moves L2->SM per launch
         kernel = {"f64": "relax_kernel<32,double,128,4>", "f32": "relax_kernel<32,float,128,4>", "i16": "relax_kernel<32,short,128,7>"}[stream]
         notes = {
-            "f64": "bounded by the L2->SM fabric: every flip moves its 8N-byte column L2->SM (~9.7 TB/s, ~33 B/clk/SM)",
+            "f64": "bounded by the L2->SM fabric: every flip moves its 8N-byte column L2->SM (~10 TB/s, ~34 B/clk/SM)",
             "f32": "float32 shadow of W: 4N bytes per flip, float64 fields, exact re-evaluation inside the grown margin",
             "i16": "exact integer stream: int32 fields and int16 columns (2N bytes per flip) give the reference's float64 "
                    "decisions bit for bit; exact ties are re-evaluated in float64 in the reference's summation order"}
@@ -267,7 +267,7 @@ def main():
                              "note": "per GPU; achieved = ALGORITHMIC bytes of the reference algorithm (8N per flip + 8N per sweep, "
                                      "SURVEY 8d) over the relaxation kernel time; >1 because W stays in L2 (see traffic) and "
                                      "this stream moves fewer bytes than the algorithm names (streamed_bytes_per_launch); "
-                                     + notes[stream] + "; profiles/r01_relax_final_ncu_summary.txt",
+                                     + notes[stream] + "; profiles/r01_relax_i16_final_ncu_summary.txt, profiles/r01_relax_f64_ncu_summary.txt",
                              "peak_source": "measured" if peaks else "fallback",
                              "algorithmic_bytes_per_launch": int(alg_bytes), "streamed_bytes_per_launch": int(streamed),
                              "streamed_gbs": streamed * args.steps / (relax_ms_max * 1e-3) / 1e9,

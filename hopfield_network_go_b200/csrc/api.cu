@@ -68,6 +68,11 @@ constexpr int NCCL_FLOAT64 = 8, NCCL_INT32 = 2, NCCL_SUM = 0, NCCL_MIN = 4;
         }                                                                                   \
     } while (0)
 
+// host_rng.cpp: the x/exp/rand PCG source behind hn_rng (state access + jump-ahead for device-side generation)
+void rng_jump_table(uint64_t table[64][4]);
+void rng_get_state(hn_rng r, uint64_t out[2]);
+void rng_advance(hn_rng r, uint64_t draws);
+
 }  // namespace hn
 
 using namespace hn;
@@ -105,6 +110,7 @@ struct hn_handle_s {
     int P = 0;
     DevBuf targets;
     // relaxation working set
+    DevBuf jump;   // LCG jump table of hn_generate_probes
     DevBuf probes, pool, offsets, H, finals, steps, stable, flips, margin, dist, hash, energies, history;
     DevBuf rep, first, hits, flag, rank, table, attractor, ufirst, uhits, small, partial;
     DevBuf bitsA, bitsB, bitsC, bitsAT, bitsCT, perms, eunst, estab, esum, emargin;
@@ -1115,6 +1121,39 @@ int hn_upload_probes(hn_handle h, const uint64_t* probes_packed, int32_t n_probe
     h->resident_B = n_probes;
     return HN_OK;
 }
+int hn_generate_probes(hn_handle h, hn_rng r, int32_t count, double rand_min, double rand_max) {
+    if (!check_handle(h, "hn_generate_probes")) return HN_E_INVALID;
+    if (!r || count <= 0 || !(rand_min < rand_max)) { set_error("hn_generate_probes: bad argument"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    uint64_t table[64][4], state[2];
+    rng_jump_table(table);
+    rng_get_state(r, state);
+    HN_TRY(h->jump.reserve(sizeof(table)));
+    HN_CUDA_TRY(cudaMemcpyAsync(h->jump.p, table, sizeof(table), cudaMemcpyHostToDevice, h->st));
+    HN_TRY(h->probes.reserve(sizeof(uint64_t) * (size_t)count * h->words));
+    const long long total = (long long)count * h->words;
+    generate_states_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(state[0], state[1], h->jump.as<uint64_t>(), h->N,
+                                                                        h->words, count, rand_min, rand_max, h->probes.as<uint64_t>());
+    HN_CUDA_TRY(cudaGetLastError());
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));   // `table` is a stack buffer
+    rng_advance(r, (uint64_t)count * (uint64_t)h->N);   // the host stream continues after the draws taken on the device
+    h->resident_B = count;
+    return HN_OK;
+}
+
+int hn_download_probes(hn_handle h, uint64_t* probes_packed_out, int32_t n_probes) {
+    if (!check_handle(h, "hn_download_probes")) return HN_E_INVALID;
+    if (!probes_packed_out || n_probes <= 0 || n_probes > h->resident_B) {
+        set_error("hn_download_probes: %d probes asked, %d resident", n_probes, h->resident_B);
+        return HN_E_INVALID;
+    }
+    HN_TRY(set_device(h));
+    HN_CUDA_TRY(cudaMemcpyAsync(probes_packed_out, h->probes.p, sizeof(uint64_t) * (size_t)n_probes * h->words,
+                                cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
 int hn_relax_resident(hn_handle h, uint32_t flags, double* device_ms) {
     if (!check_handle(h, "hn_relax_resident")) return HN_E_INVALID;
     if (h->resident_B <= 0 || h->resident_pool <= 0) { set_error("hn_relax_resident: upload probes and a pool first"); return HN_E_STATE; }

@@ -115,6 +115,29 @@ void maximal_invert(Pcg& g, double* state, int n, double ratio) {
 
 struct hn_rng_s { Pcg g; explicit hn_rng_s(uint64_t s) : g(s) {} };
 
+namespace hn {
+// Jump-ahead of the 128-bit LCG under the PCG source: entry j holds (M^(2^j), I*(M^(2^j)-1)/(M-1)) as
+// {mult lo, mult hi, plus lo, plus hi}; advancing by d composes the entries of the set bits of d.
+void rng_jump_table(uint64_t table[64][4]) {
+    u128 m = Pcg::kMul, c = Pcg::kInc;
+    for (int j = 0; j < 64; j++) {
+        table[j][0] = (uint64_t)m; table[j][1] = (uint64_t)(m >> 64);
+        table[j][2] = (uint64_t)c; table[j][3] = (uint64_t)(c >> 64);
+        c = (m + 1) * c;
+        m = m * m;
+    }
+}
+void rng_get_state(hn_rng r, uint64_t out[2]) { out[0] = (uint64_t)r->g.state; out[1] = (uint64_t)(r->g.state >> 64); }
+void rng_advance(hn_rng r, uint64_t draws) {   // as if `draws` Uint64 values had been drawn
+    uint64_t t[64][4];
+    rng_jump_table(t);
+    u128 s = r->g.state;
+    for (int j = 0; j < 64; j++)
+        if ((draws >> j) & 1ULL) s = s * (((u128)t[j][1] << 64) | t[j][0]) + (((u128)t[j][3] << 64) | t[j][2]);
+    r->g.state = s;
+}
+}  // namespace hn
+
 extern "C" {
 
 int hn_rng_create(uint64_t seed, hn_rng* out) {
@@ -127,6 +150,12 @@ uint64_t hn_rng_uint64(hn_rng r) { return r->g.next(); }
 uint64_t hn_rng_uint64n(hn_rng r, uint64_t n) { return r->g.below(n); }
 double hn_rng_float64(hn_rng r) { return r->g.unit(); }
 double hn_rng_norm_float64(hn_rng r) { return norm_float64(r->g); }
+
+int hn_rng_advance(hn_rng r, uint64_t draws) {
+    if (!r) { hn::set_error("hn_rng_advance: rng is NULL"); return HN_E_INVALID; }
+    hn::rng_advance(r, draws);
+    return HN_OK;
+}
 
 int hn_rng_shuffle_u16(hn_rng r, uint16_t* list, int32_t n) {
     if (!r || !list || n < 0) { hn::set_error("hn_rng_shuffle_u16: bad argument"); return HN_E_INVALID; }

@@ -370,4 +370,38 @@ __global__ void pack_f64_kernel(const double* __restrict__ x, uint64_t* __restri
     }
 }
 
+
+// states.StateGenerator (states/StateGenerator.go:44-52, :65-74) on the device: unit i of state s takes draw number
+// s*N + i of the PCG XSL-RR 128/64 stream (one Uint64 per unit: Float64() = (Uint64() & (2^53-1)) / 2^53),
+// x = f*(max-min)+min, bit = x > 0 (domain activation).  One thread per output word: it jumps the 128-bit LCG to
+// its first draw with the power table (rng_jump_table) and then steps it 64 times.
+__global__ void generate_states_kernel(uint64_t state_lo, uint64_t state_hi, const uint64_t* __restrict__ jump,  // [64][4]
+                                       int N, int words, int count, double rmin, double rmax, uint64_t* __restrict__ out) {
+    using u128 = unsigned __int128;
+    const long long total = (long long)count * words;
+    const u128 kMul = ((u128)2549297995355413924ULL << 64) | 4865540595714422341ULL;
+    const u128 kInc = ((u128)6364136223846793005ULL << 64) | 1442695040888963407ULL;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(t / words), w = (int)(t % words);
+        const unsigned long long first = (unsigned long long)s * (unsigned long long)N + (unsigned long long)w * 64ULL;
+        u128 st = ((u128)state_hi << 64) | state_lo;
+        for (int j = 0; j < 64; j++)
+            if ((first >> j) & 1ULL)
+                st = st * (((u128)jump[j * 4 + 1] << 64) | jump[j * 4 + 0]) + (((u128)jump[j * 4 + 3] << 64) | jump[j * 4 + 2]);
+        uint64_t bits = 0;
+        const int n = min(64, N - w * 64);
+        for (int i = 0; i < n; i++) {
+            st = st * kMul + kInc;
+            const uint64_t hi = (uint64_t)(st >> 64), lo = (uint64_t)st;
+            const unsigned rot = (unsigned)(hi >> 58);
+            const uint64_t x = hi ^ lo;
+            const uint64_t r = (x >> rot) | (x << ((64u - rot) & 63u));
+            const double f = (double)(r & ((1ULL << 53) - 1)) / 9007199254740992.0;
+            const double v = __dadd_rn(__dmul_rn(f, rmax - rmin), rmin);   // Uniform.Rand: rnd*(Max-Min) + Min, unfused
+            if (v > 0.0) bits |= 1ULL << i;
+        }
+        out[t] = bits;
+    }
+}
+
 }  // namespace hn

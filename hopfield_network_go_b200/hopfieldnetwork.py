@@ -44,6 +44,10 @@ class Rand:
     def Uint64n(self, n: int) -> int:
         return capi.load().hn_rng_uint64n(self._h, n)
 
+    def Advance(self, draws: int) -> None:
+        """Skip `draws` Uint64 values in O(log draws) (hn_rng_advance)."""
+        check(capi.load().hn_rng_advance(self._h, draws))
+
     def Float64(self) -> float:
         return capi.load().hn_rng_float64(self._h)
 
@@ -328,6 +332,17 @@ class HopfieldNetwork:
     def upload_probes(self, probes) -> None:
         p = self._packed(probes)
         check(capi.load().hn_upload_probes(self._h, ptr(p), p.shape[0]))
+
+    def generate_probes(self, count: int, rand_min: float = -1.0, rand_max: float = 1.0, rng: Optional["Rand"] = None) -> None:
+        """states.StateGenerator on the device (StateGenerator.go:44-74): `count` random probes straight into the
+        resident probe buffer, drawn from `rng` (default: the network's generator), which is advanced accordingly."""
+        g = rng if rng is not None else self.randomGenerator
+        check(capi.load().hn_generate_probes(self._h, g._h, count, rand_min, rand_max))
+
+    def download_probes(self, count: int) -> np.ndarray:
+        out = np.zeros((count, words(self.dimension)), dtype=np.uint64)
+        check(capi.load().hn_download_probes(self._h, ptr(out), count))
+        return out
 
     def relax_resident(self, dedup=False) -> float:
         ms = C.c_double()

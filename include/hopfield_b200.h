@@ -283,6 +283,13 @@ int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint
  * Upload once, relax many times without host traffic; see bench.py.          */
 int hn_upload_perm_pool(hn_handle h, const uint16_t* perm_pool, int32_t n_pool);
 int hn_upload_probes(hn_handle h, const uint64_t* probes_packed, int32_t n_probes);
+/* states.StateGenerator on the device (states/StateGenerator.go:44-52, :65-74): `count` probe states are
+ * generated straight into the resident probe buffer — unit i of state s from draw s*N+i of the generator's stream
+ * (Uniform{min,max}.Rand() then the domain activation), bit for bit what hn_rng_generate_states returns — and the host
+ * generator is advanced by count*N draws, so the stream continues as if the host had drawn them.  No probe upload. */
+int hn_generate_probes(hn_handle h, hn_rng r, int32_t count, double rand_min, double rand_max);
+/* Copy the first n resident probes (uploaded or generated) back to the host, packed. */
+int hn_download_probes(hn_handle h, uint64_t* probes_packed_out, int32_t n_probes);
 /* Relax the uploaded probes with the uploaded pool (offsets all 0). Results
  * stay on the device; *device_ms gets the CUDA-event time of the whole call. */
 int hn_relax_resident(hn_handle h, uint32_t flags, double* device_ms);
@@ -351,6 +358,11 @@ int      hn_rng_perm_pool(hn_rng r, int32_t dimension, int32_t n_rows, int32_t s
  * noiseapplication/NoiseApplication.go:51-105 does.                          */
 int      hn_rng_apply_noise(hn_rng r, int32_t noise_method, double noise_scale,
                             double* state_f64, int32_t dimension);
+
+/* Skip `draws` Uint64 values of the stream in O(log draws) (128-bit LCG jump-ahead): the state after the call is the
+ * state `draws` calls of hn_rng_uint64 would leave.  Used by hn_generate_probes; lets ranks of a multi-GPU job take
+ * disjoint sections of ONE reference stream (states/StateGeneratorBuilder.go:115-123 seeds one generator).        */
+int      hn_rng_advance(hn_rng r, uint64_t draws);
 
 /* states.StateGenerator (states/StateGenerator.go:44-52, :65-74): `count` states whose elements are
  * distuv.Uniform{min,max}.Rand() = Float64()*(max-min)+min followed by the domain activation, packed. */

@@ -9,6 +9,7 @@ import pytest
 
 from hopfield_network_go_b200 import capi
 from hopfield_network_go_b200 import hopfieldnetwork as hn
+from oracle import orc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -90,3 +91,24 @@ def test_pack_unpack_roundtrip_and_activation(built):
         assert np.array_equal(capi.pack_states(bip), p)
         if n % 64:
             assert (p[:, -1] >> np.uint64(n % 64)).max() == 0   # padding bits are zero
+
+
+def test_rng_advance_equals_drawing(built):
+    """hn_rng_advance(k) leaves the state k Uint64 draws would leave (the jump-ahead behind hn_generate_probes)."""
+    for seed, k in ((1, 0), (1, 1), (7, 2), (42, 1000), (5, 4096 * 3 + 17), (9, (1 << 33) + 12345)):
+        a, b = hn.Rand(seed), hn.Rand(seed)
+        if k <= 20000:
+            for _ in range(k):
+                a.Uint64()
+            b.Advance(k)
+        else:   # composition: advance(k) == advance(k1) then advance(k - k1)
+            a.Advance(1 << 33)
+            a.Advance(k - (1 << 33))
+            b.Advance(k)
+        assert [a.Uint64() for _ in range(4)] == [b.Uint64() for _ in range(4)]
+    # against the oracle's independent restatement of the generator
+    o, g = orc.Rng(77), hn.Rand(77)
+    g.Advance(5000)
+    for _ in range(5000):
+        o.uint64()
+    assert o.uint64() == g.Uint64()

@@ -148,3 +148,45 @@ def test_delta_epoch_config5_size(built):
     assert np.array_equal(rel_g, orc.pack(rel_o))
     assert np.array_equal(net.GetMatrix(), onet.w)
     net.close()
+
+
+@pytest.mark.parametrize("n,count,lo,hi", [(100, 37, -1.0, 1.0), (4096, 64, -1.0, 1.0), (257, 20, -0.25, 1.0), (64, 5, -3.0, 0.5)])
+def test_device_side_probe_generation(built, n, count, lo, hi):
+    """hn_generate_probes (StateGenerator.go:44-74 on the device, LCG jump-ahead) == the host generator, bit for bit,
+    and the host stream continues where the device draws ended."""
+    from hopfield_network_go_b200 import hopfieldnetwork as hn
+    net = gpu_net(n)
+    g_dev, g_host = hn.Rand(1234 + n), hn.Rand(1234 + n)
+    g_dev.Uint64(); g_host.Uint64()                       # not at the start of the stream
+    net.generate_probes(count, lo, hi, rng=g_dev)
+    expect = g_host.CreateStateCollection(n, count, lo, hi)
+    assert np.array_equal(net.download_probes(count), expect)
+    assert g_dev.Uint64() == g_host.Uint64()
+    o = orc.Rng(1234 + n)
+    o.uint64()
+    assert np.array_equal(expect, orc.pack(o.generate_states(0, n, count, lo, hi)))
+    net.close()
+
+
+def test_generated_probes_relax_like_uploaded_ones(built):
+    n, p, b = 512, 40, 96
+    onet, _, pool, _, targets = make_problem(n, p, b, 33)
+    from hopfield_network_go_b200 import hopfieldnetwork as hn
+    net = gpu_net(n)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(targets))
+    net.generate_probes(b, rng=hn.Rand(99))
+    probes = net.download_probes(b)
+    net.upload_perm_pool(pool)
+    net.relax_resident(dedup=True)
+    import ctypes as C
+    from hopfield_network_go_b200 import capi
+    finals = np.zeros_like(probes); steps = np.zeros(b, dtype=np.int32)
+    out = capi.HnRelaxOut()
+    out.final_states, out.num_steps = capi.ptr(finals), capi.ptr(steps)
+    capi.check(capi.load().hn_download_results(net._h, C.byref(out)))
+    ref = net.relax_batch(probes, pool, dedup=True)
+    assert np.array_equal(finals, ref.FinalStates) and np.array_equal(steps, ref.NumSteps)
+    ores = onet.relax_batch(orc.unpack(probes, n), pool, threads=8)
+    assert_relax_equal(ref, ores, n)
+    net.close()

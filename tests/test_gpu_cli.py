@@ -47,7 +47,10 @@ def test_cli_end_to_end(built, tmp_path):
     probes = gen.generate_states(0, n, b)
     sched = orc.Rng(seed)            # Hebbian learning draws nothing: the schedule is the first draw of the network RNG
     pool = sched.perm_pool(n, 100)
-    onet.set_weights(np.load(os.path.join(d, "matrix.npy")))       # identical bits for the trajectories
+    from hopfield_network_go_b200 import gonumio
+    assert "matrix.bin" in files and "targetStates.bin" in files                       # main.go:187-188
+    assert np.array_equal(gonumio.LoadVectorCollection(os.path.join(d, "targetStates.bin")), t)
+    onet.set_weights(gonumio.LoadMatrix(os.path.join(d, "matrix.bin")))   # identical bits for the trajectories
     ores = onet.relax_batch(probes.copy(), pool, threads=4)
     assert np.array_equal(np.array(rr["FinalState"].to_pylist()), ores["final"])
     assert rr["NumSteps"].to_pylist() == ores["num_steps"].tolist()
@@ -57,3 +60,31 @@ def test_cli_end_to_end(built, tmp_path):
     assert us["StateIndex"].to_pylist() == first.tolist() and us["Hits"].to_pylist() == hits.tolist()
     hist = pq.read_table(os.path.join(d, "relaxationHistory.pq"))
     assert hist.num_rows == int(ores["num_steps"].sum())
+
+
+@pytest.mark.gpu
+def test_cli_loads_state_files(built, tmp_path):
+    """-targetStatesFile / -probeStatesFile (main.go:46-48,166-177,211-219) override random generation."""
+    import pyarrow.parquet as pq
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import hopfield_main
+    from hopfield_network_go_b200 import gonumio
+    from oracle import orc
+    n, p, b = 64, 5, 40
+    gen = orc.Rng(5)
+    t, probes = gen.generate_states(0, n, p), gen.generate_states(0, n, b)
+    gonumio.SaveVectorCollection(t, str(tmp_path / "t.bin"))
+    gonumio.SaveVectorCollection(probes, str(tmp_path / "p.bin"))
+    d = str(tmp_path / "out")
+    assert hopfield_main.main(["-dimension", str(n), "-numTargetStates", "99", "-numProbeStates", "7", "-dataDir", d, "-seed", "3",
+                               "-targetStatesFile", str(tmp_path / "t.bin"), "-probeStatesFile", str(tmp_path / "p.bin")]) == 0
+    sm = pq.read_table(os.path.join(d, "networkSummary.pq")).to_pylist()[0]
+    assert sm["TargetStates"] == p and sm["ProbeStates"] == b                     # counts come from the files
+    assert np.array_equal(gonumio.LoadVectorCollection(os.path.join(d, "targetStates.bin")), t)
+    onet = orc.Net(n)
+    onet.set_weights(gonumio.LoadMatrix(os.path.join(d, "matrix.bin")))
+    onet.set_targets(t)
+    ores = onet.relax_batch(probes.copy(), orc.Rng(3).perm_pool(n, 100), threads=4)
+    rr = pq.read_table(os.path.join(d, "relaxationResult.pq"))
+    assert np.array_equal(np.array(rr["FinalState"].to_pylist()), ores["final"])
+    assert rr["NumSteps"].to_pylist() == ores["num_steps"].tolist()

@@ -8,7 +8,8 @@ relaxationResult.pq, targetStateProbe.pq, uniqueStates.pq, learnStateData.pq, ne
 
 Differences, all deliberate: additive flags -seed / -device; runs are reproducible; `-threads` is recorded in the
 summary but compute runs on the GPU; REPEATED double columns are written as parquet LIST columns (pyarrow);
-matrix / target states are saved as .npy (the gonumio binary format of main.go:187-188 is SURVEY 8f #2)."""
+matrix.bin / targetStates.bin and -targetStatesFile / -probeStatesFile use gonum's binary encoding as restated in
+hopfield_network_go_b200/gonumio.py (SURVEY 8f #2; unverified against a Go build)."""
 from __future__ import annotations
 
 import argparse
@@ -51,6 +52,8 @@ def parse(argv=None):
     a("-dataDir", default="data/hopfieldData")
     a("-allowIntensiveDataCollection", type=go_bool, nargs="?", const=True, default=False)
     a("-verbose", type=go_bool, nargs="?", const=True, default=False)
+    a("-targetStatesFile", default="")        # main.go:46
+    a("-probeStatesFile", default="")         # main.go:48
     a("-seed", type=int, default=0x5EED)      # additive
     a("-device", type=int, default=0)         # additive
     return ap.parse_args(argv)
@@ -59,7 +62,7 @@ def parse(argv=None):
 def main(argv=None):
     import pyarrow as pa
     import pyarrow.parquet as pq
-    from hopfield_network_go_b200 import capi
+    from hopfield_network_go_b200 import capi, gonumio
     from hopfield_network_go_b200 import hopfieldnetwork as hn
 
     args = parse(argv)
@@ -87,15 +90,19 @@ def main(argv=None):
         return pa.array([r.tolist() for r in rows], type=pa.list_(pa.float64()))
 
     # LEARNING PHASE (main.go:157-188)
-    targets = generator.CreateStateCollection(n, args.numTargetStates)
+    if args.targetStatesFile:                                             # main.go:166-177 (the file overrides generation)
+        targets = capi.pack_states(np.ascontiguousarray(gonumio.LoadVectorCollection(args.targetStatesFile)))
+        args.numTargetStates = len(targets)
+    else:
+        targets = generator.CreateStateCollection(n, args.numTargetStates)
     learn = network.LearnStates(targets, want_energies=True)
     pq.write_table(pa.table({
         "Epoch": pa.array([d.Epoch for d in learn], pa.int32()),
         "TargetStateIndex": pa.array([d.TargetStateIndex for d in learn], pa.int32()),
         "EnergyProfile": lists([d.EnergyProfile for d in learn]),
         "Stable": pa.array([d.Stable for d in learn], pa.bool_())}), os.path.join(args.dataDir, "learnStateData.pq"))
-    np.save(os.path.join(args.dataDir, "matrix.npy"), network.GetMatrix())
-    np.save(os.path.join(args.dataDir, "targetStates.npy"), f64(targets))
+    gonumio.SaveMatrix(network.GetMatrix(), os.path.join(args.dataDir, "matrix.bin"))                 # main.go:187
+    gonumio.SaveVectorCollection(f64(targets), os.path.join(args.dataDir, "targetStates.bin"))        # main.go:188
 
     # target analysis (main.go:190-204)
     e, _, stab, _ = network.energy_profiles(targets)
@@ -106,7 +113,11 @@ def main(argv=None):
     log(f"learned {len(targets)} targets, {int(stab.sum())} stable")
 
     # PROBING PHASE (main.go:206-221)
-    probes = generator.CreateStateCollection(n, args.numProbeStates)
+    if args.probeStatesFile:                                              # main.go:211-219
+        probes = capi.pack_states(np.ascontiguousarray(gonumio.LoadVectorCollection(args.probeStatesFile)))
+        args.numProbeStates = len(probes)
+    else:
+        probes = generator.CreateStateCollection(n, args.numProbeStates)
     res = network.ConcurrentRelaxStates(probes, args.threads, dedup=True, want_energies=True,
                                         history=args.allowIntensiveDataCollection)
 

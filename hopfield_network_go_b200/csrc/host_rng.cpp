@@ -8,6 +8,7 @@
 // NormFloat64.  Reference call sites: hopfieldutils/HopfieldUtils.go:35-39,
 // noiseapplication/NoiseApplication.go:64-105, HopfieldNetworkBuilder.go:231-232.
 // A Go host does not need this file: it calls x/exp/rand directly.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -139,6 +140,62 @@ void rng_advance(hn_rng r, uint64_t draws) {   // as if `draws` Uint64 values ha
 }  // namespace hn
 
 extern "C" {
+
+// Host-side merge of per-GPU unique-attractor tables (multi-GPU probe sharding): groups entries by their
+// 128-bit canonical-state hash; a group's first index is the minimum, its hits the sum; groups are returned in
+// ascending first index = the first-seen order of handleUniqueRelaxedState (UniqueRelaxedStateHandler.go:41-66)
+// over the whole probe set.  O(n) open addressing; pure host code.
+int hn_merge_unique(int64_t n, const int64_t* first, const int32_t* hits, const uint64_t* hash,
+                    int64_t* first_out, int64_t* hits_out, int64_t* rep_out, int64_t* n_groups_out) {
+    if (n < 0 || !n_groups_out || (n > 0 && (!first || !hits || !hash || !first_out || !hits_out || !rep_out))) {
+        hn::set_error("hn_merge_unique: bad argument");
+        return HN_E_INVALID;
+    }
+    size_t cap = 16;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    std::vector<int64_t> slot, gfirst, ghits, grep;
+    try {
+        slot.assign(cap, -1);
+        gfirst.reserve((size_t)n); ghits.reserve((size_t)n); grep.reserve((size_t)n);
+    } catch (const std::bad_alloc&) { hn::set_error("hn_merge_unique: out of host memory"); return HN_E_OOM; }
+    auto home = [&](int64_t i) { return (size_t)((hash[2 * i] ^ (hash[2 * i + 1] * 0x9E3779B97F4A7C15ULL)) & (cap - 1)); };
+    constexpr int64_t kAhead = 16;   // the table is far larger than the caches: fetch the home slots ahead
+    for (int64_t i = 0; i < n; i++) {
+        if (i + kAhead < n) __builtin_prefetch(&slot[home(i + kAhead)], 1, 0);
+        const uint64_t h0 = hash[2 * i], h1 = hash[2 * i + 1];
+        size_t s = home(i);
+        for (;;) {
+            const int64_t g = slot[s];
+            if (g < 0) {
+                slot[s] = (int64_t)gfirst.size();
+                gfirst.push_back(first[i]); ghits.push_back(hits[i]); grep.push_back(i);
+                break;
+            }
+            const int64_t r = grep[(size_t)g];
+            if (hash[2 * r] == h0 && hash[2 * r + 1] == h1) {
+                ghits[(size_t)g] += hits[i];
+                if (first[i] < gfirst[(size_t)g]) { gfirst[(size_t)g] = first[i]; grep[(size_t)g] = i; }
+                break;
+            }
+            s = (s + 1) & (cap - 1);
+        }
+    }
+    // NOTE: a group's representative may move to a later entry (smaller first index), but the hash it is compared by is
+    // the same for every member, so the probe loop above stays correct.
+    const size_t ng = gfirst.size();
+    std::vector<int64_t> order(ng);
+    for (size_t g = 0; g < ng; g++) order[g] = (int64_t)g;
+    bool ascending = true;
+    for (size_t g = 1; g < ng; g++) if (gfirst[g] < gfirst[g - 1]) { ascending = false; break; }
+    if (!ascending)
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return gfirst[(size_t)a] < gfirst[(size_t)b]; });
+    for (size_t j = 0; j < ng; j++) {
+        const size_t g = (size_t)order[j];
+        first_out[j] = gfirst[g]; hits_out[j] = ghits[g]; rep_out[j] = grep[g];
+    }
+    *n_groups_out = (int64_t)ng;
+    return HN_OK;
+}
 
 int hn_rng_create(uint64_t seed, hn_rng* out) {
     if (!out) { hn::set_error("hn_rng_create: out is NULL"); return HN_E_INVALID; }

@@ -22,7 +22,7 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def merge_unique_tables(tables: List[dict]) -> dict:
+def merge_unique_tables(tables: List[dict], numpy_only: bool = False) -> dict:
     """Merge per-rank unique tables.
 
     tables[r] = {"offset": global index of the rank's first probe,
@@ -32,7 +32,10 @@ def merge_unique_tables(tables: List[dict]) -> dict:
                  "states": optional uint64 [U_r][words] canonical-comparable packed states (for verification)}
     Returns {"first": global StateIndex per unique attractor in first-seen order, "hits", "rank_of", "local_id"}.
     Equality is decided on the 128-bit hash; where `states` are supplied, hash-equal entries from different
-    ranks are verified on the full state (a mismatch raises)."""
+    ranks are verified on the full state (a mismatch raises).  Without `states` the merge runs in the C library
+    (hn_merge_unique, O(n)); `numpy_only=True` forces the numpy restatement below (tests compare the two)."""
+    if not numpy_only and all(t.get("states") is None for t in tables):   # the library's O(n) host merge
+        return _merge_native(tables)
     firsts, hits, hashes, ranks, lids, states = [], [], [], [], [], []
     for r, t in enumerate(tables):
         u = len(t["first"])
@@ -77,6 +80,34 @@ def merge_unique_tables(tables: List[dict]) -> dict:
     out_order = np.argsort(g_first, kind="stable")                # first-seen order == ascending first index
     return {"first": g_first[out_order].astype(np.int32), "hits": g_hits[out_order].astype(np.int32),
             "rank_of": rk[rep][out_order], "local_id": lid[rep][out_order]}
+
+
+def _merge_native(tables: List[dict]) -> dict:
+    """merge_unique_tables through hn_merge_unique (hash grouping in C, O(n))."""
+    import ctypes as C
+    from . import capi
+    counts = np.array([len(t["first"]) for t in tables], dtype=np.int64)
+    starts = np.concatenate(([0], np.cumsum(counts)))
+    n = int(starts[-1])
+    if n == 0:
+        z = np.zeros(0, np.int32)
+        return {"first": z, "hits": z.copy(), "rank_of": z.copy(), "local_id": z.copy()}
+    first = np.empty(n, np.int64)
+    hits = np.empty(n, np.int32)
+    hsh = np.empty((n, 2), np.uint64)
+    for r, t in enumerate(tables):
+        a, b = int(starts[r]), int(starts[r + 1])
+        np.add(np.asarray(t["first"]), int(t["offset"]), out=first[a:b], casting="unsafe")
+        hits[a:b] = t["hits"]
+        hsh[a:b] = np.asarray(t["hash"], dtype=np.uint64).reshape(b - a, 2)
+    f_out, h_out, r_out = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int64)
+    ng = C.c_int64()
+    capi.check(capi.load().hn_merge_unique(n, capi.ptr(first), capi.ptr(hits), capi.ptr(hsh), capi.ptr(f_out),
+                                           capi.ptr(h_out), capi.ptr(r_out), C.byref(ng)))
+    rep = r_out[:ng.value]
+    rank_of = (np.searchsorted(starts[1:], rep, side="right")).astype(np.int32)
+    return {"first": f_out[:ng.value].astype(np.int32), "hits": h_out[:ng.value].astype(np.int32),
+            "rank_of": rank_of, "local_id": (rep - starts[rank_of]).astype(np.int32)}
 
 
 def canonical_states(packed: np.ndarray, n: int, domain: int) -> np.ndarray:

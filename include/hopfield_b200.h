@@ -312,6 +312,15 @@ int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip);
 /* ---- conversions -------------------------------------------------------
  * f64 rows -> packed with the domain activation function applied. Host-side
  * helpers for hosts that hold gonum-style float64 state vectors.             */
+/* Merge of per-GPU unique-attractor tables on the host (probes sharded over GPUs): `n` entries, each the
+ * first occurrence of an attractor on some GPU with its GLOBAL probe index `first`, its hit count and the 128-bit hash
+ * of its canonical final state (hn_relax_out.state_hash of that probe).  Entries with equal hashes are one attractor:
+ * first = minimum, hits = sum; the merged table comes back in ascending first index — the order and the counts
+ * handleUniqueRelaxedState (datacollector/UniqueRelaxedStateHandler.go:41-66) produces over the whole probe set.
+ * rep_out[j] = index of the entry that supplied first_out[j].  Outputs hold up to n entries.  Pure host code.   */
+int hn_merge_unique(int64_t n, const int64_t* first, const int32_t* hits, const uint64_t* hash /* [n][2] */,
+                    int64_t* first_out, int64_t* hits_out, int64_t* rep_out, int64_t* n_groups_out);
+
 /* Page-locked host staging buffers (additive extension): every host pointer of this API may be pageable, but
  * probes / results in buffers from hn_host_alloc move at PCIe speed and without a staging copy (a Go binding
  * keeps its flattened []float64 / []uint64 slices in such buffers; reference: the [] *mat.VecDense results of

@@ -99,3 +99,27 @@ def test_target_shards_sum_to_full_dw(built):
             part.hebbian(t[b:e])
         acc += part.w
     assert np.array_equal(acc, full.w)
+
+
+def test_native_merge_equals_numpy_merge():
+    """hn_merge_unique (O(n) hash grouping in the library) == the numpy restatement, including tables whose offsets
+    are not ascending and attractors shared by several ranks."""
+    import numpy as np
+    from hopfield_network_go_b200 import multigpu
+    rs = np.random.default_rng(11)
+    pool = rs.integers(0, 2**63, size=(700, 2), dtype=np.uint64)
+    for trial in range(6):
+        tabs = []
+        for r in range(5):
+            u = int(rs.integers(0, 400))
+            idx = rs.choice(700, size=u, replace=False)
+            first = np.sort(rs.choice(10000, size=u, replace=False)).astype(np.int32)
+            off = r * 10000 if trial < 4 else (4 - r) * 10000
+            tabs.append({"offset": off, "first": first, "hits": rs.integers(1, 50, size=u).astype(np.int32), "hash": pool[idx]})
+        a = multigpu.merge_unique_tables(tabs)
+        b = multigpu.merge_unique_tables(tabs, numpy_only=True)
+        assert set(a) == set(b)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (trial, k)
+        assert int(a["hits"].sum()) == sum(int(t["hits"].sum()) for t in tabs)
+        assert np.all(np.diff(a["first"]) > 0)

@@ -580,24 +580,27 @@ int hebbian_epoch_impl(hn_handle h, const uint64_t* states, int n, ValueMap vm) 
 
 // tvm: value map of the target states as the rule sees them (mapped rules re-activate);
 // the relaxed copies always carry the network domain's values.
-int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised, const uint16_t* perms, int n,
-                     uint64_t* relaxed_out, ValueMap tvm, bool thermal = false) {
+// UpdateState (HopfieldNetwork.go:280-291) for n states: bitsB -> bitsC, one sweep each in its own fresh order
+// (row p of `perms`), no stability test.
+int sweep_once(hn_handle h, int n, const uint16_t* perms) {
     const int N = h->N, words = h->words;
     HN_TRY(ensure_margin(h));
-    HN_TRY(refresh_wt(h));
-    HN_TRY(upload_states(h, h->bitsA, states, n));
-    HN_TRY(upload_states(h, h->bitsB, noised, n));
     HN_TRY(h->bitsC.reserve(sizeof(uint64_t) * (size_t)n * words));
-    // permutations: one fresh order per copy (HopfieldNetwork.go:281-282)
+    if (h->maxabs == 0.0) {
+        // all-zero matrix (the first Delta epoch of a fresh network): every field is an exact zero whatever the state,
+        // h <= 0 selects the low value for every unit (BipolarDomainManager.go:10-22).  Without this every decision
+        // would take the exact tie path: seconds per epoch at N = 16384.
+        HN_CUDA_TRY(cudaMemsetAsync(h->bitsC.p, 0, sizeof(uint64_t) * (size_t)n * words, h->st));
+        return HN_OK;
+    }
+    HN_TRY(refresh_wt(h));
     uint16_t *d_perm = nullptr, *d_inv = nullptr;
     HN_TRY(upload_pool(h, perms, n, h->perms, &d_perm, &d_inv));
-    // offsets[p] = p : copy p uses its own row
-    HN_TRY(h->offsets.reserve(sizeof(int32_t) * (size_t)n));
+    HN_TRY(h->offsets.reserve(sizeof(int32_t) * (size_t)n));   // offsets[p] = p : state p uses its own row
     std::vector<int32_t> off((size_t)n);
     for (int i = 0; i < n; i++) off[i] = i;
     HN_CUDA_TRY(cudaMemcpyAsync(h->offsets.p, off.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));  // `off` must outlive the copy
-    // fields of the noised copies, then ONE sweep each without stability test (UpdateState)
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
     HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
     HN_TRY(h->small.reserve(sizeof(Scratch)));
@@ -609,10 +612,18 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
     p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n;
     p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.max_unstable = 0; p.domain = h->cfg.domain;
-    p.check_stability = 0; p.serial_stream = 0; 
+    p.check_stability = 0; p.serial_stream = 0;
     p.final_states = h->bitsC.as<uint64_t>();
     p.work_counter = &sc->work_counter; p.status = sc->status;
-    HN_TRY(launch_relax(h, p));
+    return launch_relax(h, p);
+}
+
+int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised, const uint16_t* perms, int n,
+                     uint64_t* relaxed_out, ValueMap tvm, bool thermal = false) {
+    const int N = h->N, words = h->words;
+    HN_TRY(upload_states(h, h->bitsA, states, n));
+    HN_TRY(upload_states(h, h->bitsB, noised, n));
+    HN_TRY(sweep_once(h, n, perms));   // one sweep per noised copy in its own fresh order (HopfieldNetwork.go:281-282)
     if (relaxed_out)
         HN_CUDA_TRY(cudaMemcpyAsync(relaxed_out, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));
     // dW[i][j] = sum_mu 0.5*(t_mu,i - r_mu,i) * t_mu,j
@@ -632,6 +643,7 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
         double* part = h->partial.as<double>();
         sumsq_partial_kernel<<<np, RED_THREADS, 0, h->st>>>(h->W, N, h->ldw, part);
         sumsq_final_kernel<<<1, RED_THREADS, 0, h->st>>>(part, np, part + np);
+        HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
         OpBits ta{h->bitsA.as<uint64_t>(), words, n, N, tvm.lo, tvm.hi};
         OpF64 tb{h->W, h->ldw, N};
         EpiStore te{h->H.as<double>(), h->ldw, n, N};
@@ -1071,32 +1083,9 @@ int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint
     if (n <= 0 || !states_packed || !perms) { set_error("hn_update_states: bad argument"); return HN_E_INVALID; }
     HN_TRY(set_device(h));
     HN_TRY(validate_pool_host(h, perms, n));
-    HN_TRY(ensure_margin(h));
-    HN_TRY(refresh_wt(h));
-    const int N = h->N, words = h->words;
+    const int words = h->words;
     HN_TRY(upload_states(h, h->bitsB, states_packed, n));
-    HN_TRY(h->bitsC.reserve(sizeof(uint64_t) * (size_t)n * words));
-    uint16_t *d_perm = nullptr, *d_inv = nullptr;
-    HN_TRY(upload_pool(h, perms, n, h->perms, &d_perm, &d_inv));
-    HN_TRY(h->offsets.reserve(sizeof(int32_t) * (size_t)n));
-    std::vector<int32_t> off((size_t)n);
-    for (int i = 0; i < n; i++) off[i] = i;
-    HN_CUDA_TRY(cudaMemcpyAsync(h->offsets.p, off.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->st));
-    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
-    HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
-    HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
-    HN_TRY(h->small.reserve(sizeof(Scratch)));
-    Scratch* sc = h->scratch();
-    HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));
-    RelaxParams p{};
-    p.N = N; p.ldw = h->ldw; p.words = words;
-    p.Wrow = h->W;
-    p.H0 = h->H.as<double>(); p.ldh = h->ldw;
-    p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv;
-    p.ldp = h->ldp; p.n_pool = n; p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.domain = h->cfg.domain;
-    p.check_stability = 0; 
-    p.final_states = h->bitsC.as<uint64_t>(); p.work_counter = &sc->work_counter; p.status = sc->status;
-    HN_TRY(launch_relax(h, p));
+    HN_TRY(sweep_once(h, n, perms));
     HN_CUDA_TRY(cudaMemcpyAsync(states_packed, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     return HN_OK;

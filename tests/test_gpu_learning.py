@@ -187,3 +187,20 @@ def test_learn_states_thermal_rule_full_loop(built):
     assert [(d.Epoch, d.TargetStateIndex, d.Stable) for d in lsd] == rows
     assert np.allclose(net.GetMatrix(), onet.w, rtol=1e-8, atol=1e-9 * np.abs(onet.w).max())
     net.close()
+
+
+@pytest.mark.parametrize("domain", [0, 1])
+def test_update_state_on_zero_matrix(built, domain):
+    """A fresh network has W = 0: every field is an exact zero, h <= 0 selects the low value for every unit
+    (HopfieldNetwork.go:280-291 with BipolarDomainManager.go:10-22) — the closed-form path of sweep_once."""
+    n, b = 300, 9
+    rng = orc.Rng(8)
+    s = rng.generate_states(domain, n, b)
+    perms = rng.fresh_perms(n, b)
+    onet = orc.Net(n, domain=domain)
+    expect = np.stack([onet.update_state(s[i].copy(), perms[i]) for i in range(b)])
+    assert (expect == (0.0 if domain else -1.0)).all()
+    net = gpu_net(n, domain)
+    out = net.UpdateState(s, perms)
+    assert np.array_equal(out, orc.pack(expect)) and not out.any()
+    net.close()

@@ -299,20 +299,20 @@ int launch_relax_c(hn_handle h, const RelaxParams& p) {
     return HN_E_INVALID;
 }
 // Integer stream: the per-flip work of a warp is dominated by what every warp repeats (scan, barriers, flag, addresses),
-// so probes get FEW, FAT threads: 32 units per thread (int32 fields + packed sign bytes: 72 registers), 7 CTAs of
-// 128 threads per SM at N = 4096 (227k probes/s against 185k with 256 threads x 16 units).
+// so probes get FEW, FAT threads: 32 units per thread (32 int32 fields + 16 registers of column in flight: 56 registers),
+// 9 CTAs of 128 threads per SM at N = 4096 (265k probes/s; 7 CTAs 236k, 8 CTAs 256k, 10 CTAs spill: 180k).
 int launch_relax_int(hn_handle h, const RelaxParams& p) {
     const int n = h->N;
-#ifdef RELAX_INT_OLD_GEOM
-    return launch_relax_c<int16_t>(h, p);
+    if (n <= 256) return launch_relax_t<8, int16_t, 32, 32>(h, p, 0);
+    if (n <= 512) return launch_relax_t<16, int16_t, 32, 32>(h, p, 0);
+    if (n <= 1024) return launch_relax_t<32, int16_t, 32, 32>(h, p, 0);
+    if (n <= 2048) return launch_relax_t<32, int16_t, 64, 18>(h, p, 0);
+#ifndef RELAX_INT_MINB_4096
+#define RELAX_INT_MINB_4096 9
 #endif
-    if (n <= 256) return launch_relax_t<8, int16_t, 32, 28>(h, p, 0);
-    if (n <= 512) return launch_relax_t<16, int16_t, 32, 28>(h, p, 0);
-    if (n <= 1024) return launch_relax_t<32, int16_t, 32, 28>(h, p, 0);
-    if (n <= 2048) return launch_relax_t<32, int16_t, 64, 14>(h, p, 0);
-    if (n <= 4096) return launch_relax_t<32, int16_t, 128, 7>(h, p, 0);
-    if (n <= 8192) return launch_relax_t<32, int16_t, 256, 3>(h, p, 0);
-    if (n <= 16384) return launch_relax_t<32, int16_t, 512, 1>(h, p, 0);
+    if (n <= 4096) return launch_relax_t<32, int16_t, 128, RELAX_INT_MINB_4096>(h, p, 0);
+    if (n <= 8192) return launch_relax_t<32, int16_t, 256, 4>(h, p, 0);
+    if (n <= 16384) return launch_relax_t<32, int16_t, 512, 2>(h, p, 0);
     set_error("relaxation kernel supports dimension <= 16384 (got %d)", n);
     return HN_E_INVALID;
 }

@@ -241,17 +241,12 @@ relax_kernel(RelaxParams p) {
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
         T = thr(0);
-        FT h[UPT];         // float64: local fields h of my units.  Integer stream: ALIGNED exact fields minus one,
-                           // a' = g*v - 1 (g = scale*Wraw*s, v = +-1 by the unit's bit): candidate <=> a' < 0 (one
-                           // funnel shift per unit collects the sign bits), exact tie <=> a' == -1
-        int q[INTF ? (UPT + 1) / 2 : 1];   // integer stream: v * delta of my units as signed bytes, two units per word
-                                           // (even unit: byte 0, odd unit: byte 3) = the multipliers of dp2a.lo / dp2a.hi
-        const int qneg = p.domain == HN_DOMAIN_BINARY ? 0xFE : 0xFC;   // byte ^ qneg negates +-1 (binary) / +-2 (bipolar)
-        uint32_t qdir_up = 1u;   // direction the sign bytes are currently multiplied with (1: a flip 0 -> 1)
-        if constexpr (INTF) {
-#pragma unroll
-            for (int j = 0; j < (UPT + 1) / 2; j++) q[j] = 0;
-        }
+        FT h[UPT];         // float64: local fields h of my units.  Integer stream: u = g - b with the EXACT field
+                           // g = scale*Wraw*s and b the unit's current bit: the unit wants to flip or sits on an exact tie
+                           // (v*g <= 0) <=> signbit(u) != b... precisely: b = 1: g <= 0 <=> u < 0;  b = 0: g >= 0 <=> u >= 0,
+                           // so the candidacy mask is signmask(u) ^ ~bits: one funnel shift per unit and ONE xor per flip.
+                           // A flip adds the same multiple (+-delta) of the column to every field: no per-unit sign
+                           // registers; the flipped unit's owner only moves its own u by -+1 (its bit changed).
         mask_t sbm = 0;    // my units' current bits; SIGNW(r) = 0x80000000 when the bit is clear (v = -1): hi32(h)^SIGNW = hi32(h*v)
 #define SIGNW(r) ((int)((uint32_t)((~sbm >> (r)) & 1u) << 31))
 #pragma unroll
@@ -261,22 +256,21 @@ relax_kernel(RelaxParams p) {
                 const int u = unit_of(c, e), r = c * VEC + e;
                 if (u < N) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
-                    if constexpr (!INTF) sbm |= (mask_t)b << r;
+                    sbm |= (mask_t)b << r;
                     if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
                         const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
-                        h[r] = (b ? g : -g) - 1;
-                        q[r >> 1] |= ((b ? (int)dscale : -(int)dscale) & 0xFF) << ((r & 1) ? 24 : 0);
+                        h[r] = g - (int)b;
                     } else h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited
                     sbm |= (mask_t)1 << r;
-                    if constexpr (INTF) h[r] = 0x7FFFFFFF; else h[r] = __longlong_as_double(0x7FF0000000000000LL);   // (its column entries are 0)
+                    if constexpr (INTF) h[r] = 0x3FFFFFFF; else h[r] = __longlong_as_double(0x7FF0000000000000LL);   // (bit 1, u >= 0; its column entries are 0)
                 }
             }
         }
         // candidacy of my units: bit r set iff hi32(h*v) < T   (aligned field below tau)
         auto cand_mask = [&]() -> mask_t {
             mask_t m = 0;
-            if constexpr (INTF) {   // sign bit of a': wants to flip (aligned < 0) or exact tie (== 0)
+            if constexpr (INTF) {   // signmask(u) ^ ~bits: wants to flip (v*g < 0) or exact tie (g == 0)
                 if constexpr (UPT >= 8) {   // two independent chains halve the dependent latency
                     uint32_t hi = 0, lo = 0;
 #pragma unroll
@@ -289,6 +283,8 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                     for (int r = UPT - 1; r >= 0; r--) m = (mask_t)__funnelshift_l((uint32_t)h[r], (uint32_t)m, 1);
                 }
+                m ^= ~sbm;
+                if constexpr (UPT < 8 * (int)sizeof(mask_t)) m &= ((mask_t)1 << UPT) - 1;
             } else {
 #pragma unroll
                 for (int r = 0; r < UPT; r++)
@@ -296,14 +292,16 @@ relax_kernel(RelaxParams p) {
             }
             return m;
         };
-        // integer stream, owner of a flipping unit: its own sign changes, so its aligned field and its column sign
-        // are negated (a -> -a  <=>  a' -> ~a' - 1).  Commutes with the column update of the same flip.
+        // owner of a flipping unit: new bit into its bit mask and the packed state; integer stream: u = g - b moves by
+        // -+1 with its bit (commutes with the column update of the same flip).
         auto owner_flip = [&](int rr, int k) {
             if constexpr (INTF) {
+                const int step = ((sbm >> rr) & 1u) ? 1 : -1;   // bit 1 -> 0: u = g - 0;  bit 0 -> 1: u = g - 1
 #pragma unroll
                 for (int r = 0; r < UPT; r++)
-                    if (r == rr) { h[r] = ~h[r] - 1; q[r >> 1] ^= qneg << ((r & 1) ? 24 : 0); }
-            } else sbm ^= (mask_t)1 << rr;
+                    if (r == rr) h[r] += step;
+            }
+            sbm ^= (mask_t)1 << rr;
             s_bits[k >> 5] ^= 1u << (k & 31);
         };
         mask_t cm = cand_mask();
@@ -362,8 +360,8 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                     for (int r = 0; r < UPT; r++) { if constexpr (INTF) hw[r] = h[r]; else hw[r] = __double2hiint(h[r]); }
                     const int a = tree_select(hw, rr);
-                    const bool inside = INTF ? (a == -1) : ((a & 0x7FFFFFFF) < T);
                     const uint32_t obit = (s_bits[k >> 5] >> (k & 31)) & 1u;
+                    const bool inside = INTF ? (a + (int)obit == 0) : ((a & 0x7FFFFFFF) < T);   // integer stream: g == 0
                     s_flag = (inside ? 2 : 0) | (int)obit;
                 }
                 __syncthreads();
@@ -382,13 +380,10 @@ relax_kernel(RelaxParams p) {
                     const CT* mycol = reinterpret_cast<const CT*>(p.Wcol) + ((unsigned)k * (unsigned)p.ldw + (unsigned)(tid * VEC));   // my chunk 0 of column k (N*ldw < 2^32)
                     const double d = nb ? dscale : -dscale;
                     if constexpr (INTF) {
-                        // exact int16 column stream, 2N bytes per flip: a' += (v*(+-delta)) * K by dp2a.  The sign bytes are
-                        // kept pre-multiplied by the direction of the last flip and turned over only when it changes.
-                        if (nb != qdir_up) {
-#pragma unroll
-                            for (int j = 0; j < (UPT + 1) / 2; j++) q[j] ^= qneg | (qneg << 24);
-                            qdir_up = nb;
-                        }
+                        // exact int16 column stream, 2N bytes per flip: u += (+-delta) * K[:,k] by dp2a — two int16 column entries
+                        // per word against the multiplier in byte 0 (dp2a.lo: even unit) / byte 3 (dp2a.hi: odd unit)
+                        const int ds = nb ? (int)dscale : -(int)dscale;
+                        const int q = (ds & 0xFF) | ((ds & 0xFF) << 24);
                         auto ipass = [&](auto full_tag) {
                         constexpr bool FULL = decltype(full_tag)::value;   // every chunk lies inside the padded row
                         constexpr int XW = (VEC + 1) / 2;
@@ -419,7 +414,7 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                             for (int e = 0; e < VEC; e++) {
                                 const int r = c * VEC + e;
-                                h[r] = (r & 1) ? __dp2a_hi(x[c][e >> 1], q[r >> 1], h[r]) : __dp2a_lo(x[c][e >> 1], q[r >> 1], h[r]);
+                                h[r] = (r & 1) ? __dp2a_hi(x[c][e >> 1], q, h[r]) : __dp2a_lo(x[c][e >> 1], q, h[r]);
                             }
                         }
                         };
@@ -496,7 +491,7 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
                 if constexpr (INTF) {
-                    if (h[r] < -1) cnt++;          // aligned field negative: certainly unstable
+                    if (((sbm >> r) & 1u) ? (h[r] < -1) : (h[r] > 0)) cnt++;   // v*g < 0: certainly unstable
                 } else {
                     const int a = __double2hiint(h[r]) ^ SIGNW(r);
                     if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
@@ -511,7 +506,7 @@ relax_kernel(RelaxParams p) {
                 for (int r = 0; r < UPT; r++) {
                     const int u = unit_of_r(r);
                     bool inside;
-                    if constexpr (INTF) inside = h[r] == -1; else inside = (__double2hiint(h[r]) & 0x7FFFFFFF) < T;
+                    if constexpr (INTF) inside = h[r] + (int)((sbm >> r) & 1u) == 0; else inside = (__double2hiint(h[r]) & 0x7FFFFFFF) < T;
                     if (inside && u > last) cmin = min(cmin, (uint32_t)u);
                 }
                 cmin = block_min(cmin);

@@ -99,9 +99,9 @@ struct hn_handle_s {
     double* dW = nullptr;
     float* W32 = nullptr;       // float32 shadow of the column matrix (HN_COLUMNS_F32)
     double* Wraw = nullptr;     // un-normalised W captured at normalisation (HN_COLUMNS_I16): W = c * Wraw
-    int16_t* K16 = nullptr;     // int16 image of 2*Wraw, column matrix layout
+    int16_t* K16 = nullptr;     // int16 image of int_scale*Wraw, column matrix layout
     bool int_ok = false;        // the integer structure of the CURRENT W is known and fits int16
-    double int_scale = 2.0;     // K16 = int_scale * Wraw (2: Hebbian / bipolar Delta; 4: binary-domain Delta)
+    double int_scale = 2.0;     // K16 = int_scale * Wraw: the smallest of 0.5, 1, 2, 4 that makes it integer valued
     bool w32_valid = false;
     double maxabs = 0;
     bool w_symmetric = true;   // W known symmetric -> column k == row k
@@ -199,8 +199,11 @@ int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H,
     return launch_gemm_f64(a, b, e, count, h->N, h->N, h->st);
 }
 
-// Integer structure for HN_COLUMNS_I16 from h->Wraw (already on the device): K16 = int16(2*Wraw) in column-matrix
-// layout; int_ok only if every entry is an exact integer within int16 and the exactness bound of the field holds.
+// Integer structure for the exact integer stream from h->Wraw (already on the device): K16 = scale*Wraw in column-matrix
+// layout with the smallest scale in {0.5, 1, 2, 4} that makes every entry an integer (Hebbian: sums of +-1 products, all
+// of the parity of P; Delta: half / quarter integers); int_ok only if every entry fits int16 and the exactness bound of
+// the field holds.  (An int8 image with dp4a was tried for |K| <= 127: half the column bytes, no faster — the kernel is
+// bound by its dependent chain and issue slots, not by the L2->SM bytes; profiles/r01_relax_i16_final_ncu_summary.txt.)
 int build_integer_structure(hn_handle h, bool symmetric) {
     const int64_t total = (int64_t)h->N * h->ldw;
     if (!h->K16) HN_CUDA_TRY(cudaMalloc(&h->K16, sizeof(int16_t) * (size_t)total));
@@ -219,7 +222,7 @@ int build_integer_structure(hn_handle h, bool symmetric) {
     maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->Wraw, h->N, h->ldw, mx);
     HN_CUDA_TRY(cudaGetLastError());
     int32_t f = 1; double m = 0;
-    for (double scale : {2.0, 4.0}) {   // half-integers (Hebbian, bipolar Delta) or quarter-integers (binary Delta)
+    for (double scale : {0.5, 1.0, 2.0, 4.0}) {
         HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
         to_i16_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(src, h->K16, total, scale, flag);
         HN_CUDA_TRY(cudaGetLastError());
@@ -847,7 +850,7 @@ int hn_set_integer_structure(hn_handle h, const double* w_raw) {
     HN_CUDA_TRY(cudaMemcpy2DAsync(h->Wraw, sizeof(double) * h->ldw, w_raw, sizeof(double) * N, sizeof(double) * N, N,
                                   cudaMemcpyHostToDevice, h->st));
     HN_TRY(build_integer_structure(h, h->w_symmetric));
-    if (!h->int_ok) { set_error("hn_set_integer_structure: 4*matrix is not integer valued within int16"); return HN_E_INVALID; }
+    if (!h->int_ok) { set_error("hn_set_integer_structure: no multiple 0.5, 1, 2 or 4 of the matrix is integer valued within int16"); return HN_E_INVALID; }
     return HN_OK;
 }
 int hn_integer_stream_active(hn_handle h, int32_t* active) {

@@ -108,12 +108,12 @@ typedef struct hn_config {
  *                   decision inside the margin is re-evaluated exactly on the float64 matrix in the reference's
  *                   summation order, so final states, step counts, flags and distances do not change.
  *   HN_COLUMNS_I16  exact integer stream for weights learned in this handle (Hebbian / Delta from the zero matrix,
- *                   learning rate 1): then W = c * Wraw with 2*Wraw integer, and the kernel keeps the EXACT int32
- *                   fields g = 2 * Wraw s, adding int16 columns (2N bytes per flip).  sign(g) is the sign of the
+ *                   learning rate 1): then W = c * Wraw with K = m * Wraw integer for an m in {0.5, 1, 2, 4}, and the
+ *                   kernel keeps the EXACT int32 fields g = K s, adding int16 columns (2N bytes per flip).  sign(g) is the sign of the
  *                   reference's field wherever g != 0 (its rounding error is orders of magnitude below c); g == 0 is
  *                   an exact tie of the true field and is re-evaluated on the float64 matrix in the reference's
  *                   summation order.  Falls back to HN_COLUMNS_F64 whenever the integer structure is not known
- *                   (hn_set_weights, further learning after normalisation, |2 Wraw| > 32767).                   */
+ *                   (hn_set_weights, further learning after normalisation, |K| > 32767).                     */
 #define HN_COLUMNS_F64 0
 #define HN_COLUMNS_F32 1
 #define HN_COLUMNS_I16 2
@@ -150,7 +150,7 @@ int hn_set_weights(hn_handle h, const double* w_host);
 int hn_get_weights(hn_handle h, double* w_host);
 /* Declares the integer structure of the resident weights for HN_COLUMNS_I16: the current W equals c * w_unnormalized
  * for some c > 0 (e.g. a host that saved both the normalised matrix and the pre-normalisation matrix and resumes).
- * Checked: 2*w_unnormalized is integer valued within int16 and proportional to W.  Row-major float64, N*N.      */
+ * Checked: 0.5, 1, 2 or 4 times w_unnormalized is integer valued within int16, and it is proportional to W.  Row-major float64, N*N.      */
 int hn_set_integer_structure(hn_handle h, const double* w_unnormalized_host);
 /* 1 if the next relaxation will use the exact integer stream, else 0 */
 int hn_integer_stream_active(hn_handle h, int32_t* active);

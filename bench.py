@@ -247,7 +247,7 @@ def main():
         col_bytes = {"f64": 8, "f32": 4, "i16": 2}[stream]
         field_bytes = 4 if stream == "i16" else 8
         streamed = col_bytes * n * flips + field_bytes * n * sweeps     # what this stream really moves L2->SM per launch
-        kernel = {"f64": "relax_kernel<32,double,128,4>", "f32": "relax_kernel<32,float,128,4>", "i16": "relax_kernel<32,short,128,7>"}[stream]
+        kernel = {"f64": "relax_kernel<32,double,128,4>", "f32": "relax_kernel<32,float,128,4>", "i16": "relax_kernel<32,short,128,9>"}[stream]
         notes = {
             "f64": "bounded by the L2->SM fabric: every flip moves its 8N-byte column L2->SM (~10 TB/s, ~34 B/clk/SM)",
             "f32": "float32 shadow of W: 4N bytes per flip, float64 fields, exact re-evaluation inside the grown margin",
@@ -267,7 +267,7 @@ def main():
                              "note": "per GPU; achieved = ALGORITHMIC bytes of the reference algorithm (8N per flip + 8N per sweep, "
                                      "SURVEY 8d) over the relaxation kernel time; >1 because W stays in L2 (see traffic) and "
                                      "this stream moves fewer bytes than the algorithm names (streamed_bytes_per_launch); "
-                                     + notes[stream] + "; profiles/r01_relax_i16_final_ncu_summary.txt, profiles/r01_relax_f64_ncu_summary.txt",
+                                     + notes[stream] + "; profiles/r01_relax_i16_final_v2_ncu_summary.txt, profiles/r01_relax_f64_ncu_summary.txt",
                              "peak_source": "measured" if peaks else "fallback",
                              "algorithmic_bytes_per_launch": int(alg_bytes), "streamed_bytes_per_launch": int(streamed),
                              "streamed_gbs": streamed * args.steps / (relax_ms_max * 1e-3) / 1e9,

@@ -243,7 +243,7 @@ relax_kernel(RelaxParams p) {
         T = thr(0);
         FT h[UPT];         // float64: local fields h of my units.  Integer stream: u = g - b with the EXACT field
                            // g = scale*Wraw*s and b the unit's current bit: the unit wants to flip or sits on an exact tie
-                           // (v*g <= 0) <=> signbit(u) != b... precisely: b = 1: g <= 0 <=> u < 0;  b = 0: g >= 0 <=> u >= 0,
+                           // (v*g <= 0) exactly when  b = 1: g <= 0 <=> u < 0;   b = 0: g >= 0 <=> u >= 0,
                            // so the candidacy mask is signmask(u) ^ ~bits: one funnel shift per unit and ONE xor per flip.
                            // A flip adds the same multiple (+-delta) of the column to every field: no per-unit sign
                            // registers; the flipped unit's owner only moves its own u by -+1 (its bit changed).

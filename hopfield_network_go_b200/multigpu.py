@@ -124,12 +124,36 @@ def canonical_states(packed: np.ndarray, n: int, domain: int) -> np.ndarray:
 
 
 def gather_unique_tables(local: dict, group=None) -> Optional[dict]:
-    """All ranks call; rank 0 returns the merged table, the others None.  `local` as in merge_unique_tables."""
+    """All ranks call; rank 0 returns the merged table, the others None.  `local` as in merge_unique_tables.
+    Tables travel as ONE padded int64 tensor per rank (first | hits << 32, hash lo, hash hi) through dist.gather —
+    on the device for the nccl backend, on the host for gloo; tables that carry `states` use the object gather."""
+    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    gathered: List[Optional[dict]] = [None] * world
-    dist.gather_object(local, gathered if rank == 0 else None, dst=0, group=group)
+    if local.get("states") is not None:
+        gathered: List[Optional[dict]] = [None] * world
+        dist.gather_object(local, gathered if rank == 0 else None, dst=0, group=group)
+        return merge_unique_tables(gathered) if rank == 0 else None  # type: ignore[arg-type]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    u = len(local["first"])
+    head = torch.tensor([u, int(local["offset"])], dtype=torch.int64, device=dev)
+    heads = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(heads, head, group=group)
+    heads = [h.cpu().numpy() for h in heads]
+    umax = max(1, max(int(h[0]) for h in heads))
+    pay = np.zeros((umax, 3), dtype=np.int64)
+    pay[:u, 0] = np.asarray(local["first"], dtype=np.int64) | (np.asarray(local["hits"], dtype=np.int64) << 32)
+    pay[:u, 1:] = np.ascontiguousarray(local["hash"], dtype=np.uint64).reshape(u, 2).view(np.int64)
+    mine = torch.from_numpy(pay).to(dev)
+    bufs = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, bufs, dst=0, group=group)
     if rank != 0:
         return None
-    return merge_unique_tables(gathered)  # type: ignore[arg-type]
+    tables = []
+    for r in range(world):
+        ur = int(heads[r][0])
+        t = bufs[r][:ur].cpu().numpy()
+        tables.append({"offset": int(heads[r][1]), "first": (t[:, 0] & 0xFFFFFFFF).astype(np.int32),
+                       "hits": (t[:, 0] >> 32).astype(np.int32), "hash": np.ascontiguousarray(t[:, 1:]).view(np.uint64)})
+    return merge_unique_tables(tables)

@@ -37,13 +37,16 @@ def _local_table(net, probes, pool, n, begin, end):
     return {"offset": begin, "first": first, "hits": hits, "hash": hsh, "states": packed}
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, with_states=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     net, probes, pool, n = _problem()
     begin, end = multigpu.shard_range(probes.shape[0], rank, world)
-    merged = multigpu.gather_unique_tables(_local_table(net, probes, pool, n, begin, end))
+    local = _local_table(net, probes, pool, n, begin, end)
+    if not with_states:            # the tensor gather + hn_merge_unique path (what bench.py uses)
+        local.pop("states")
+    merged = multigpu.gather_unique_tables(local)
     if rank == 0:
         q.put((merged["first"].tolist(), merged["hits"].tolist()))
     dist.barrier()
@@ -59,7 +62,8 @@ def test_shard_range_partitions():
         assert max(sizes) - min(sizes) <= 1
 
 
-def test_two_rank_gloo_merge_equals_single_stream(built):
+@pytest.mark.parametrize("with_states", [True, False])
+def test_two_rank_gloo_merge_equals_single_stream(built, with_states):
     net, probes, pool, n = _problem()
     res = net.relax_batch(probes.copy(), pool, threads=2)
     _, first, hits = orc.unique_table(res["energies"])
@@ -67,7 +71,7 @@ def test_two_rank_gloo_merge_equals_single_stream(built):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, with_states)) for r in range(2)]
     for p in procs: p.start()
     got_first, got_hits = q.get(timeout=120)
     for p in procs: p.join(timeout=60)

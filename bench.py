@@ -103,7 +103,8 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], **{k: cfg[k] for k in ("N", "P")}, "probes_per_step": sample},
+            "config": {"workload": cfg["name"], **{k: cfg[k] for k in ("N", "P")}, "probes_per_gpu": cfg["B"],
+                       "probes_per_step": sample, "note": "bounded sample of the same workload per step (CPU)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} probes per step x {len(times)} steps of the same workload, oracle "
                                        "C restatement of the reference algorithm as written (N dots/sweep + 2-3 gemv)"},

@@ -253,7 +253,9 @@ def main():
             "f64": "bounded by the L2->SM fabric: every flip moves its 8N-byte column L2->SM (~10 TB/s, ~34 B/clk/SM)",
             "f32": "float32 shadow of W: 4N bytes per flip, float64 fields, exact re-evaluation inside the grown margin",
             "i16": "exact integer stream: int32 fields and int16 columns (2N bytes per flip) give the reference's float64 "
-                   "decisions bit for bit; exact ties are re-evaluated in float64 in the reference's summation order"}
+                   "decisions bit for bit; exact ties are re-evaluated in float64 in the reference's summation order; the int16 "
+                   "image of W (32 MiB) lives in L2, so DRAM is idle and the kernel is bound by instruction issue (75 % of issue "
+                   "slots, ncu) and the dependent chain of a flip, not by bytes"}
         line = {"metric": METRIC, "value": world * b * args.steps / (step_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

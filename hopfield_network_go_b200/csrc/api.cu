@@ -271,7 +271,7 @@ int select_columns(hn_handle h, RelaxParams& p) {
 bool wants_integer_stream(hn_handle h) { return h->cfg.column_stream == HN_COLUMNS_I16 || h->cfg.column_stream == HN_COLUMNS_AUTO; }
 bool integer_stream(hn_handle h) { return wants_integer_stream(h) && h->int_ok; }
 
-template <int UPT, typename CT, int THREADS = 256, int MINB = 0>
+template <int UPT, typename CT, int THREADS, int MINB>
 int launch_relax_t(hn_handle h, const RelaxParams& p, int grid_cap) {
     auto kern = relax_kernel<UPT, CT, THREADS, MINB>;
     const size_t smem = relax_smem_bytes(h->N, h->ldp, UPT);
@@ -310,10 +310,7 @@ int launch_relax_int(hn_handle h, const RelaxParams& p) {
     if (n <= 512) return launch_relax_t<16, int16_t, 32, 32>(h, p, 0);
     if (n <= 1024) return launch_relax_t<32, int16_t, 32, 32>(h, p, 0);
     if (n <= 2048) return launch_relax_t<32, int16_t, 64, 18>(h, p, 0);
-#ifndef RELAX_INT_MINB_4096
-#define RELAX_INT_MINB_4096 9
-#endif
-    if (n <= 4096) return launch_relax_t<32, int16_t, 128, RELAX_INT_MINB_4096>(h, p, 0);
+    if (n <= 4096) return launch_relax_t<32, int16_t, 128, 9>(h, p, 0);
     if (n <= 8192) return launch_relax_t<32, int16_t, 256, 4>(h, p, 0);
     if (n <= 16384) return launch_relax_t<32, int16_t, 512, 2>(h, p, 0);
     set_error("relaxation kernel supports dimension <= 16384 (got %d)", n);

@@ -102,12 +102,6 @@ __device__ __forceinline__ double exact_field_warp(const double* __restrict__ ro
 }
 
 constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
-#ifndef RELAX_MIN_CTAS
-#define RELAX_MIN_CTAS 4   // 64 registers per thread: +11% at N=4096, +18..26% at N<=2048 over 3 CTAs/SM
-#endif
-#ifndef RELAX_MIN_CTAS_INT
-#define RELAX_MIN_CTAS_INT 5   // int32 aligned fields + int sign words: 48 registers
-#endif
 constexpr int RELAX_TAU_STEP = 256;
 
 // Dynamic shared memory layout (see relax_smem_bytes):
@@ -150,9 +144,10 @@ __device__ __forceinline__ int tree_select(const int (&v)[N_], int idx) {
     return t[0];
 }
 
-// MINB = CTAs per SM the register allocation must allow (0: the default for 256-thread-equivalent occupancy)
-template <int UPT, typename CT, int THREADS, int MINB = 0>
-__global__ void __launch_bounds__(THREADS, MINB > 0 ? MINB : ((std::is_same<CT, int16_t>::value ? RELAX_MIN_CTAS_INT : RELAX_MIN_CTAS) * 256) / THREADS)
+// UPT units per thread, THREADS threads per probe, MINB = CTAs per SM the register allocation must allow (chosen per
+// geometry in api.cu: launch_relax_c / launch_relax_int)
+template <int UPT, typename CT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 relax_kernel(RelaxParams p) {
     constexpr int RELAX_THREADS = THREADS;   // threads per probe: 256 up to N=4096, 512 / 1024 for N=8192 / 16384
     constexpr int RELAX_WARPS = THREADS / 32;

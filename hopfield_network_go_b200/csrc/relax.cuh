@@ -7,13 +7,17 @@
 // state is stable iff #{i : e_i > 0} <= maxUnstable, e = -0.5 (W s) (.) v.
 //
 // B200 design (DESIGN.md "K2"):
-//  * the local fields h = W s of a probe live in registers (UPT doubles per
-//    thread) and are updated INCREMENTALLY: a flip of unit k adds +-delta*W[:,k]
-//    (one coalesced, 128-bit vectorised pass over a 8N-byte column that is
-//    L2/HBM resident) instead of recomputing N dot products per sweep;
+//  * the local fields h = W s of a probe live in registers (UPT per thread:
+//    float64, or exact int32 on the integer stream) and are updated
+//    INCREMENTALLY: a flip of unit k adds +-delta*W[:,k] (one coalesced,
+//    128/256-bit vectorised pass over the column, L2 resident) instead of
+//    recomputing N dot products per sweep;
 //  * between two flips h does not change, so the CTA scans ahead with one
-//    warp-shuffle/`redux` min-reduction to the next position of the sweep order
-//    whose unit wants to flip: the sequential chain is flips long, not N long;
+//    `redux` min-reduction per 1024 positions to the next position of the sweep
+//    order whose unit wants to flip: the sequential chain is flips long, not N long;
+//  * few, fat threads: 32 units per thread (one warp per probe up to N = 1024,
+//    4 warps at N = 4096) because what every warp repeats per flip (scan, two
+//    barriers, flag, addresses) costs more than the update itself;
 //  * energies and the stability test are O(N) reductions over the h already in
 //    registers (no gemv);
 //  * a decision whose incremental |h_k| is below the margin tau (rounding noise
@@ -111,11 +115,11 @@ constexpr int RELAX_TAU_STEP = 256;
 //   s_cand  [ncw, padded to 4]   uint32  POSITION-indexed candidate bitmap: bit i is set iff the unit at
 //           position i of this sweep has aligned field h*v < tau, i.e. wants to flip or sits inside the margin.
 //
-// Per flip: every thread updates its UPT fields in registers (one coalesced 256-bit pass over the column),
-// re-derives the candidacy of its units (hi-word integer compare) and toggles the bitmap only where it
-// changed; __syncthreads; every warp finds the next candidate position with one coalesced read of the bitmap
-// (32 words = 1024 positions per step) + ballot/ffs; the unit's owner publishes (inside-margin?, old bit);
-// __syncthreads.  The L1/LSU data pipe carries the column and almost nothing else.
+// Per flip: every thread updates its UPT fields in registers (one coalesced pass over the column), re-derives the
+// candidacy of its units (float: hi-word integer compare; integer stream: sign bits by funnel shifts) and toggles
+// the bitmap only where it changed; __syncthreads; every warp finds the next candidate position with one coalesced
+// read of the bitmap (32 words = 1024 positions per step) + redux.min; the unit's owner publishes (inside-margin?,
+// old bit); __syncthreads.  The L1/LSU data pipe carries the column and almost nothing else.
 template <int UPT, typename CT> struct RelaxCfg {
     static constexpr int VMAX = std::is_same<CT, int16_t>::value ? 8 : 4;   // one 128-bit load of int16 / float32, one 256-bit load of float64
     static constexpr int VEC = UPT >= VMAX ? VMAX : UPT;   // contiguous units per ownership chunk

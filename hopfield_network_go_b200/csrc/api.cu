@@ -84,7 +84,8 @@ struct Scratch {
     int32_t unique_total;              // dedup: number of unique attractors
     int32_t asym_flag;                 // detect_symmetry
     int32_t int_flag;                  // build_integer_structure: scale*Wraw not an int16 integer somewhere
-    int32_t pad[2];
+    int32_t not_quarters;              // ensure_margin: some W_ij is not a multiple of 0.25
+    int32_t pad;
     unsigned long long rowabs_bits;    // ensure_margin: max_i sum_k |W_ik| (double bits)
     unsigned long long maxabs_bits;    // ensure_margin: max |W_ij|
     unsigned long long maxabs_raw_bits;  // build_integer_structure: max |Wraw_ij|
@@ -107,6 +108,7 @@ struct hn_handle_s {
     bool w_symmetric = true;   // W known symmetric -> column k == row k
     bool margin_valid = false;
     double tau_base = 0, tau_flip = 0;
+    bool exact_arith = false;   // every W_ij is a multiple of 0.25 and N*max|W| is small: fields are exact in float64
     int P = 0;
     DevBuf targets;
     // relaxation working set
@@ -157,12 +159,15 @@ int ensure_margin(hn_handle h) {
     HN_TRY(h->small.reserve(sizeof(Scratch)));
     Scratch* sc = h->scratch();
     HN_CUDA_TRY(cudaMemsetAsync(&sc->rowabs_bits, 0, 16, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(&sc->not_quarters, 0, 4, h->st));
     rowabs_max_kernel<<<h->N, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, &sc->rowabs_bits);
     HN_CUDA_TRY(cudaGetLastError());
-    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->W, h->N, h->ldw, &sc->maxabs_bits);
+    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->W, h->N, h->ldw, &sc->maxabs_bits, &sc->not_quarters);
     HN_CUDA_TRY(cudaGetLastError());
     double rr[2] = {0, 0};
+    int32_t not_quarters = 1;
     HN_CUDA_TRY(cudaMemcpyAsync(rr, &sc->rowabs_bits, 16, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync(&not_quarters, &sc->not_quarters, 4, cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     const double r = rr[0];
     h->maxabs = rr[1];
@@ -170,6 +175,10 @@ int ensure_margin(hn_handle h) {
     // |incremental field - fresh DotUnitary field| <= (N [GEMM] + N/4+3 [fresh] + flips) * u * R; x2 safety
     h->tau_base = 2.0 * (1.25 * h->N + 4.0) * u * r;
     h->tau_flip = 2.0 * u * r;
+    // Exact arithmetic: all entries multiples of 1/4 (un-normalised Hebbian / Delta weights) and every partial sum of a
+    // field, N*max|W| in units of 1/4, far inside 2^53: GEMM, incremental updates and the reference's own dot products
+    // are all exact, so the incremental field EQUALS the reference's and no margin is needed (a zero field is a zero).
+    h->exact_arith = !not_quarters && 4.0 * (double)h->N * h->maxabs < 2251799813685248.0;   // 2^51
     h->margin_valid = true;
     return HN_OK;
 }
@@ -219,7 +228,7 @@ int build_integer_structure(hn_handle h, bool symmetric) {
         transpose_kernel<<<g, b, 0, h->st>>>(h->Wraw, h->dW, h->N, h->ldw);
         src = h->dW;
     }
-    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->Wraw, h->N, h->ldw, mx);
+    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->Wraw, h->N, h->ldw, mx, nullptr);
     HN_CUDA_TRY(cudaGetLastError());
     int32_t f = 1; double m = 0;
     for (double scale : {0.5, 1.0, 2.0, 4.0}) {
@@ -255,6 +264,11 @@ int select_columns(hn_handle h, RelaxParams& p) {
     const double dscale = h->cfg.domain == HN_DOMAIN_BINARY ? 1.0 : 2.0;
     p.tau_base = h->tau_base;
     p.tau_flip = h->tau_flip;
+    p.exact_arith = 0;
+    if (h->exact_arith && h->cfg.column_stream != HN_COLUMNS_F32 && !integer_stream(h)) {
+        p.exact_arith = 1;           // no margin: "inside" means the field is an exact zero, decided as h <= 0 -> low
+        p.tau_base = p.tau_flip = 0.0;
+    }
     if (h->cfg.column_stream == HN_COLUMNS_F32) {
         HN_TRY(ensure_w32(h));
         p.Wcol = h->W32;
@@ -413,7 +427,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         HN_TRY(h->energies.reserve(sizeof(double) * (size_t)B * N));
         HN_TRY(launch_fields(h, h->finals.as<uint64_t>(), B, h->H.as<double>(), domain_values(h->cfg.domain)));
         energy_epilogue_kernel<<<B, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, h->finals.as<uint64_t>(), words,
-                                                            h->W, h->ldw, N, h->cfg.domain, h->tau_base,
+                                                            h->W, h->ldw, N, h->cfg.domain, h->exact_arith ? 0.0 : h->tau_base,
                                                             h->cfg.max_relax_unstable_units, h->energies.as<double>(),
                                                             nullptr, nullptr, nullptr, nullptr);
         HN_CUDA_TRY(cudaGetLastError());
@@ -674,7 +688,7 @@ int energy_profiles_impl(hn_handle h, const uint64_t* d_states, int n, double* e
     HN_TRY(h->estab.reserve((size_t)n));
     HN_TRY(h->esum.reserve(sizeof(double) * (size_t)n));
     energy_epilogue_kernel<<<n, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, d_states, h->words, h->W, h->ldw, N,
-                                                        h->cfg.domain, h->tau_base, h->cfg.max_relax_unstable_units,
+                                                        h->cfg.domain, h->exact_arith ? 0.0 : h->tau_base, h->cfg.max_relax_unstable_units,
                                                         energies_out ? h->energies.as<double>() : nullptr,
                                                         h->eunst.as<int32_t>(), h->estab.as<uint8_t>(), h->esum.as<double>(),
                                                         nullptr);

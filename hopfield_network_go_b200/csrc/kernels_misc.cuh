@@ -141,12 +141,18 @@ __global__ void rowabs_max_kernel(const double* __restrict__ w, int n, int ld, u
     if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(r));
 }
 
-// max_ij |W_ij| (per-flip rounding bound of the float32 column stream); atomicMax on the bits
-__global__ void maxabs_kernel(const double* __restrict__ w, int n, int ld, unsigned long long* out) {
+// max_ij |W_ij| (per-flip rounding bound of the float32 column stream); atomicMax on the bits.
+// not_quarters (optional) <- 1 if some entry is not an integer multiple of 0.25 (exact-arithmetic test, ensure_margin)
+__global__ void maxabs_kernel(const double* __restrict__ w, int n, int ld, unsigned long long* out, int32_t* not_quarters) {
     double m = 0.0;
+    bool off = false;
     const int64_t total = (int64_t)n * ld;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-        m = fmax(m, fabs(w[i]));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = w[i];
+        m = fmax(m, fabs(x));
+        off |= rint(4.0 * x) != 4.0 * x;
+    }
+    if (not_quarters && off) *not_quarters = 1;
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }

@@ -55,6 +55,7 @@ struct RelaxParams {
     int serial_stream;    // 1: one CTA walks the probes in order, offsets = running sweep count
     double int_scale;    // exact integer stream: fields g = int_scale * (Wraw s)
     double tau_base, tau_flip;  // margin tau(F) = tau_base + tau_flip * F (tau_flip includes the float32 stream bound)
+    int exact_arith;     // float64 stream on quarter-integer weights: every field is exact, tau = 0, a zero field is a zero
     // outputs (device)
     uint64_t* final_states;  // [B][words]
     int32_t* num_steps;      // [B]
@@ -368,9 +369,9 @@ relax_kernel(RelaxParams p) {
                 const uint32_t ob = (uint32_t)fl & 1u;
                 uint32_t nb = ob ^ 1u;
                 if (fl & 2) {  // inside the margin: decide exactly, in the reference's summation order
-                    const double hx = exact_field(k);
                     margin++;
-                    nb = hx > 0.0 ? 1u : 0u;
+                    if (p.exact_arith) nb = 0u;   // the reference's field is this exact zero too: h <= 0 selects the low value
+                    else nb = exact_field(k) > 0.0 ? 1u : 0u;
                 }
                 if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
@@ -497,6 +498,15 @@ relax_kernel(RelaxParams p) {
                 }
             }
             cnt = block_sum(cnt);
+            if (!INTF && p.exact_arith) {   // exact zeros: e = -0.5 * 0 * v is not > 0; only counted as margin decisions
+                uint32_t z = 0;
+#pragma unroll
+                for (int r = 0; r < UPT; r++)
+                    if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T) z++;
+                margin += (int)block_sum(z);
+                if ((int)cnt <= p.max_unstable) { is_stable = 1; break; }
+                continue;
+            }
             // units inside the margin: exact recomputation, in increasing unit index
             int last = -1;
             for (;;) {

@@ -113,6 +113,7 @@ struct hn_handle_s {
     DevBuf targets;
     // relaxation working set
     DevBuf jump;   // LCG jump table of hn_generate_probes
+    DevBuf zf;     // per probe: final state has an exactly-zero field (unique-table key)
     DevBuf probes, pool, offsets, H, finals, steps, stable, flips, margin, dist, hash, energies, history;
     DevBuf rep, first, hits, flag, rank, table, attractor, ufirst, uhits, small, partial;
     DevBuf bitsA, bitsB, bitsC, bitsAT, bitsCT, perms, eunst, estab, esum, emargin;
@@ -382,6 +383,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     HN_TRY(h->small.reserve(sizeof(Scratch)));
     if (want_dist && h->P > 0) HN_TRY(h->dist.reserve(sizeof(int32_t) * (size_t)B * h->P));
     if (dedup) HN_TRY(h->hash.reserve(sizeof(uint64_t) * 2 * (size_t)B));
+    if (dedup) HN_TRY(h->zf.reserve((size_t)B));
     if (hist) HN_TRY(h->history.reserve(sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
 
     int launches = 0;
@@ -416,6 +418,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     p.distances = (want_dist && h->P > 0) ? h->dist.as<int32_t>() : nullptr;
     p.targets = h->targets.as<uint64_t>(); p.P = h->P;
     p.hash = dedup ? h->hash.as<uint64_t>() : nullptr;
+    p.zero_field = dedup ? h->zf.as<uint8_t>() : nullptr;
     p.history = hist ? h->history.as<uint64_t>() : nullptr;
     p.work_counter = &sc->work_counter; p.status = sc->status;
     HN_TRY(launch_relax(h, p));
@@ -451,7 +454,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         HN_CUDA_TRY(cudaMemsetAsync(h->hits.p, 0, sizeof(int32_t) * (size_t)B, h->st));
         const int tb = 256, gb = (B + tb - 1) / tb;
         dedup_insert_kernel<<<gb, tb, 0, h->st>>>(h->finals.as<uint64_t>(), h->hash.as<uint64_t>(), B, words, N,
-                                                 h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>());
+                                                 h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>(), h->zf.as<uint8_t>());
         dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), B, h->first.as<int32_t>(), h->hits.as<int32_t>());
         dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), B, h->flag.as<int32_t>());
         scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), &sc->unique_total);

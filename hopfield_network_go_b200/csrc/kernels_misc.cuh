@@ -272,10 +272,13 @@ energy_epilogue_kernel(const double* __restrict__ H, int ldh, const uint64_t* __
 // ---- unique-attractor table (datacollector/UniqueRelaxedStateHandler.go:41-73) ----
 // key: sign-canonical packed final state (== identical energy profile, the
 // reference's key); 128-bit hash picks the bucket, the full state decides equality.
+// za / zb: the state has a unit whose field is an exact zero.  Its unit energy is then -0.5*(+0*v) = -+0, whose SIGN
+// follows v, so s and -s print different energy profiles (the reference's key is fmt.Sprint of the profile,
+// UniqueRelaxedStateHandler.go:44) and must not be merged; without such a unit the profiles are bit-identical.
 __device__ __forceinline__ bool same_canonical(const uint64_t* a, const uint64_t* b, int words, int n,
-                                               int domain) {
-    const bool ia = domain == HN_DOMAIN_BIPOLAR && (a[0] & 1ULL);
-    const bool ib = domain == HN_DOMAIN_BIPOLAR && (b[0] & 1ULL);
+                                               int domain, bool za, bool zb) {
+    const bool ia = domain == HN_DOMAIN_BIPOLAR && (a[0] & 1ULL) && !za;
+    const bool ib = domain == HN_DOMAIN_BIPOLAR && (b[0] & 1ULL) && !zb;
     for (int w = 0; w < words; w++) {
         uint64_t x = a[w], y = b[w];
         uint64_t mask = ~0ULL;
@@ -289,7 +292,7 @@ __device__ __forceinline__ bool same_canonical(const uint64_t* a, const uint64_t
 // table[slot] = representative probe index or -1. rep[p] = representative of p.
 __global__ void dedup_insert_kernel(const uint64_t* __restrict__ finals, const uint64_t* __restrict__ hash,
                                     int B, int words, int n, int domain, int32_t* table, int cap_mask,
-                                    int32_t* __restrict__ rep) {
+                                    int32_t* __restrict__ rep, const uint8_t* __restrict__ zero_field) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     uint32_t slot = (uint32_t)(hash[(size_t)p * 2] ^ (hash[(size_t)p * 2 + 1] >> 17)) & cap_mask;
@@ -297,7 +300,8 @@ __global__ void dedup_insert_kernel(const uint64_t* __restrict__ finals, const u
         int32_t cur = atomicCAS(&table[slot], -1, p);
         if (cur == -1) { rep[p] = p; return; }
         if (hash[(size_t)cur * 2] == hash[(size_t)p * 2] && hash[(size_t)cur * 2 + 1] == hash[(size_t)p * 2 + 1] &&
-            same_canonical(finals + (size_t)cur * words, finals + (size_t)p * words, words, n, domain)) {
+            same_canonical(finals + (size_t)cur * words, finals + (size_t)p * words, words, n, domain,
+                           zero_field[cur] != 0, zero_field[p] != 0)) {
             rep[p] = cur;
             return;
         }

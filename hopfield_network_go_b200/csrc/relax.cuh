@@ -66,6 +66,7 @@ struct RelaxParams {
     const uint64_t* targets; // [P][words]
     int P;
     uint64_t* hash;          // [B][2] canonical-state hash or nullptr
+    uint8_t* zero_field;     // [B] 1 iff the final state has a unit with an exactly zero field (dedup key, see same_canonical)
     uint64_t* history;       // [B][max_iter+1][words] or nullptr
     int32_t* work_counter;   // dynamic probe scheduler
     int32_t* status;         // [0]: set to 1 when the pool was exhausted; [1]: rows needed
@@ -311,6 +312,7 @@ relax_kernel(RelaxParams p) {
         }
 
         int flips = 0, margin = 0, sweeps = 0, is_stable = 0, pool_fail = 0;
+        int zero_field = 0;   // the state after the LAST sweep has a unit whose (reference-order) field is exactly zero
         for (int sweep = 0; sweep < p.max_iter; sweep++) {
             const long long row = rowbase + sweep;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
@@ -503,12 +505,15 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
                 for (int r = 0; r < UPT; r++)
                     if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T) z++;
-                margin += (int)block_sum(z);
+                const int nz = (int)block_sum(z);
+                margin += nz;
+                zero_field = nz > 0;
                 if ((int)cnt <= p.max_unstable) { is_stable = 1; break; }
                 continue;
             }
             // units inside the margin: exact recomputation, in increasing unit index
             int last = -1;
+            zero_field = 0;
             for (;;) {
                 uint32_t cmin = RELAX_NONE;
 #pragma unroll
@@ -523,6 +528,7 @@ relax_kernel(RelaxParams p) {
                 last = (int)cmin;
                 const double hx = exact_field(last);
                 margin++;
+                if (hx == 0.0) zero_field = 1;
                 const uint32_t ob = (s_bits[last >> 5] >> (last & 31)) & 1u;
                 const double vi = ob ? 1.0 : -1.0;
                 const double en = -0.5 * (hx * vi);
@@ -546,6 +552,7 @@ relax_kernel(RelaxParams p) {
             if (p.stable) p.stable[pi] = (uint8_t)is_stable;
             if (p.flips) p.flips[pi] = flips;
             if (p.margin_hits) p.margin_hits[pi] = margin;
+            if (p.zero_field) p.zero_field[pi] = (uint8_t)zero_field;
             if (p.serial_stream) { s_probe = pi + 1; s_rowbase = rowbase + sweeps; }
         }
         // Manhattan distance with inversion to every target (DistanceMeasure.go:28-42):
@@ -565,7 +572,7 @@ relax_kernel(RelaxParams p) {
         // 128-bit hash of the sign-canonical final state (bipolar: s and -s share an
         // energy profile bit for bit, which is the reference's dedup key).
         if (p.hash) {
-            const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u);
+            const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !zero_field;
             uint64_t h0 = 0, h1 = 0;
             for (int w = tid; w < nbw; w += RELAX_THREADS) {
                 uint32_t x = s_bits[w];

@@ -102,6 +102,7 @@ struct hn_handle_s {
     double* Wraw = nullptr;     // un-normalised W captured at normalisation (HN_COLUMNS_I16): W = c * Wraw
     int16_t* K16 = nullptr;     // int16 image of int_scale*Wraw, column matrix layout
     bool int_ok = false;        // the integer structure of the CURRENT W is known and fits int16
+    double key_scale = 0.0;     // int_ok: (K s)_i = rint(key_scale * (W s)_i): exact energy-profile key on the float streams
     double int_scale = 2.0;     // K16 = int_scale * Wraw: the smallest of 0.5, 1, 2, 4 that makes it integer valued
     bool w32_valid = false;
     double maxabs = 0;
@@ -184,7 +185,7 @@ int ensure_margin(hn_handle h) {
     return HN_OK;
 }
 
-void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; h->int_ok = false; }
+void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; h->int_ok = false; h->key_scale = 0.0; }
 
 // exact symmetry test of the resident W (decides whether column k can be read as row k)
 int detect_symmetry(hn_handle h) {
@@ -214,7 +215,7 @@ int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H,
 // of the parity of P; Delta: half / quarter integers); int_ok only if every entry fits int16 and the exactness bound of
 // the field holds.  (An int8 image with dp4a was tried for |K| <= 127: half the column bytes, no faster — the kernel is
 // bound by its dependent chain and issue slots, not by the L2->SM bytes; profiles/r01_relax_i16_final_ncu_summary.txt.)
-int build_integer_structure(hn_handle h, bool symmetric) {
+int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W = fl(c * Wraw)
     const int64_t total = (int64_t)h->N * h->ldw;
     if (!h->K16) HN_CUDA_TRY(cudaMalloc(&h->K16, sizeof(int16_t) * (size_t)total));
     HN_TRY(h->small.reserve(sizeof(Scratch)));
@@ -245,6 +246,7 @@ int build_integer_structure(hn_handle h, bool symmetric) {
     // fresh-dot rounding error << c  <=>  N^2 * max|2 Wraw| * 2^-50 < 0.5   (same precondition as oracle_fast.c)
     const bool exact = (double)h->N * (double)h->N * (h->int_scale * m) * 8.881784197001252e-16 < 0.5;
     h->int_ok = (f == 0) && exact && m > 0.0;
+    h->key_scale = (h->int_ok && c > 0.0) ? h->int_scale / c : 0.0;   // K s = key_scale * (W s), to the nearest integer
     return HN_OK;
 }
 
@@ -266,6 +268,7 @@ int select_columns(hn_handle h, RelaxParams& p) {
     p.tau_base = h->tau_base;
     p.tau_flip = h->tau_flip;
     p.exact_arith = 0;
+    p.key_scale = h->int_ok ? h->key_scale : 0.0;
     if (h->exact_arith && h->cfg.column_stream != HN_COLUMNS_F32 && !integer_stream(h)) {
         p.exact_arith = 1;           // no margin: "inside" means the field is an exact zero, decided as h <= 0 -> low
         p.tau_base = p.tau_flip = 0.0;
@@ -454,7 +457,8 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         HN_CUDA_TRY(cudaMemsetAsync(h->hits.p, 0, sizeof(int32_t) * (size_t)B, h->st));
         const int tb = 256, gb = (B + tb - 1) / tb;
         dedup_insert_kernel<<<gb, tb, 0, h->st>>>(h->finals.as<uint64_t>(), h->hash.as<uint64_t>(), B, words, N,
-                                                 h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>(), h->zf.as<uint8_t>());
+                                                 h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>(), h->zf.as<uint8_t>(),
+                                                 (p.exact_arith || integer_stream(h) || p.key_scale != 0.0) ? 1 : 0);
         dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), B, h->first.as<int32_t>(), h->hits.as<int32_t>());
         dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), B, h->flag.as<int32_t>());
         scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), &sc->unique_total);
@@ -863,7 +867,7 @@ int hn_set_integer_structure(hn_handle h, const double* w_raw) {
     HN_CUDA_TRY(cudaMemsetAsync(h->Wraw, 0, wb, h->st));
     HN_CUDA_TRY(cudaMemcpy2DAsync(h->Wraw, sizeof(double) * h->ldw, w_raw, sizeof(double) * N, sizeof(double) * N, N,
                                   cudaMemcpyHostToDevice, h->st));
-    HN_TRY(build_integer_structure(h, h->w_symmetric));
+    HN_TRY(build_integer_structure(h, h->w_symmetric, c));
     if (!h->int_ok) { set_error("hn_set_integer_structure: no multiple 0.5, 1, 2 or 4 of the matrix is integer valued within int16"); return HN_E_INVALID; }
     return HN_OK;
 }
@@ -944,7 +948,7 @@ int hn_normalize_frobenius(hn_handle h, double* norm_out) {
     const int np = 1024;
     HN_TRY(h->partial.reserve(sizeof(double) * (np + 2)));
     double* part = h->partial.as<double>();
-    const bool capture = wants_integer_stream(h);
+    const bool capture = true;   // every stream: the integer structure also gives the exact unique-table key (relax.cuh)
     if (capture) {  // keep the un-normalised matrix: W = (1/norm) * Wraw is the integer structure of the new weights
         const size_t wb = sizeof(double) * (size_t)h->N * h->ldw;
         if (!h->Wraw) HN_CUDA_TRY(cudaMalloc(&h->Wraw, wb));
@@ -959,7 +963,7 @@ int hn_normalize_frobenius(hn_handle h, double* norm_out) {
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     if (norm_out) *norm_out = nrm[0];
     weights_changed(h);
-    if (capture && nrm[0] > 0.0 && std::isfinite(nrm[0])) HN_TRY(build_integer_structure(h, h->w_symmetric));
+    if (capture && nrm[0] > 0.0 && std::isfinite(nrm[0])) HN_TRY(build_integer_structure(h, h->w_symmetric, nrm[1]));
     return HN_OK;
 }
 

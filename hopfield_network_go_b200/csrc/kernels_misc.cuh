@@ -292,16 +292,19 @@ __device__ __forceinline__ bool same_canonical(const uint64_t* a, const uint64_t
 // table[slot] = representative probe index or -1. rep[p] = representative of p.
 __global__ void dedup_insert_kernel(const uint64_t* __restrict__ finals, const uint64_t* __restrict__ hash,
                                     int B, int words, int n, int domain, int32_t* table, int cap_mask,
-                                    int32_t* __restrict__ rep, const uint8_t* __restrict__ zero_field) {
+                                    int32_t* __restrict__ rep, const uint8_t* __restrict__ zero_field, int hash_is_key) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     uint32_t slot = (uint32_t)(hash[(size_t)p * 2] ^ (hash[(size_t)p * 2 + 1] >> 17)) & cap_mask;
     for (;;) {
         int32_t cur = atomicCAS(&table[slot], -1, p);
         if (cur == -1) { rep[p] = p; return; }
+        // hash_is_key: the 128 bits hash the exact energy profile (relax.cuh) and ARE the key; else they pick the bucket
+        // and the sign-canonical state decides
         if (hash[(size_t)cur * 2] == hash[(size_t)p * 2] && hash[(size_t)cur * 2 + 1] == hash[(size_t)p * 2 + 1] &&
+            (hash_is_key ||
             same_canonical(finals + (size_t)cur * words, finals + (size_t)p * words, words, n, domain,
-                           zero_field[cur] != 0, zero_field[p] != 0)) {
+                           zero_field[cur] != 0, zero_field[p] != 0))) {
             rep[p] = cur;
             return;
         }

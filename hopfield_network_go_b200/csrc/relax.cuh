@@ -55,6 +55,7 @@ struct RelaxParams {
     int serial_stream;    // 1: one CTA walks the probes in order, offsets = running sweep count
     double int_scale;    // exact integer stream: fields g = int_scale * (Wraw s)
     double tau_base, tau_flip;  // margin tau(F) = tau_base + tau_flip * F (tau_flip includes the float32 stream bound)
+    double key_scale;    // != 0: weights have a known integer structure, rint(key_scale * h) is the exact integer field (unique-table key)
     int exact_arith;     // float64 stream on quarter-integer weights: every field is exact, tau = 0, a zero field is a zero
     // outputs (device)
     uint64_t* final_states;  // [B][words]
@@ -313,6 +314,7 @@ relax_kernel(RelaxParams p) {
 
         int flips = 0, margin = 0, sweeps = 0, is_stable = 0, pool_fail = 0;
         int zero_field = 0;   // the state after the LAST sweep has a unit whose (reference-order) field is exactly zero
+        uint64_t tz0 = 0, tz1 = 0;   // integer stream: hash marks of those units, by the sign of v (profile key below)
         for (int sweep = 0; sweep < p.max_iter; sweep++) {
             const long long row = rowbase + sweep;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
@@ -514,6 +516,7 @@ relax_kernel(RelaxParams p) {
             // units inside the margin: exact recomputation, in increasing unit index
             int last = -1;
             zero_field = 0;
+            tz0 = tz1 = 0;
             for (;;) {
                 uint32_t cmin = RELAX_NONE;
 #pragma unroll
@@ -528,8 +531,12 @@ relax_kernel(RelaxParams p) {
                 last = (int)cmin;
                 const double hx = exact_field(last);
                 margin++;
-                if (hx == 0.0) zero_field = 1;
                 const uint32_t ob = (s_bits[last >> 5] >> (last & 31)) & 1u;
+                if (hx == 0.0) {   // unit energy -0.5*(+0*v): a zero whose sign follows v
+                    zero_field = 1;
+                    tz0 ^= mix64(((uint64_t)(last + 1) << 1 | ob) ^ 0xA24BAED4963EE407ULL);
+                    tz1 ^= mix64(((uint64_t)(last + 1) << 1 | ob) * 0x9FB21C651E98DF25ULL + 0x632BE59BD9B4E019ULL);
+                }
                 const double vi = ob ? 1.0 : -1.0;
                 const double en = -0.5 * (hx * vi);
                 if (en > 0.0) cnt++;
@@ -569,11 +576,39 @@ relax_kernel(RelaxParams p) {
                 }
             }
         }
-        // 128-bit hash of the sign-canonical final state (bipolar: s and -s share an
-        // energy profile bit for bit, which is the reference's dedup key).
+        // 128-bit unique-table key.  The reference keys on the printed energy profile
+        // (UniqueRelaxedStateHandler.go:44).  Where the profile is known EXACTLY — integer stream: v*g per unit;
+        // exact float arithmetic: the float64 values themselves — the key is a hash of the profile (plus, on the integer
+        // stream, a mark for every unit whose re-evaluated float field is +0: its energy is a zero whose sign follows
+        // v), so distinct states with identical profiles share a key exactly as in the reference (two stored patterns of
+        // a P=2 network do) and s / -s separate exactly when a zero energy changes sign.  Otherwise: hash of the
+        // sign-canonical final state (s and -s share a profile bit for bit unless a field is an exact zero).
         if (p.hash) {
-            const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !zero_field;
             uint64_t h0 = 0, h1 = 0;
+            if (INTF || p.exact_arith || p.key_scale != 0.0) {
+#pragma unroll
+                for (int r = 0; r < UPT; r++) {
+                    const int u = unit_of_r(r);
+                    if (u < N) {
+                        const uint32_t b = (uint32_t)((sbm >> r) & 1u);
+                        uint64_t val;
+                        if constexpr (INTF) {
+                            val = (uint64_t)(uint32_t)(b ? (int)h[r] + 1 : -(int)h[r]);   // v*g from u = g - b
+                        } else if (p.exact_arith) {
+                            const double hv = (double)h[r];
+                            val = (uint64_t)__double_as_longlong((hv == 0.0 ? 0.0 : hv) * (b ? 1.0 : -1.0));   // h*v, the bits behind e
+                        } else {
+                            const long long g = __double2ll_rn((double)h[r] * p.key_scale);   // exact: |error| << 1/2
+                            val = (uint64_t)(uint32_t)(int)(b ? g : -g);
+                        }
+                        const uint64_t y = mix64((uint64_t)(u + 1) * 0x9E3779B97F4A7C15ULL);
+                        h0 ^= mix64(val ^ y);
+                        h1 ^= mix64((val + 0x2545F4914F6CDD1DULL) * 0xD6E8FEB86659FD93ULL ^ (y >> 7));
+                    }
+                }
+                if (!p.exact_arith && tid == 0) { h0 ^= tz0; h1 ^= tz1; }   // units whose re-evaluated float field is +0
+            } else {
+            const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !zero_field;
             for (int w = tid; w < nbw; w += RELAX_THREADS) {
                 uint32_t x = s_bits[w];
                 if (inv) {
@@ -583,6 +618,7 @@ relax_kernel(RelaxParams p) {
                 const uint64_t y = ((uint64_t)(w + 1) << 32) | x;
                 h0 ^= mix64(y ^ 0x9E3779B97F4A7C15ULL);
                 h1 ^= mix64(y * 0xD6E8FEB86659FD93ULL + 0x2545F4914F6CDD1DULL);
+            }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

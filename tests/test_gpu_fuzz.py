@@ -62,3 +62,57 @@ def test_random_small_configuration(built, seed):
     _, first, hits = orc.unique_table(ores["energies"])
     assert np.array_equal(res.UniqueFirst, first) and np.array_equal(res.UniqueHits, hits), c
     net.close()
+
+
+def _case2(seed):
+    rs = np.random.default_rng(1000 + seed)
+    n = int(rs.choice([200, 257, 300, 511, 513, 700, 1024, 1025, 1500, 2049]))
+    return dict(n=n, p=int(rs.integers(2, max(3, n // 12))), domain=int(rs.integers(0, 2)),
+                rule=int(rs.choice([hn.HebbianLearningRule, hn.DeltaLearningRule])), epochs=int(rs.integers(1, 4)),
+                stream=int(rs.integers(0, 4)), mode=str(rs.choice(["plain", "offsets", "serial", "history"])),
+                max_unstable=int(rs.choice([0, 0, 2])), b=int(rs.integers(2, 20 if n > 1024 else 48)))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_medium_configuration(built, seed):
+    """Every thread geometry up to N = 2049 (one, two and four warps per probe), every column stream, with offsets /
+    the serial stream / history capture, learned in the library, against the oracle."""
+    import ctypes as C
+    c = _case2(seed)
+    n, p, domain, b = c["n"], c["p"], c["domain"], c["b"]
+    rng = orc.Rng(7000 + seed)
+    t = rng.generate_states(domain, n, p)
+    net = gpu_net(n, domain, rule=c["rule"], epochs=c["epochs"], seed=seed, SetColumnStream=c["stream"],
+                  SetLearningNoiseMethod=hn.MaximalInversion, SetLearningNoiseRatio=0.1,
+                  SetMaximumRelaxationUnstableUnits=c["max_unstable"])
+    net.LearnStates(t.copy())
+    onet = orc.Net(n, domain=domain, max_unstable=c["max_unstable"], w=net.GetMatrix())
+    onet.set_targets(t)
+    probes = rng.generate_states(domain, n, b)
+    kw_o, kw_g = {}, {}
+    pool = rng.perm_pool(n, 100)
+    if c["mode"] == "offsets":
+        pool = rng.perm_pool(n, 140)
+        off = (np.arange(b) * 7 % 40).astype(np.int32)
+        kw_o["offsets"] = off; kw_g["offsets"] = off
+    elif c["mode"] == "serial":
+        pool = rng.perm_pool(n, 100 * b)
+        kw_o["serial_stream"] = True; kw_g["serial_stream"] = True
+    elif c["mode"] == "history":
+        kw_g["history"] = True
+    ores = onet.relax_batch(probes.copy(), pool, threads=1 if c["mode"] == "serial" else 4, want_energies=True, **kw_o)
+    res = net.relax_batch(probes, pool, dedup=True, want_energies=True, **kw_g)
+    assert_relax_equal(res, ores, n)
+    assert np.allclose(res.EnergyProfiles, ores["energies"], rtol=1e-9, atol=1e-300), c
+    _, first, hits = orc.unique_table(ores["energies"])
+    assert np.array_equal(res.UniqueFirst, first) and np.array_equal(res.UniqueHits, hits), c
+    if c["mode"] == "history":
+        for i in range(min(b, 6)):
+            st = probes[i].copy()
+            hist = np.zeros((onet.c.max_iter + 1, n))
+            info = orc.OrcRelaxInfo()
+            orc.lib().orc_relax_state(onet.ref(), st.ctypes.data_as(C.c_void_p), pool.ctypes.data_as(C.c_void_p), pool.shape[0], 0,
+                                      C.byref(info), None, None, hist.ctypes.data_as(C.c_void_p), 0)
+            k = info.num_steps
+            assert res.NumSteps[i] == k and np.array_equal(res.History[i, :k], orc.pack(hist[:k])), c
+    net.close()

@@ -102,6 +102,7 @@ struct hn_handle_s {
     double* Wraw = nullptr;     // un-normalised W captured at normalisation (HN_COLUMNS_I16): W = c * Wraw
     int16_t* K16 = nullptr;     // int16 image of int_scale*Wraw, column matrix layout
     bool int_ok = false;        // the integer structure of the CURRENT W is known and fits int16
+    double int_maxabs = 0.0;    // max |K16 entry|
     double key_scale = 0.0;     // int_ok: (K s)_i = rint(key_scale * (W s)_i): exact energy-profile key on the float streams
     double int_scale = 2.0;     // K16 = int_scale * Wraw: the smallest of 0.5, 1, 2, 4 that makes it integer valued
     bool w32_valid = false;
@@ -246,6 +247,7 @@ int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W =
     // fresh-dot rounding error << c  <=>  N^2 * max|2 Wraw| * 2^-50 < 0.5   (same precondition as oracle_fast.c)
     const bool exact = (double)h->N * (double)h->N * (h->int_scale * m) * 8.881784197001252e-16 < 0.5;
     h->int_ok = (f == 0) && exact && m > 0.0;
+    h->int_maxabs = h->int_scale * m;
     h->key_scale = (h->int_ok && c > 0.0) ? h->int_scale / c : 0.0;   // K s = key_scale * (W s), to the nearest integer
     return HN_OK;
 }
@@ -400,7 +402,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     const bool int_fields = integer_stream(h) && h->w_symmetric;
     if (int_fields)
         HN_TRY(launch_igemm_fields(d_probes, h->words, B, h->K16, h->ldw, N, h->cfg.domain == HN_DOMAIN_BIPOLAR,
-                                   reinterpret_cast<int32_t*>(h->H.as<double>()), h->ldw, h->st));
+                                   reinterpret_cast<int32_t*>(h->H.as<double>()), h->ldw, h->int_maxabs <= 127.0, h->st));
     else
         HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
     launches++;
@@ -426,6 +428,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     p.work_counter = &sc->work_counter; p.status = sc->status;
     HN_TRY(launch_relax(h, p));
     launches++;
+    const bool profile_keyed = p.exact_arith || integer_stream(h) || p.key_scale != 0.0;   // see the epilogue of relax_kernel
     HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
 
     if (want_energies) {
@@ -458,7 +461,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
         const int tb = 256, gb = (B + tb - 1) / tb;
         dedup_insert_kernel<<<gb, tb, 0, h->st>>>(h->finals.as<uint64_t>(), h->hash.as<uint64_t>(), B, words, N,
                                                  h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>(), h->zf.as<uint8_t>(),
-                                                 (p.exact_arith || integer_stream(h) || p.key_scale != 0.0) ? 1 : 0);
+                                                 profile_keyed ? 1 : 0);
         dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), B, h->first.as<int32_t>(), h->hits.as<int32_t>());
         dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), B, h->flag.as<int32_t>());
         scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), &sc->unique_total);

@@ -29,6 +29,8 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib, bool bipolar) {
 }
 
 // grid: (ceil(N/IG_BN), ceil(B/IG_BM)); 256 threads = 8 warps as 4 (M) x 2 (N), warp tile 32 x 32
+// SINGLE: every |K| <= 127, the low byte of an entry is the entry as a signed byte: one s8 x s8 MMA per tile, no high plane
+template <bool SINGLE>
 __global__ void __launch_bounds__(256)
 igemm_fields_kernel(const uint64_t* __restrict__ states, int words, int B, const int16_t* __restrict__ K, int ldk, int N,
                     int bipolar, int32_t* __restrict__ G, int ldg) {
@@ -90,7 +92,7 @@ igemm_fields_kernel(const uint64_t* __restrict__ states, int words, int B, const
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             ql[i] = __byte_perm(w[2 * i], w[2 * i + 1], 0x6420);
-            qh[i] = __byte_perm(w[2 * i], w[2 * i + 1], 0x7531);
+            if constexpr (!SINGLE) qh[i] = __byte_perm(w[2 * i], w[2 * i + 1], 0x7531);
         }
     };
 
@@ -115,8 +117,10 @@ igemm_fields_kernel(const uint64_t* __restrict__ states, int words, int B, const
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int off = (wn0 + j * 8 + g) * IG_LD + ks * 32 + 4 * t;
-                bh[j][0] = *reinterpret_cast<const uint32_t*>(&sBh[buf][off]);
-                bh[j][1] = *reinterpret_cast<const uint32_t*>(&sBh[buf][off + 16]);
+                if constexpr (!SINGLE) {
+                    bh[j][0] = *reinterpret_cast<const uint32_t*>(&sBh[buf][off]);
+                    bh[j][1] = *reinterpret_cast<const uint32_t*>(&sBh[buf][off + 16]);
+                }
                 bl[j][0] = *reinterpret_cast<const uint32_t*>(&sBl[buf][off]);
                 bl[j][1] = *reinterpret_cast<const uint32_t*>(&sBl[buf][off + 16]);
             }
@@ -124,8 +128,8 @@ igemm_fields_kernel(const uint64_t* __restrict__ states, int words, int B, const
             for (int i = 0; i < 2; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    imma_s8s8(acc_h[i][j], af[i], bh[j]);
-                    imma_s8u8(acc_l[i][j], af[i], bl[j]);
+                    if constexpr (SINGLE) imma_s8s8(acc_l[i][j], af[i], bl[j]);
+                    else { imma_s8s8(acc_h[i][j], af[i], bh[j]); imma_s8u8(acc_l[i][j], af[i], bl[j]); }
                 }
         }
         if (kt + 1 < ktiles) sstore(buf ^ 1, (kt + 1) * IG_BK);
@@ -140,8 +144,8 @@ igemm_fields_kernel(const uint64_t* __restrict__ states, int words, int B, const
             for (int hrow = 0; hrow < 2; hrow++) {
                 const int row = m0 + wm0 + i * 16 + g + 8 * hrow;
                 if (row < B && col < ldg) {   // ldg is even and >= N; padding columns get zeros (K rows beyond N are zero)
-                    const int v0 = 256 * acc_h[i][j][2 * hrow] + acc_l[i][j][2 * hrow];
-                    const int v1 = 256 * acc_h[i][j][2 * hrow + 1] + acc_l[i][j][2 * hrow + 1];
+                    const int v0 = (SINGLE ? 0 : 256 * acc_h[i][j][2 * hrow]) + acc_l[i][j][2 * hrow];
+                    const int v1 = (SINGLE ? 0 : 256 * acc_h[i][j][2 * hrow + 1]) + acc_l[i][j][2 * hrow + 1];
                     *reinterpret_cast<int2*>(G + (size_t)row * ldg + col) = make_int2(v0, v1);
                 }
             }
@@ -149,10 +153,11 @@ igemm_fields_kernel(const uint64_t* __restrict__ states, int words, int B, const
 }
 
 static inline int launch_igemm_fields(const uint64_t* states, int words, int B, const int16_t* K, int ldk, int N, bool bipolar,
-                                      int32_t* G, int ldg, cudaStream_t st) {
+                                      int32_t* G, int ldg, bool fits_s8, cudaStream_t st) {
     if (B <= 0) return HN_OK;
     dim3 grid((N + IG_BN - 1) / IG_BN, (B + IG_BM - 1) / IG_BM);
-    igemm_fields_kernel<<<grid, 256, 0, st>>>(states, words, B, K, ldk, N, bipolar ? 1 : 0, G, ldg);
+    if (fits_s8) igemm_fields_kernel<true><<<grid, 256, 0, st>>>(states, words, B, K, ldk, N, bipolar ? 1 : 0, G, ldg);
+    else igemm_fields_kernel<false><<<grid, 256, 0, st>>>(states, words, B, K, ldk, N, bipolar ? 1 : 0, G, ldg);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }

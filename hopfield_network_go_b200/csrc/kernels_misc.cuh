@@ -2,6 +2,7 @@
 // weight update + constraints + Frobenius normalisation, energy epilogue,
 // permutation inversion, bit-matrix transpose, unique-attractor table.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "relax.cuh"
 

@@ -73,11 +73,6 @@ struct RelaxParams {
     int32_t* status;         // [0]: set to 1 when the pool was exhausted; [1]: rows needed
 };
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
-    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
-    x ^= x >> 31; return x;
-}
 
 
 // Exact field of one unit in the reference's summation order (gonum f64.DotUnitary,
@@ -178,6 +173,8 @@ relax_kernel(RelaxParams p) {
     __shared__ __align__(16) uint32_t s_red[2][32];
     __shared__ double s_exact[4];
     __shared__ int s_probe;
+    __shared__ int s_zero_field;                 // the state after the LAST sweep has a unit whose reference-order field is exactly zero
+    __shared__ unsigned long long s_tz[2];       // hash marks of those units, by the sign of v (unique-table key, epilogue)
     __shared__ int s_flag;
     __shared__ long long s_rowbase;
 
@@ -260,7 +257,11 @@ relax_kernel(RelaxParams p) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
                     sbm |= (mask_t)b << r;
                     if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
+                        #ifdef RELAX_LDCS
+                        const int g = p.H0i ? __ldcs(&p.H0i[(size_t)pi * p.ldh + u]) : (int)llrint(p.int_scale * __ldcs(&p.H0[(size_t)pi * p.ldh + u]));
+#else
                         const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
+#endif
                         h[r] = g - (int)b;
                     } else h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited
@@ -313,8 +314,7 @@ relax_kernel(RelaxParams p) {
         }
 
         int flips = 0, margin = 0, sweeps = 0, is_stable = 0, pool_fail = 0;
-        int zero_field = 0;   // the state after the LAST sweep has a unit whose (reference-order) field is exactly zero
-        uint64_t tz0 = 0, tz1 = 0;   // integer stream: hash marks of those units, by the sign of v (profile key below)
+        if (tid == 0) { s_zero_field = 0; s_tz[0] = s_tz[1] = 0ULL; }   // rare-path state lives in shared memory, not registers
         for (int sweep = 0; sweep < p.max_iter; sweep++) {
             const long long row = rowbase + sweep;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
@@ -509,14 +509,13 @@ relax_kernel(RelaxParams p) {
                     if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T) z++;
                 const int nz = (int)block_sum(z);
                 margin += nz;
-                zero_field = nz > 0;
+                if (tid == 0) s_zero_field = nz > 0;
                 if ((int)cnt <= p.max_unstable) { is_stable = 1; break; }
                 continue;
             }
             // units inside the margin: exact recomputation, in increasing unit index
             int last = -1;
-            zero_field = 0;
-            tz0 = tz1 = 0;
+            if (tid == 0) { s_zero_field = 0; s_tz[0] = s_tz[1] = 0ULL; }
             for (;;) {
                 uint32_t cmin = RELAX_NONE;
 #pragma unroll
@@ -532,10 +531,10 @@ relax_kernel(RelaxParams p) {
                 const double hx = exact_field(last);
                 margin++;
                 const uint32_t ob = (s_bits[last >> 5] >> (last & 31)) & 1u;
-                if (hx == 0.0) {   // unit energy -0.5*(+0*v): a zero whose sign follows v
-                    zero_field = 1;
-                    tz0 ^= mix64(((uint64_t)(last + 1) << 1 | ob) ^ 0xA24BAED4963EE407ULL);
-                    tz1 ^= mix64(((uint64_t)(last + 1) << 1 | ob) * 0x9FB21C651E98DF25ULL + 0x632BE59BD9B4E019ULL);
+                if (hx == 0.0 && tid == 0) {   // unit energy -0.5*(+0*v): a zero whose sign follows v
+                    s_zero_field = 1;
+                    s_tz[0] ^= mix64(((uint64_t)(last + 1) << 1 | ob) ^ 0xA24BAED4963EE407ULL);
+                    s_tz[1] ^= mix64(((uint64_t)(last + 1) << 1 | ob) * 0x9FB21C651E98DF25ULL + 0x632BE59BD9B4E019ULL);
                 }
                 const double vi = ob ? 1.0 : -1.0;
                 const double en = -0.5 * (hx * vi);
@@ -559,7 +558,7 @@ relax_kernel(RelaxParams p) {
             if (p.stable) p.stable[pi] = (uint8_t)is_stable;
             if (p.flips) p.flips[pi] = flips;
             if (p.margin_hits) p.margin_hits[pi] = margin;
-            if (p.zero_field) p.zero_field[pi] = (uint8_t)zero_field;
+            if (p.zero_field) p.zero_field[pi] = (uint8_t)s_zero_field;
             if (p.serial_stream) { s_probe = pi + 1; s_rowbase = rowbase + sweeps; }
         }
         // Manhattan distance with inversion to every target (DistanceMeasure.go:28-42):
@@ -586,29 +585,45 @@ relax_kernel(RelaxParams p) {
         if (p.hash) {
             uint64_t h0 = 0, h1 = 0;
             if (INTF || p.exact_arith || p.key_scale != 0.0) {
+                // 128 key bits: four multilinear hashes  sum_u value_u * c_j(u)  mod 2^32  with unit-dependent odd constants
+                // (a universal family: distinct profiles collide with probability ~2^-32 per hash), per thread; threads are
+                // combined by XOR.  No 64-bit arithmetic in this kernel's epilogue.
+                uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+                auto mix_in = [&](uint32_t uk, uint32_t v) {
+                    k0 += v * (uk | 1u);
+                    k1 += v * (__funnelshift_l(uk, uk, 11) * 0x85EBCA6Bu | 1u);
+                    k2 += v * ((uk ^ 0xC2B2AE35u) * 0x27D4EB2Fu | 1u);
+                    k3 += (v ^ (v >> 15)) * (__funnelshift_l(uk, uk, 19) * 0x165667B1u | 1u);
+                };
 #pragma unroll
                 for (int r = 0; r < UPT; r++) {
                     const int u = unit_of_r(r);
                     if (u < N) {
                         const uint32_t b = (uint32_t)((sbm >> r) & 1u);
-                        uint64_t val;
+                        const uint32_t uk = (uint32_t)(u + 1) * 0x9E3779B1u;
                         if constexpr (INTF) {
-                            val = (uint64_t)(uint32_t)(b ? (int)h[r] + 1 : -(int)h[r]);   // v*g from u = g - b
+                            mix_in(uk, (uint32_t)(b ? (int)h[r] + 1 : -(int)h[r]));   // v*g from u = g - b
                         } else if (p.exact_arith) {
                             const double hv = (double)h[r];
-                            val = (uint64_t)__double_as_longlong((hv == 0.0 ? 0.0 : hv) * (b ? 1.0 : -1.0));   // h*v, the bits behind e
+                            const long long t = __double_as_longlong((hv == 0.0 ? 0.0 : hv) * (b ? 1.0 : -1.0));   // h*v, the bits behind e
+                            mix_in(uk, (uint32_t)t);
+                            mix_in(uk ^ 0x5BD1E995u, (uint32_t)(t >> 32));
                         } else {
                             const long long g = __double2ll_rn((double)h[r] * p.key_scale);   // exact: |error| << 1/2
-                            val = (uint64_t)(uint32_t)(int)(b ? g : -g);
+                            mix_in(uk, (uint32_t)(int)(b ? g : -g));
                         }
-                        const uint64_t y = mix64((uint64_t)(u + 1) * 0x9E3779B97F4A7C15ULL);
-                        h0 ^= mix64(val ^ y);
-                        h1 ^= mix64((val + 0x2545F4914F6CDD1DULL) * 0xD6E8FEB86659FD93ULL ^ (y >> 7));
                     }
                 }
-                if (!p.exact_arith && tid == 0) { h0 ^= tz0; h1 ^= tz1; }   // units whose re-evaluated float field is +0
+                // final avalanche per thread so that the XOR across threads does not cancel structure
+                k0 ^= k0 >> 16; k0 *= 0x7FEB352Du; k0 ^= k0 >> 15;
+                k1 ^= k1 >> 15; k1 *= 0x846CA68Bu; k1 ^= k1 >> 16;
+                k2 ^= k2 >> 17; k2 *= 0xC2B2AE35u; k2 ^= k2 >> 13;
+                k3 ^= k3 >> 14; k3 *= 0x85EBCA6Bu; k3 ^= k3 >> 16;
+                h0 = ((uint64_t)k1 << 32) | k0;
+                h1 = ((uint64_t)k3 << 32) | k2;
+                if (!p.exact_arith && tid == 0) { h0 ^= s_tz[0]; h1 ^= s_tz[1]; }   // units whose re-evaluated float field is +0
             } else {
-            const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !zero_field;
+            const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !s_zero_field;
             for (int w = tid; w < nbw; w += RELAX_THREADS) {
                 uint32_t x = s_bits[w];
                 if (inv) {

@@ -89,3 +89,29 @@ def test_i16_stream_thread_geometries(built, n, p, b):
     assert_relax_equal(res, ores, n)
     assert np.array_equal(res.MarginHits, ores["margin_hits"])
     net.close()
+
+
+def test_i16_stream_with_entries_beyond_a_byte(built):
+    """Strongly correlated targets push |K| past 127: the two-plane (hi/lo byte) integer fields GEMM and int16 columns
+    with large entries; small-P cases elsewhere take the single-plane GEMM."""
+    n, p, b = 512, 300, 48
+    rng = orc.Rng(17)
+    base = rng.generate_states(0, n, 1)[0]
+    t = np.tile(base, (p, 1))
+    flip = rng.generate_states(0, n, p) > 0                 # each target = the base pattern with ~3 % of units inverted
+    mask = np.zeros_like(flip)
+    mask[:, : n // 16] = flip[:, : n // 16]
+    t = np.ascontiguousarray(np.where(mask, -t, t))
+    net = gpu_net(n, SetColumnStream=I16)
+    net.LearnStates(t.copy())
+    assert net.integer_stream_active()
+    w = net.GetMatrix()
+    assert np.abs(w).max() / np.abs(w[np.nonzero(w)]).min() > 127      # the integer image really needs more than a byte
+    onet = orc.Net(n, w=w)
+    onet.set_targets(t)
+    probes = rng.generate_states(0, n, b)
+    pool = rng.perm_pool(n, 100)
+    ores = onet.relax_batch(probes.copy(), pool, threads=8)
+    res = net.relax_batch(probes, pool, dedup=True)
+    assert_relax_equal(res, ores, n)
+    net.close()

@@ -1,8 +1,9 @@
 // igemm_s8.cuh — exact integer contraction for the integer column stream (HN_COLUMNS_I16):
 //   G[B x N] (int32) = S[B x N] (states as +-1 / 0-1 int8, expanded from packed bits) * K[N x N]^T (int16)
-// i.e. the initial aligned-field numerators g = scale * Wraw * s of a probe batch, on the integer tensor-core path
+// i.e. the initial exact integer fields g = scale * Wraw * s of a probe batch, on the integer tensor-core path
 // (mma.sync.m16n8k32.s8: SASS IMMA).  K is split into a signed high byte plane and an unsigned low byte plane,
-// K = 256*Khi + Klo, so two s8 x {s8,u8} MMAs per tile give the exact int32 result: G = 256*(S Khi^T) + S Klo^T.
+// K = 256*Khi + Klo, so two s8 x {s8,u8} MMAs per tile give the exact int32 result: G = 256*(S Khi^T) + S Klo^T;
+// while every |K| <= 127 the low byte IS the entry as a signed byte and one s8 x s8 MMA does (SINGLE).
 // Replaces the float64 fields GEMM (gemm_f64.cuh) when the integer structure of W is known and W is symmetric
 // (K is stored column-major == row-major then); everything is exact, there is no rounding anywhere.
 #pragma once

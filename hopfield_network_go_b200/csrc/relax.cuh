@@ -257,11 +257,7 @@ relax_kernel(RelaxParams p) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
                     sbm |= (mask_t)b << r;
                     if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
-                        #ifdef RELAX_LDCS
-                        const int g = p.H0i ? __ldcs(&p.H0i[(size_t)pi * p.ldh + u]) : (int)llrint(p.int_scale * __ldcs(&p.H0[(size_t)pi * p.ldh + u]));
-#else
-                        const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
-#endif
+                                                const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
                         h[r] = g - (int)b;
                     } else h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited

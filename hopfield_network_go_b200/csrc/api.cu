@@ -100,7 +100,7 @@ struct hn_handle_s {
     double* dW = nullptr;
     float* W32 = nullptr;       // float32 shadow of the column matrix (HN_COLUMNS_F32)
     double* Wraw = nullptr;     // un-normalised W captured at normalisation (HN_COLUMNS_I16): W = c * Wraw
-    int16_t* K16 = nullptr;     // int16 image of int_scale*Wraw, column matrix layout
+    int16_t* K16 = nullptr;     // int16 image M = 2*int_scale*Wraw (+ self-correction on the diagonal, to_i16_kernel), column matrix layout
     bool int_ok = false;        // the integer structure of the CURRENT W is known and fits int16
     double int_maxabs = 0.0;    // max |K16 entry|
     double key_scale = 0.0;     // int_ok: (K s)_i = rint(key_scale * (W s)_i): exact energy-profile key on the float streams
@@ -236,7 +236,8 @@ int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W =
     int32_t f = 1; double m = 0;
     for (double scale : {0.5, 1.0, 2.0, 4.0}) {
         HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
-        to_i16_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(src, h->K16, total, scale, flag);
+        to_i16_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(src, h->K16, total, h->ldw, scale,
+                                                                       h->cfg.domain == HN_DOMAIN_BINARY ? -2 : -1, flag);
         HN_CUDA_TRY(cudaGetLastError());
         HN_CUDA_TRY(cudaMemcpyAsync(&f, flag, 4, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaMemcpyAsync(&m, mx, 8, cudaMemcpyDeviceToHost, h->st));
@@ -247,7 +248,7 @@ int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W =
     // fresh-dot rounding error << c  <=>  N^2 * max|2 Wraw| * 2^-50 < 0.5   (same precondition as oracle_fast.c)
     const bool exact = (double)h->N * (double)h->N * (h->int_scale * m) * 8.881784197001252e-16 < 0.5;
     h->int_ok = (f == 0) && exact && m > 0.0;
-    h->int_maxabs = h->int_scale * m;
+    h->int_maxabs = 2.0 * h->int_scale * m + 2.0;   // bound on |M| = |2K + diagonal term|
     h->key_scale = (h->int_ok && c > 0.0) ? h->int_scale / c : 0.0;   // K s = key_scale * (W s), to the nearest integer
     return HN_OK;
 }

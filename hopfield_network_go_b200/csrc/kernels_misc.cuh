@@ -175,13 +175,19 @@ thermal_factor_kernel(const double* __restrict__ H, int ldh, int n, const double
     if (threadIdx.x == 0) f[s] = exp(-1.0 * (1.0 / (1.0 + nrm[0])) * sqrt(r) / 1.0);
 }
 
-// int16 image of scale*Wraw (exact integer stream); flag <- 1 if some scale*w is not an integer within int16
-__global__ void to_i16_kernel(const double* __restrict__ w, int16_t* __restrict__ k16, int64_t total, double scale, int32_t* flag) {
+// int16 image M of the weights for the exact integer stream: M = 2*K with K = scale*Wraw integer valued, and
+// M_kk = 2*K_kk + diag (diag = -2/delta: -1 bipolar, -2 binary) so that a flip of unit k moves its own tracked field
+// U_k = 2 g_k - 2 b_k by exactly Delta_s*M_kk = 2 Delta_s K_kk - 2 Delta_b: the column update needs no owner fix-up.
+// flag <- 1 if some scale*w is not an integer or M leaves int16.  Row-major [n][ld] in both layouts (diagonal = [k][k]).
+__global__ void to_i16_kernel(const double* __restrict__ w, int16_t* __restrict__ k16, int64_t total, int ld, double scale,
+                              int diag, int32_t* flag) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const double x = scale * w[i];
         const double r = rint(x);
-        if (r != x || fabs(r) > 32767.0) *flag = 1;
-        k16[i] = (int16_t)(long long)r;
+        double m = 2.0 * r;
+        if (i / ld == i % ld) m += (double)diag;
+        if (r != x || fabs(m) > 32767.0) *flag = 1;
+        k16[i] = (int16_t)(long long)m;
     }
 }
 

@@ -240,12 +240,13 @@ relax_kernel(RelaxParams p) {
         for (int w = tid; w < nbw; w += RELAX_THREADS) s_bits[w] = pw32[w];
         __syncthreads();
         T = thr(0);
-        FT h[UPT];         // float64: local fields h of my units.  Integer stream: u = g - b with the EXACT field
-                           // g = scale*Wraw*s and b the unit's current bit: the unit wants to flip or sits on an exact tie
-                           // (v*g <= 0) exactly when  b = 1: g <= 0 <=> u < 0;   b = 0: g >= 0 <=> u >= 0,
-                           // so the candidacy mask is signmask(u) ^ ~bits: one funnel shift per unit and ONE xor per flip.
-                           // A flip adds the same multiple (+-delta) of the column to every field: no per-unit sign
-                           // registers; the flipped unit's owner only moves its own u by -+1 (its bit changed).
+        FT h[UPT];         // float64: local fields h of my units.  Integer stream: U = 2g - 2b with the EXACT field
+                           // g = K s (K = scale*Wraw) and b the unit's current bit: the unit wants to flip or sits on an
+                           // exact tie (v*g <= 0) exactly when  b = 1: g <= 0 <=> U < 0;   b = 0: g >= 0 <=> U >= 0,
+                           // so the candidacy mask is signmask(U) ^ ~bits: one funnel shift per unit and ONE xor per flip.
+                           // A flip adds the same multiple (+-delta) of the column of M = 2K to every field — including the
+                           // flipped unit's own, whose -+2 (its bit changed) sits on M's diagonal (to_i16_kernel): no
+                           // per-unit sign registers and no owner fix-up of a register chosen at run time.
         mask_t sbm = 0;    // my units' current bits; SIGNW(r) = 0x80000000 when the bit is clear (v = -1): hi32(h)^SIGNW = hi32(h*v)
 #define SIGNW(r) ((int)((uint32_t)((~sbm >> (r)) & 1u) << 31))
 #pragma unroll
@@ -257,12 +258,14 @@ relax_kernel(RelaxParams p) {
                     const uint32_t b = (s_bits[u >> 5] >> (u & 31)) & 1u;
                     sbm |= (mask_t)b << r;
                     if constexpr (INTF) {   // H0 = S * Wraw^T is exact in float64
-                                                const int g = p.H0i ? p.H0i[(size_t)pi * p.ldh + u] : (int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]);
-                        h[r] = g - (int)b;
+                                                // integer GEMM: (M s)_u = 2 g_u + diag * s_u, i.e. U_u up to -1 (bipolar) / 0 (binary);  float64 GEMM
+                        // (asymmetric weights): K s = int_scale * H0 exactly
+                        if (p.H0i) h[r] = p.H0i[(size_t)pi * p.ldh + u] - (p.domain == HN_DOMAIN_BINARY ? 0 : 1);
+                        else h[r] = 2 * ((int)llrint(p.int_scale * p.H0[(size_t)pi * p.ldh + u]) - (int)b);
                     } else h[r] = p.H0[(size_t)pi * p.ldh + u];
                 } else {  // padding: never a candidate, never visited
                     sbm |= (mask_t)1 << r;
-                    if constexpr (INTF) h[r] = 0x3FFFFFFF; else h[r] = __longlong_as_double(0x7FF0000000000000LL);   // (bit 1, u >= 0; its column entries are 0)
+                    if constexpr (INTF) h[r] = 0x3FFFFFFE; else h[r] = __longlong_as_double(0x7FF0000000000000LL);   // (bit 1, U >= 0; its column entries are 0)
                 }
             }
         }
@@ -291,15 +294,9 @@ relax_kernel(RelaxParams p) {
             }
             return m;
         };
-        // owner of a flipping unit: new bit into its bit mask and the packed state; integer stream: u = g - b moves by
-        // -+1 with its bit (commutes with the column update of the same flip).
+        // owner of a flipping unit: new bit into its bit mask and the packed state (integer stream: its own field moves
+        // through the diagonal of M with everyone else's)
         auto owner_flip = [&](int rr, int k) {
-            if constexpr (INTF) {
-                const int step = ((sbm >> rr) & 1u) ? 1 : -1;   // bit 1 -> 0: u = g - 0;  bit 0 -> 1: u = g - 1
-#pragma unroll
-                for (int r = 0; r < UPT; r++)
-                    if (r == rr) h[r] += step;
-            }
             sbm ^= (mask_t)1 << rr;
             s_bits[k >> 5] ^= 1u << (k & 31);
         };
@@ -361,7 +358,7 @@ relax_kernel(RelaxParams p) {
                     for (int r = 0; r < UPT; r++) { if constexpr (INTF) hw[r] = h[r]; else hw[r] = __double2hiint(h[r]); }
                     const int a = tree_select(hw, rr);
                     const uint32_t obit = (s_bits[k >> 5] >> (k & 31)) & 1u;
-                    const bool inside = INTF ? (a + (int)obit == 0) : ((a & 0x7FFFFFFF) < T);   // integer stream: g == 0
+                    const bool inside = INTF ? (a + 2 * (int)obit == 0) : ((a & 0x7FFFFFFF) < T);   // integer stream: g == 0
                     s_flag = (inside ? 2 : 0) | (int)obit;
                 }
                 __syncthreads();
@@ -491,7 +488,7 @@ relax_kernel(RelaxParams p) {
 #pragma unroll
             for (int r = 0; r < UPT; r++) {
                 if constexpr (INTF) {
-                    if (((sbm >> r) & 1u) ? (h[r] < -1) : (h[r] > 0)) cnt++;   // v*g < 0: certainly unstable
+                    if (((sbm >> r) & 1u) ? (h[r] < -2) : (h[r] > 0)) cnt++;   // v*g < 0: certainly unstable
                 } else {
                     const int a = __double2hiint(h[r]) ^ SIGNW(r);
                     if (a < 0 && !((a & 0x7FFFFFFF) < T)) cnt++;
@@ -518,7 +515,7 @@ relax_kernel(RelaxParams p) {
                 for (int r = 0; r < UPT; r++) {
                     const int u = unit_of_r(r);
                     bool inside;
-                    if constexpr (INTF) inside = h[r] + (int)((sbm >> r) & 1u) == 0; else inside = (__double2hiint(h[r]) & 0x7FFFFFFF) < T;
+                    if constexpr (INTF) inside = h[r] + 2 * (int)((sbm >> r) & 1u) == 0; else inside = (__double2hiint(h[r]) & 0x7FFFFFFF) < T;
                     if (inside && u > last) cmin = min(cmin, (uint32_t)u);
                 }
                 cmin = block_min(cmin);
@@ -598,7 +595,7 @@ relax_kernel(RelaxParams p) {
                         const uint32_t b = (uint32_t)((sbm >> r) & 1u);
                         const uint32_t uk = (uint32_t)(u + 1) * 0x9E3779B1u;
                         if constexpr (INTF) {
-                            mix_in(uk, (uint32_t)(b ? (int)h[r] + 1 : -(int)h[r]));   // v*g from u = g - b
+                            mix_in(uk, (uint32_t)(b ? ((int)h[r] >> 1) + 1 : -((int)h[r] >> 1)));   // v*g from U = 2g - 2b (even)
                         } else if (p.exact_arith) {
                             const double hv = (double)h[r];
                             const long long t = __double_as_longlong((hv == 0.0 ? 0.0 : hv) * (b ? 1.0 : -1.0));   // h*v, the bits behind e

@@ -398,6 +398,26 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
 
     HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
+    const bool zero_matrix = h->maxabs == 0.0 && h->cfg.max_relax_iterations >= 1;   // closed form, zero_matrix_relax_kernel
+    if (zero_matrix && (serial ? n_pool < B : n_pool < 1)) {
+        set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, serial ? B : 1);
+        return HN_E_POOL;
+    }
+    RelaxParams p{};
+    bool profile_keyed = false;
+    if (zero_matrix) {
+        HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
+        const int wpb = 8;
+        zero_matrix_relax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, h->st>>>(
+            d_probes, B, words, N, h->cfg.domain, h->cfg.max_relax_iterations, h->finals.as<uint64_t>(), h->steps.as<int32_t>(),
+            h->stable.as<uint8_t>(), h->flips.as<int32_t>(), h->margin.as<int32_t>(),
+            (want_dist && h->P > 0) ? h->dist.as<int32_t>() : nullptr, h->targets.as<uint64_t>(), h->P,
+            dedup ? h->hash.as<uint64_t>() : nullptr, dedup ? h->zf.as<uint8_t>() : nullptr, hist ? h->history.as<uint64_t>() : nullptr);
+        HN_CUDA_TRY(cudaGetLastError());
+        launches++;
+        profile_keyed = true;   // the constant key IS the key
+        HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
+    } else {
     // initial fields: S * W^T (FP64 tensor pipe); exact integer stream: G = S * K^T on the integer tensor pipe when W is
     // symmetric (K's rows are its columns), else S * Wraw^T in float64 (half/quarter-integers: exact)
     const bool int_fields = integer_stream(h) && h->w_symmetric;
@@ -409,7 +429,6 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     launches++;
     HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
 
-    RelaxParams p{};
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wrow = h->W;
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
@@ -429,8 +448,9 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     p.work_counter = &sc->work_counter; p.status = sc->status;
     HN_TRY(launch_relax(h, p));
     launches++;
-    const bool profile_keyed = p.exact_arith || integer_stream(h) || p.key_scale != 0.0;   // see the epilogue of relax_kernel
+    profile_keyed = p.exact_arith || integer_stream(h) || p.key_scale != 0.0;   // see the epilogue of relax_kernel
     HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
+    }
 
     if (want_energies) {
         // EnergyProfile of the final states (main.go:234): fresh fields by GEMM + epilogue

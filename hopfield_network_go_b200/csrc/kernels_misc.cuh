@@ -424,4 +424,41 @@ __global__ void generate_states_kernel(uint64_t state_lo, uint64_t state_hi, con
     }
 }
 
+
+// Relaxation on the all-zero matrix in closed form (a network that has learned nothing): every field is an exact zero,
+// so the first sweep sets every unit to the low value (h <= 0, BipolarDomainManager.go:10-22), no unit energy is
+// positive and the state is stable after that sweep: NumSteps = 2, flips = units that were high, and every probe ends
+// in the one all-low attractor.  One warp per probe.
+__global__ void zero_matrix_relax_kernel(const uint64_t* __restrict__ probes, int B, int words, int n, int domain, int max_iter,
+                                         uint64_t* __restrict__ finals, int32_t* __restrict__ steps, uint8_t* __restrict__ stable,
+                                         int32_t* __restrict__ flips, int32_t* __restrict__ margin, int32_t* __restrict__ dist,
+                                         const uint64_t* __restrict__ targets, int P, uint64_t* __restrict__ hash,
+                                         uint8_t* __restrict__ zero_field, uint64_t* __restrict__ history) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= B) return;
+    int f = 0;
+    for (int w = lane; w < words; w += 32) {
+        const uint64_t s = probes[(size_t)p * words + w];
+        f += __popcll(s);
+        finals[(size_t)p * words + w] = 0ULL;
+        if (history) {
+            history[((size_t)p * (max_iter + 1)) * words + w] = s;
+            history[((size_t)p * (max_iter + 1) + 1) * words + w] = 0ULL;
+        }
+    }
+    f = __reduce_add_sync(0xFFFFFFFFu, f);
+    if (dist)
+        for (int t = 0; t < P; t++) {
+            int dh = 0;
+            for (int w = lane; w < words; w += 32) dh += __popcll(targets[(size_t)t * words + w]);
+            dh = __reduce_add_sync(0xFFFFFFFFu, dh);
+            if (lane == 0) { const int m = min(dh, n - dh); dist[(size_t)p * P + t] = domain == HN_DOMAIN_BINARY ? m : 2 * m; }
+        }
+    if (lane == 0) {
+        steps[p] = 2; stable[p] = 1; flips[p] = f; margin[p] = 0;
+        if (hash) { hash[(size_t)p * 2] = 0x5A45524F4D415452ULL; hash[(size_t)p * 2 + 1] = 0x4958414C4C4C4F57ULL; }   // one attractor
+        if (zero_field) zero_field[p] = 1;
+    }
+}
+
 }  // namespace hn

@@ -95,3 +95,32 @@ def test_probes_that_are_attractors_already(built):
     assert res.UniqueHits.tolist() == [2] * p                        # s and -s are one attractor (same energy profile)
     assert (res.DistancesToTargets.min(axis=1) == 0).all()
     net.close()
+
+
+@pytest.mark.parametrize("domain", [0, 1])
+def test_relaxation_on_the_all_zero_matrix(built, domain):
+    """A network that has learned nothing: every field is an exact zero, one sweep sends every unit to the low value
+    and the state is stable (closed form in the library, zero_matrix_relax_kernel); serial stream and history too."""
+    n, b = 70, 12
+    rng = orc.Rng(3)
+    t = rng.generate_states(domain, n, 3)
+    onet = orc.Net(n, domain=domain)
+    onet.set_targets(t)
+    probes = rng.generate_states(domain, n, b)
+    pool = rng.perm_pool(n, 100)
+    ores = onet.relax_batch(probes.copy(), pool, want_energies=True)
+    net = gpu_net(n, domain)
+    net.SetLearnedStates(orc.pack(t))
+    for kw in ({}, {"serial_stream": True}):
+        res = net.relax_batch(probes, pool, dedup=True, want_energies=True, history=True, **kw)
+        assert_relax_equal(res, ores, n)
+        assert np.array_equal(res.MarginHits, ores["margin_hits"])
+        assert not res.FinalStates.any() and (res.NumSteps == 2).all() and res.Stable.all()
+        assert np.allclose(res.EnergyProfiles, ores["energies"], atol=0)
+        _, first, hits = orc.unique_table(ores["energies"])
+        assert np.array_equal(res.UniqueFirst, first) and np.array_equal(res.UniqueHits, hits)
+        assert np.array_equal(res.History[:, 0], orc.pack(probes)) and not res.History[:, 1].any()
+    with pytest.raises(capi.HopfieldError) as ei:
+        net.relax_batch(probes, pool[:5], serial_stream=True)          # the serial stream needs one row per probe
+    assert ei.value.code == capi.HN_E_POOL
+    net.close()

@@ -85,10 +85,12 @@ struct Scratch {
     int32_t asym_flag;                 // detect_symmetry
     int32_t int_flag;                  // build_integer_structure: scale*Wraw not an int16 integer somewhere
     int32_t not_quarters;              // ensure_margin: some W_ij is not a multiple of 0.25
-    int32_t pad;
+    int32_t stable_flag;               // learning: all-stable flag of this rank (all-reduced with min)
     unsigned long long rowabs_bits;    // ensure_margin: max_i sum_k |W_ik| (double bits)
     unsigned long long maxabs_bits;    // ensure_margin: max |W_ij|
     unsigned long long maxabs_raw_bits;  // build_integer_structure: max |Wraw_ij|
+    int32_t pair_count[2];             // dedup level 2: [0] merges of different states recorded, [1] refuted by the float profiles
+    unsigned long long totals[3];      // relax: sum of flips, sweeps, margin hits over the batch (sum_counters_kernel)
 };
 
 struct hn_handle_s {
@@ -117,12 +119,14 @@ struct hn_handle_s {
     DevBuf jump;   // LCG jump table of hn_generate_probes
     DevBuf zf;     // per probe: final state has an exactly-zero field (unique-table key)
     DevBuf probes, pool, offsets, H, finals, steps, stable, flips, margin, dist, hash, energies, history;
-    DevBuf rep, first, hits, flag, rank, table, attractor, ufirst, uhits, small, partial;
+    DevBuf rep, rep1, rep2, pairs, first, hits, flag, rank, table, attractor, ufirst, uhits, small, partial;
+    int64_t verified_pairs = 0, refuted_pairs = 0;   // unique table, level 2: merges of different states checked / refuted
     DevBuf bitsA, bitsB, bitsC, bitsAT, bitsCT, perms, eunst, estab, esum, emargin;
     uint16_t* d_pool = nullptr;
     uint16_t* d_inv = nullptr;
     int resident_B = 0, resident_pool = 0, result_B = 0, result_P = 0, result_unique = 0;
     uint32_t result_flags = 0;
+    bool result_profile_keyed = false;
     cudaEvent_t ev[6] = {};
     hn_relax_timing timing = {};
     int64_t tot_flips = 0, tot_sweeps = 0, tot_margin = 0;
@@ -253,6 +257,37 @@ int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W =
     return HN_OK;
 }
 
+// Caller-supplied weights (hn_set_weights, hn_broadcast_weights): try to RECOVER the integer structure the library would
+// have captured had it learned them.  A Hebbian / Delta matrix after Scale(1/norm) is W = fl(c*K), K integer; the
+// smallest non-zero |W| is then fl(c*k) for a small k.  For k = 1..8: c = w_min/k, K = rint(W/c), accepted iff
+// fl(c*K_ij) == W_ij bit for bit everywhere (plus the int16 / exactness checks of build_integer_structure).  A random
+// initial matrix, thermal weights or anything else fails the bit test and keeps the float64 stream.
+int detect_integer_structure(hn_handle h) {
+    const int64_t total = (int64_t)h->N * h->ldw;
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    Scratch* sc = h->scratch();
+    const unsigned long long inf_bits = 0x7FF0000000000000ULL;
+    HN_CUDA_TRY(cudaMemcpyAsync(&sc->maxabs_raw_bits, &inf_bits, 8, cudaMemcpyHostToDevice, h->st));
+    min_nonzero_abs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->W, total, &sc->maxabs_raw_bits);
+    HN_CUDA_TRY(cudaGetLastError());
+    double wmin = 0.0;
+    HN_CUDA_TRY(cudaMemcpyAsync(&wmin, &sc->maxabs_raw_bits, 8, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (!(wmin > 0.0) || !std::isfinite(wmin)) return HN_OK;   // the zero matrix: nothing to stream
+    if (!h->Wraw) HN_CUDA_TRY(cudaMalloc(&h->Wraw, sizeof(double) * (size_t)total));
+    for (int k = 1; k <= 8; k++) {
+        const double c = wmin / (double)k;
+        int32_t f = 1;
+        HN_CUDA_TRY(cudaMemsetAsync(&sc->int_flag, 0, 4, h->st));
+        recover_integer_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(h->W, h->Wraw, total, c, &sc->int_flag);
+        HN_CUDA_TRY(cudaGetLastError());
+        HN_CUDA_TRY(cudaMemcpyAsync(&f, &sc->int_flag, 4, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (f == 0) return build_integer_structure(h, h->w_symmetric, c);   // Wraw = K, W = fl(c*K)
+    }
+    return HN_OK;
+}
+
 // float32 shadow of the column matrix (W if symmetric else W^T), rebuilt after any weight change
 int ensure_w32(hn_handle h) {
     if (h->w32_valid) return HN_OK;
@@ -373,6 +408,76 @@ int validate_pool_host(hn_handle h, const uint16_t* pool, int rows) {
     return HN_OK;
 }
 
+// Unique-attractor table over `count` final states on the device (datacollector/UniqueRelaxedStateHandler.go:41-73).
+// Level 1 groups equal sign-canonical states (exact); where the exact-profile key exists, level 2 groups the level-1
+// representatives by that key and every such merge is verified on the float energy profiles in the reference's
+// summation order; a refuted merge salts the key and the level is redone (never seen: it takes a 128-bit collision or
+// integer profiles that coincide where the rounded float profiles do not).  weight == nullptr: every state counts once;
+// else state j stands for weight[j] probes (merge of per-GPU tables).  Results: h->attractor, h->ufirst, h->uhits
+// (first-seen order = ascending position) and Scratch::unique_total.
+int run_dedup(hn_handle h, const uint64_t* finals, uint64_t* keys, const uint8_t* zf, int count, bool profile_keyed,
+              const int32_t* weight, int* launches) {
+    const int words = h->words, N = h->N;
+    Scratch* sc = h->scratch();
+    int cap = 1024;
+    while (cap < 2 * count) cap <<= 1;
+    HN_TRY(h->table.reserve(sizeof(int32_t) * (size_t)cap));
+    HN_TRY(h->rep.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->rep1.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->first.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->hits.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->flag.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->rank.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->attractor.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->ufirst.reserve(sizeof(int32_t) * (size_t)count));
+    HN_TRY(h->uhits.reserve(sizeof(int32_t) * (size_t)count));
+    const int tb = 256, gb = (count + tb - 1) / tb;
+    HN_CUDA_TRY(cudaMemsetAsync(h->table.p, 0xFF, sizeof(int32_t) * (size_t)cap, h->st));
+    dedup_insert_kernel<<<gb, tb, 0, h->st>>>(finals, keys, count, words, N, h->cfg.domain, h->table.as<int32_t>(), cap - 1,
+                                             h->rep1.as<int32_t>(), zf);
+    HN_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    const int32_t* rep2 = nullptr;
+    if (profile_keyed) {
+        HN_TRY(h->rep2.reserve(sizeof(int32_t) * (size_t)count));
+        HN_TRY(h->pairs.reserve(sizeof(int2) * (size_t)count));
+        for (int round = 0;; round++) {
+            if (round == 8) { set_error("unique table: profile keys still collide after 8 salted passes"); return HN_E_STATE; }
+            HN_CUDA_TRY(cudaMemsetAsync(h->table.p, 0xFF, sizeof(int32_t) * (size_t)cap, h->st));
+            HN_CUDA_TRY(cudaMemsetAsync(sc->pair_count, 0, sizeof(sc->pair_count), h->st));
+            dedup_insert_profile_kernel<<<gb, tb, 0, h->st>>>(keys, h->rep1.as<int32_t>(), count, h->table.as<int32_t>(), cap - 1,
+                                                             h->rep2.as<int32_t>(), h->pairs.as<int2>(), &sc->pair_count[0]);
+            HN_CUDA_TRY(cudaGetLastError());
+            if (launches) ++*launches;
+            int32_t pc[2] = {0, 0};
+            HN_CUDA_TRY(cudaMemcpyAsync(pc, sc->pair_count, sizeof(pc), cudaMemcpyDeviceToHost, h->st));
+            HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+            if (pc[0] == 0) break;   // the usual case: no two different states share a profile key
+            dedup_verify_kernel<<<pc[0], 256, 0, h->st>>>(h->pairs.as<int2>(), finals, words, h->W, h->ldw, N, h->cfg.domain, keys,
+                                                         0xC0FFEE0000ULL + (uint64_t)round, &sc->pair_count[1]);
+            HN_CUDA_TRY(cudaGetLastError());
+            if (launches) ++*launches;
+            HN_CUDA_TRY(cudaMemcpyAsync(pc, sc->pair_count, sizeof(pc), cudaMemcpyDeviceToHost, h->st));
+            HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+            h->verified_pairs += pc[0]; h->refuted_pairs += pc[1];
+            if (pc[1] == 0) break;   // every merge of different states confirmed on the float profiles
+        }
+        rep2 = h->rep2.as<int32_t>();
+    }
+    HN_CUDA_TRY(cudaMemsetAsync(h->first.p, 0x7F, sizeof(int32_t) * (size_t)count, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(h->hits.p, 0, sizeof(int32_t) * (size_t)count, h->st));
+    dedup_compose_kernel<<<gb, tb, 0, h->st>>>(h->rep1.as<int32_t>(), rep2, count, h->rep.as<int32_t>());
+    dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), count, h->first.as<int32_t>(), h->hits.as<int32_t>(), weight);
+    dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), count, h->flag.as<int32_t>());
+    scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), count, h->rank.as<int32_t>(), &sc->unique_total);
+    dedup_finalize_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), h->hits.as<int32_t>(),
+                                               h->rank.as<int32_t>(), count, h->attractor.as<int32_t>(),
+                                               h->ufirst.as<int32_t>(), h->uhits.as<int32_t>());
+    HN_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 5;
+    return HN_OK;
+}
+
 // The whole relaxation of B probes already on the device.
 int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d_pool, const uint16_t* d_inv,
                  int n_pool, const int32_t* d_offsets, uint32_t flags, bool want_energies, bool want_dist) {
@@ -388,14 +493,14 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     HN_TRY(h->margin.reserve(sizeof(int32_t) * (size_t)B));
     HN_TRY(h->small.reserve(sizeof(Scratch)));
     if (want_dist && h->P > 0) HN_TRY(h->dist.reserve(sizeof(int32_t) * (size_t)B * h->P));
-    if (dedup) HN_TRY(h->hash.reserve(sizeof(uint64_t) * 2 * (size_t)B));
+    if (dedup) HN_TRY(h->hash.reserve(sizeof(uint64_t) * 4 * (size_t)B));
     if (dedup) HN_TRY(h->zf.reserve((size_t)B));
     if (hist) HN_TRY(h->history.reserve(sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
 
     int launches = 0;
     Scratch* sc = h->scratch();
     HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));   // work counter, status, unique total
-    if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 2 * (size_t)B, h->st));
+    if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 4 * (size_t)B, h->st));
 
     HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
     const bool zero_matrix = h->maxabs == 0.0 && h->cfg.max_relax_iterations >= 1;   // closed form, zero_matrix_relax_kernel
@@ -415,7 +520,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
             dedup ? h->hash.as<uint64_t>() : nullptr, dedup ? h->zf.as<uint8_t>() : nullptr, hist ? h->history.as<uint64_t>() : nullptr);
         HN_CUDA_TRY(cudaGetLastError());
         launches++;
-        profile_keyed = true;   // the constant key IS the key
+        profile_keyed = false;  // every final state is the all-low state: one group at level 1
         HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
     } else {
     // initial fields: S * W^T (FP64 tensor pipe); exact integer stream: G = S * K^T on the integer tensor pipe when W is
@@ -465,42 +570,23 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     }
     h->result_unique = 0;
     if (dedup) {
-        int cap = 1024;
-        while (cap < 2 * B) cap <<= 1;
-        HN_TRY(h->table.reserve(sizeof(int32_t) * (size_t)cap));
-        HN_TRY(h->rep.reserve(sizeof(int32_t) * (size_t)B));
-        HN_TRY(h->first.reserve(sizeof(int32_t) * (size_t)B));
-        HN_TRY(h->hits.reserve(sizeof(int32_t) * (size_t)B));
-        HN_TRY(h->flag.reserve(sizeof(int32_t) * (size_t)B));
-        HN_TRY(h->rank.reserve(sizeof(int32_t) * (size_t)B));
-        HN_TRY(h->attractor.reserve(sizeof(int32_t) * (size_t)B));
-        HN_TRY(h->ufirst.reserve(sizeof(int32_t) * (size_t)B));
-        HN_TRY(h->uhits.reserve(sizeof(int32_t) * (size_t)B));
-        HN_CUDA_TRY(cudaMemsetAsync(h->table.p, 0xFF, sizeof(int32_t) * (size_t)cap, h->st));
-        HN_CUDA_TRY(cudaMemsetAsync(h->first.p, 0x7F, sizeof(int32_t) * (size_t)B, h->st));
-        HN_CUDA_TRY(cudaMemsetAsync(h->hits.p, 0, sizeof(int32_t) * (size_t)B, h->st));
-        const int tb = 256, gb = (B + tb - 1) / tb;
-        dedup_insert_kernel<<<gb, tb, 0, h->st>>>(h->finals.as<uint64_t>(), h->hash.as<uint64_t>(), B, words, N,
-                                                 h->cfg.domain, h->table.as<int32_t>(), cap - 1, h->rep.as<int32_t>(), h->zf.as<uint8_t>(),
-                                                 profile_keyed ? 1 : 0);
-        dedup_count_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), B, h->first.as<int32_t>(), h->hits.as<int32_t>());
-        dedup_flag_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), B, h->flag.as<int32_t>());
-        scan_flags_kernel<<<1, 1024, 0, h->st>>>(h->flag.as<int32_t>(), B, h->rank.as<int32_t>(), &sc->unique_total);
-        dedup_finalize_kernel<<<gb, tb, 0, h->st>>>(h->rep.as<int32_t>(), h->first.as<int32_t>(), h->hits.as<int32_t>(),
-                                                   h->rank.as<int32_t>(), B, h->attractor.as<int32_t>(),
-                                                   h->ufirst.as<int32_t>(), h->uhits.as<int32_t>());
-        HN_CUDA_TRY(cudaGetLastError());
-        launches += 5;
+        HN_TRY(run_dedup(h, h->finals.as<uint64_t>(), h->hash.as<uint64_t>(), h->zf.as<uint8_t>(), B, profile_keyed, nullptr, &launches));
     }
     HN_CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(sc->totals, 0, sizeof(sc->totals), h->st));
+    sum_counters_kernel<<<std::min((B + 255) / 256, h->sms * 4), 256, 0, h->st>>>(h->flips.as<int32_t>(), h->steps.as<int32_t>(),
+                                                                                h->margin.as<int32_t>(), B, sc->totals);
+    HN_CUDA_TRY(cudaGetLastError());
     Scratch host_sc;
-    HN_CUDA_TRY(cudaMemcpyAsync(&host_sc, sc, offsetof(Scratch, asym_flag), cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync(&host_sc, sc, sizeof(Scratch), cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    h->tot_flips = (int64_t)host_sc.totals[0]; h->tot_sweeps = (int64_t)host_sc.totals[1]; h->tot_margin = (int64_t)host_sc.totals[2];
     if (host_sc.status[0]) {
         set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, host_sc.status[1]);
         return HN_E_POOL;
     }
     h->result_unique = dedup ? host_sc.unique_total : 0;
+    h->result_profile_keyed = profile_keyed;
     float f = 0, r = 0, q = 0;
     cudaEventElapsedTime(&f, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&r, h->ev[1], h->ev[2]);
@@ -542,21 +628,16 @@ int download_results(hn_handle h, hn_relax_out* out) {
     }
     if (out->state_hash) {
         if (!(h->result_flags & HN_RELAX_DEDUP)) { set_error("state hashes were not computed (HN_RELAX_DEDUP)"); return HN_E_STATE; }
-        HN_TRY(d2h(out->state_hash, h->hash.p, sizeof(uint64_t) * 2 * (size_t)B));
+        // the two words the groups were finally formed on: the exact-profile key where it exists, else the state hash
+        const char* src = (const char*)h->hash.p + (h->result_profile_keyed ? 16 : 0);
+        HN_CUDA_TRY(cudaMemcpy2DAsync(out->state_hash, 16, src, 32, 16, (size_t)B, cudaMemcpyDeviceToHost, h->st));
     }
     if (out->history) {
         if (!(h->result_flags & HN_RELAX_HISTORY)) { set_error("history was not captured"); return HN_E_STATE; }
         HN_TRY(d2h(out->history, h->history.p, sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
     }
-    // totals (small device->host reductions done on the host copies of the counters)
-    std::vector<int32_t> fl((size_t)B), stp((size_t)B), mg((size_t)B);
-    HN_CUDA_TRY(cudaMemcpyAsync(fl.data(), h->flips.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->st));
-    HN_CUDA_TRY(cudaMemcpyAsync(stp.data(), h->steps.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->st));
-    HN_CUDA_TRY(cudaMemcpyAsync(mg.data(), h->margin.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
-    int64_t tf = 0, ts = 0, tm = 0;
-    for (int i = 0; i < B; i++) { tf += fl[i]; ts += stp[i] - 1; tm += mg[i]; }
-    out->total_flips = tf; out->total_sweeps = ts; out->total_margin_hits = tm;
+    out->total_flips = h->tot_flips; out->total_sweeps = h->tot_sweeps; out->total_margin_hits = h->tot_margin;   // summed on the device
     out->device_ms = h->timing.fields_ms + h->timing.relax_ms + h->timing.post_ms;
     return HN_OK;
 }
@@ -593,6 +674,31 @@ struct OpBitsDiffG {  // scale * kscale[k] * (val_a(bitA) - val_b(bitB)); kscale
 int all_reduce_dw(hn_handle h) {
     if (!h->comm) return HN_OK;
     HN_NCCL_TRY(g_nccl.AllReduce(h->dW, h->dW, (size_t)h->N * h->ldw, NCCL_FLOAT64, NCCL_SUM, h->comm, h->st));
+    return HN_OK;
+}
+
+// AllStatesAreStable across ranks (LearningMethod.go:56-58 with the targets sharded): minimum of the per-rank flags
+int all_reduce_min_flag(hn_handle h, bool* flag) {
+    if (!h->comm) return HN_OK;
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    int32_t* d = &h->scratch()->stable_flag;
+    int32_t v = *flag ? 1 : 0;
+    HN_CUDA_TRY(cudaMemcpyAsync(d, &v, 4, cudaMemcpyHostToDevice, h->st));
+    HN_NCCL_TRY(g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_MIN, h->comm, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync(&v, d, 4, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    *flag = v != 0;
+    return HN_OK;
+}
+
+int apply_update_and_constraints(hn_handle h);
+// a rank whose shard of this epoch's targets is empty still takes part in the all-reduce (with a zero dW) and applies
+// the same update, so replicas stay identical (iterative-batch prefixes can leave late ranks without targets)
+int empty_shard_epoch(hn_handle h) {
+    HN_CUDA_TRY(cudaMemsetAsync(h->dW, 0, sizeof(double) * (size_t)h->N * h->ldw, h->st));
+    HN_TRY(all_reduce_dw(h));
+    HN_TRY(apply_update_and_constraints(h));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     return HN_OK;
 }
 
@@ -833,7 +939,7 @@ int hn_destroy(hn_handle h) {
     if (h->st) cudaStreamSynchronize(h->st);
     DevBuf* bufs[] = {&h->targets, &h->probes, &h->pool, &h->offsets, &h->H, &h->finals, &h->steps, &h->stable,
                       &h->flips, &h->margin, &h->dist, &h->hash, &h->energies, &h->history, &h->rep, &h->first, &h->hits,
-                      &h->flag, &h->rank, &h->table, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
+                      &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
                       &h->bitsA, &h->bitsB, &h->bitsC, &h->bitsAT, &h->bitsCT, &h->perms, &h->eunst, &h->estab, &h->esum,
                       &h->emargin};
     for (DevBuf* b : bufs) b->release();
@@ -858,7 +964,7 @@ int hn_set_weights(hn_handle h, const double* w_host) {
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     HN_TRY(detect_symmetry(h));
     weights_changed(h);
-    return HN_OK;
+    return detect_integer_structure(h);
 }
 
 int hn_get_weights(hn_handle h, double* w_host) {
@@ -892,7 +998,11 @@ int hn_set_integer_structure(hn_handle h, const double* w_raw) {
     HN_CUDA_TRY(cudaMemcpy2DAsync(h->Wraw, sizeof(double) * h->ldw, w_raw, sizeof(double) * N, sizeof(double) * N, N,
                                   cudaMemcpyHostToDevice, h->st));
     HN_TRY(build_integer_structure(h, h->w_symmetric, c));
-    if (!h->int_ok) { set_error("hn_set_integer_structure: no multiple 0.5, 1, 2 or 4 of the matrix is integer valued within int16"); return HN_E_INVALID; }
+    if (!h->int_ok) {
+        HN_TRY(detect_integer_structure(h));   // a refused declaration leaves whatever the matrix itself reveals in force
+        set_error("hn_set_integer_structure: no multiple 0.5, 1, 2 or 4 of the matrix is integer valued within int16");
+        return HN_E_INVALID;
+    }
     return HN_OK;
 }
 int hn_integer_stream_active(hn_handle h, int32_t* active) {
@@ -1000,12 +1110,119 @@ int hn_energy_profiles(hn_handle h, const uint64_t* states_packed, int32_t n, do
     return energy_profiles_impl(h, h->bitsA.as<uint64_t>(), n, energies_out, unstable_out, stable_out, state_energy_out);
 }
 
-int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t rule, int32_t method,
-                    int32_t epochs, int32_t noise_method, double noise_scale, hn_rng rng, int32_t learn_cap,
-                    int32_t* learn_epoch_out, int32_t* learn_index_out, uint8_t* learn_stable_out,
-                    double* learn_energy_out, int32_t* n_learn_rows) {
-    if (!check_handle(h, "hn_learn_states")) return HN_E_INVALID;
-    if (n <= 0 || !states_packed) { set_error("hn_learn_states: bad argument"); return HN_E_INVALID; }
+int hn_unit_energy(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t unit_index, double* energy_out) {
+    if (!check_handle(h, "hn_unit_energy")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed || !energy_out || unit_index < 0 || unit_index >= h->N) {
+        set_error("hn_unit_energy: bad argument (unit index %d, dimension %d)", unit_index, h->N);
+        return HN_E_INVALID;
+    }
+    HN_TRY(set_device(h));
+    HN_TRY(upload_states(h, h->bitsA, states_packed, n));
+    HN_TRY(h->esum.reserve(sizeof(double) * (size_t)n));
+    unit_energy_kernel<<<(n + 63) / 64, 64, 0, h->st>>>(h->W, h->ldw, h->bitsA.as<uint64_t>(), h->words, h->N, n,
+                                                       h->cfg.domain, unit_index, h->esum.as<double>());
+    HN_CUDA_TRY(cudaGetLastError());
+    HN_CUDA_TRY(cudaMemcpyAsync(energy_out, h->esum.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+// LearnStates over targets [shard_begin, shard_end) of the n given ones (the whole list when no communicator is attached).
+// Every rank passes the SAME n states and an identically seeded rng: noise and update orders are drawn for all n targets
+// in the reference's order (LearningRule.go:98-104) so the stream equals the single-process one, and each rank keeps its
+// shard's.  dW is all-reduced inside the epoch (all_reduce_dw), the all-stable early exit (LearningMethod.go:56-58) is the
+// minimum over ranks, so every replica runs the same number of epochs and W stays bitwise identical.
+static int learn_states_impl(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t shard_begin, int32_t shard_end,
+                             int32_t rule, int32_t method, int32_t epochs, int32_t noise_method, double noise_scale,
+                             hn_rng rng, int32_t learn_cap, int32_t* learn_epoch_out, int32_t* learn_index_out,
+                             uint8_t* learn_stable_out, double* learn_energy_out, int32_t* n_learn_rows) {
+    const bool is_thermal = rule == HN_RULE_THERMAL_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA;
+    const bool is_delta = rule == HN_RULE_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_DELTA || is_thermal;
+    const int N = h->N, words = h->words;
+    HN_TRY(append_targets(h, states_packed, n));  // HopfieldNetwork.go:258 (every replica holds the whole list)
+    // value map the rule sees: bipolarMappedHebbian re-activates with the BINARY manager (sic,
+    // LearningRule.go:80); bipolarMappedDelta with the Bipolar manager (:119).
+    ValueMap tvm = domain_values(h->cfg.domain);
+    if (rule == HN_RULE_BIPOLAR_MAPPED_HEBBIAN) tvm = ValueMap{0.0, 1.0};
+    if (rule == HN_RULE_BIPOLAR_MAPPED_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA) tvm = ValueMap{-1.0, 1.0};
+    int produced = 0, last_epoch = 0;
+    std::vector<uint64_t> noised;
+    std::vector<uint16_t> perms;
+    std::vector<double> tmp((size_t)N);
+    std::vector<uint8_t> stab;
+    std::vector<double> en;
+
+    auto full_set = [&](int cnt, int epoch_offset) -> int {  // LearningMethod.go:38-61 over states[:cnt]
+        const int lo = std::min(shard_begin, cnt), hi = std::min(shard_end, cnt), mine = hi - lo;
+        const uint64_t* my_states = states_packed + (size_t)lo * words;
+        for (int epoch = 0; epoch < epochs; epoch++) {
+            if (!is_delta) {
+                if (mine > 0) HN_TRY(hebbian_epoch_impl(h, my_states, mine, tvm));
+                else HN_TRY(empty_shard_epoch(h));
+            } else {
+                noised.assign((size_t)std::max(mine, 1) * words, 0);
+                perms.resize((size_t)std::max(mine, 1) * N);
+                std::vector<uint16_t> scratch_perm((size_t)N);
+                for (int s = 0; s < cnt; s++) {  // LearningRule.go:98-104, draw order: noise then shuffle, ALL targets
+                    const bool keep = s >= lo && s < hi;
+                    const uint64_t* src = states_packed + (size_t)s * words;
+                    for (int i = 0; i < N; i++) tmp[i] = ((src[i >> 6] >> (i & 63)) & 1ULL) ? tvm.hi : tvm.lo;
+                    HN_TRY(hn_rng_apply_noise(rng, noise_method, noise_scale, tmp.data(), N));
+                    if (keep) {
+                        uint64_t* dst = noised.data() + (size_t)(s - lo) * words;
+                        for (int i = 0; i < N; i++) if (tmp[i] > 0.0) dst[i >> 6] |= 1ULL << (i & 63);  // network activation
+                    }
+                    uint16_t* pr = keep ? perms.data() + (size_t)(s - lo) * N : scratch_perm.data();
+                    for (int i = 0; i < N; i++) pr[i] = (uint16_t)i;
+                    HN_TRY(hn_rng_shuffle_u16(rng, pr, N));
+                }
+                if (mine > 0) HN_TRY(delta_epoch_impl(h, my_states, noised.data(), perms.data(), mine, nullptr, tvm, is_thermal));
+                else HN_TRY(empty_shard_epoch(h));
+            }
+            // per-target diagnostics (LearningMethod.go:45-53) on the ORIGINAL states in the network domain
+            bool all_stable = true;
+            if (mine > 0) {
+                stab.resize((size_t)mine);
+                const bool want_e = learn_energy_out != nullptr && produced < learn_cap;
+                if (want_e) en.resize((size_t)mine * N);
+                HN_TRY(upload_states(h, h->bitsA, my_states, mine));
+                HN_TRY(energy_profiles_impl(h, h->bitsA.as<uint64_t>(), mine, want_e ? en.data() : nullptr, nullptr, stab.data(), nullptr));
+                for (int s = 0; s < mine; s++) {
+                    if (!stab[s]) all_stable = false;
+                    if (produced < learn_cap) {
+                        if (learn_epoch_out) learn_epoch_out[produced] = epoch + epoch_offset;
+                        if (learn_index_out) learn_index_out[produced] = lo + s;
+                        if (learn_stable_out) learn_stable_out[produced] = stab[s];
+                        if (want_e) std::memcpy(learn_energy_out + (size_t)produced * N, en.data() + (size_t)s * N, sizeof(double) * N);
+                    }
+                    produced++;
+                }
+            }
+            last_epoch = epoch + epoch_offset;
+            HN_TRY(all_reduce_min_flag(h, &all_stable));   // AllStatesAreStable over EVERY rank's targets
+            if (all_stable) break;  // :56-58
+        }
+        return HN_OK;
+    };
+    if (method == HN_METHOD_FULL_SET) {
+        HN_TRY(full_set(n, 0));
+    } else {  // iterativeBatchLearningMethod, LearningMethod.go:70-89 (BATCHSIZE 5)
+        const int batches = n / 5;
+        int total = 0;
+        for (int it = 1; it <= batches; it++) {
+            HN_TRY(full_set(5 * it, total));
+            total = last_epoch;
+        }
+    }
+    HN_TRY(hn_normalize_frobenius(h, nullptr));  // HopfieldNetwork.go:260 (replicated: identical on every rank)
+    if (n_learn_rows) *n_learn_rows = produced;
+    return HN_OK;
+}
+
+static int learn_states_check(hn_handle h, const char* fn, const uint64_t* states_packed, int32_t n, int32_t rule,
+                              int32_t method, int32_t epochs, double noise_scale, hn_rng rng) {
+    if (!check_handle(h, fn)) return HN_E_INVALID;
+    if (n <= 0 || !states_packed) { set_error("%s: bad argument", fn); return HN_E_INVALID; }
     if (epochs <= 0) {  // HopfieldNetworkBuilder.go:219-221
         set_error("HopfieldNetworkBuilder encountered an error during build! Epochs must be a positive integer!");
         return HN_E_INVALID;
@@ -1018,80 +1235,41 @@ int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n, int32
         set_error("unknown learning rule %d / method %d", rule, method);
         return HN_E_INVALID;
     }
-    const bool is_thermal = rule == HN_RULE_THERMAL_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA;
-    const bool is_delta = rule == HN_RULE_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_DELTA || is_thermal;
-    if (is_delta && !rng) { set_error("hn_learn_states: the delta rule needs an rng"); return HN_E_INVALID; }
-    HN_TRY(set_device(h));
-    const int N = h->N, words = h->words;
-    HN_TRY(append_targets(h, states_packed, n));  // HopfieldNetwork.go:258
-    // value map the rule sees: bipolarMappedHebbian re-activates with the BINARY manager (sic,
-    // LearningRule.go:80); bipolarMappedDelta with the Bipolar manager (:119).
-    ValueMap tvm = domain_values(h->cfg.domain);
-    if (rule == HN_RULE_BIPOLAR_MAPPED_HEBBIAN) tvm = ValueMap{0.0, 1.0};
-    if (rule == HN_RULE_BIPOLAR_MAPPED_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA) tvm = ValueMap{-1.0, 1.0};
-    const ValueMap nvm = domain_values(h->cfg.domain);
-    int produced = 0, last_epoch = 0;
-    std::vector<uint64_t> noised;
-    std::vector<uint16_t> perms;
-    std::vector<double> tmp((size_t)N);
-    std::vector<uint8_t> stab;
-    std::vector<double> en;
-
-    auto full_set = [&](int cnt, int epoch_offset) -> int {  // LearningMethod.go:38-61
-        for (int epoch = 0; epoch < epochs; epoch++) {
-            if (!is_delta) {
-                HN_TRY(hebbian_epoch_impl(h, states_packed, cnt, tvm));
-            } else {
-                noised.assign((size_t)cnt * words, 0);
-                perms.resize((size_t)cnt * N);
-                for (int s = 0; s < cnt; s++) {  // LearningRule.go:98-104, draw order: noise then shuffle
-                    const uint64_t* src = states_packed + (size_t)s * words;
-                    for (int i = 0; i < N; i++) tmp[i] = ((src[i >> 6] >> (i & 63)) & 1ULL) ? tvm.hi : tvm.lo;
-                    HN_TRY(hn_rng_apply_noise(rng, noise_method, noise_scale, tmp.data(), N));
-                    uint64_t* dst = noised.data() + (size_t)s * words;
-                    for (int i = 0; i < N; i++) if (tmp[i] > 0.0) dst[i >> 6] |= 1ULL << (i & 63);  // network activation
-                    uint16_t* pr = perms.data() + (size_t)s * N;
-                    for (int i = 0; i < N; i++) pr[i] = (uint16_t)i;
-                    HN_TRY(hn_rng_shuffle_u16(rng, pr, N));
-                }
-                HN_TRY(delta_epoch_impl(h, states_packed, noised.data(), perms.data(), cnt, nullptr, tvm, is_thermal));
-            }
-            // per-target diagnostics (LearningMethod.go:45-53) on the ORIGINAL states in the network domain
-            stab.resize((size_t)cnt);
-            const bool want_e = learn_energy_out != nullptr && produced < learn_cap;
-            if (want_e) en.resize((size_t)cnt * N);
-            HN_TRY(upload_states(h, h->bitsA, states_packed, cnt));
-            HN_TRY(energy_profiles_impl(h, h->bitsA.as<uint64_t>(), cnt, want_e ? en.data() : nullptr, nullptr, stab.data(), nullptr));
-            bool all_stable = true;
-            for (int s = 0; s < cnt; s++) {
-                if (!stab[s]) all_stable = false;
-                if (produced < learn_cap) {
-                    if (learn_epoch_out) learn_epoch_out[produced] = epoch + epoch_offset;
-                    if (learn_index_out) learn_index_out[produced] = s;
-                    if (learn_stable_out) learn_stable_out[produced] = stab[s];
-                    if (want_e) std::memcpy(learn_energy_out + (size_t)produced * N, en.data() + (size_t)s * N, sizeof(double) * N);
-                }
-                produced++;
-                last_epoch = epoch + epoch_offset;
-            }
-            if (all_stable) break;  // AllStatesAreStable :56-58
-        }
-        return HN_OK;
-    };
-    (void)nvm;
-    if (method == HN_METHOD_FULL_SET) {
-        HN_TRY(full_set(n, 0));
-    } else {  // iterativeBatchLearningMethod, LearningMethod.go:70-89 (BATCHSIZE 5)
-        const int batches = n / 5;
-        int total = 0;
-        for (int it = 1; it <= batches; it++) {
-            HN_TRY(full_set(5 * it, total));
-            total = last_epoch;
-        }
-    }
-    HN_TRY(hn_normalize_frobenius(h, nullptr));  // HopfieldNetwork.go:260
-    if (n_learn_rows) *n_learn_rows = produced;
+    const bool is_delta = rule >= HN_RULE_DELTA;
+    if (is_delta && !rng) { set_error("%s: the delta rule needs an rng", fn); return HN_E_INVALID; }
     return HN_OK;
+}
+
+int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t rule, int32_t method,
+                    int32_t epochs, int32_t noise_method, double noise_scale, hn_rng rng, int32_t learn_cap,
+                    int32_t* learn_epoch_out, int32_t* learn_index_out, uint8_t* learn_stable_out,
+                    double* learn_energy_out, int32_t* n_learn_rows) {
+    HN_TRY(learn_states_check(h, "hn_learn_states", states_packed, n, rule, method, epochs, noise_scale, rng));
+    if (h->comm) {   // a sharded replica would all-reduce a dW that already holds every target, once per rank
+        set_error("hn_learn_states: a communicator is attached; use hn_learn_states_sharded (or hn_comm_detach first)");
+        return HN_E_STATE;
+    }
+    HN_TRY(set_device(h));
+    return learn_states_impl(h, states_packed, n, 0, n, rule, method, epochs, noise_method, noise_scale, rng, learn_cap,
+                             learn_epoch_out, learn_index_out, learn_stable_out, learn_energy_out, n_learn_rows);
+}
+
+int hn_learn_states_sharded(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t shard_begin, int32_t shard_end,
+                            int32_t rule, int32_t method, int32_t epochs, int32_t noise_method, double noise_scale,
+                            hn_rng rng, int32_t learn_cap, int32_t* learn_epoch_out, int32_t* learn_index_out,
+                            uint8_t* learn_stable_out, double* learn_energy_out, int32_t* n_learn_rows) {
+    HN_TRY(learn_states_check(h, "hn_learn_states_sharded", states_packed, n, rule, method, epochs, noise_scale, rng));
+    if (shard_begin < 0 || shard_end < shard_begin || shard_end > n) {
+        set_error("hn_learn_states_sharded: shard [%d, %d) is not inside [0, %d)", shard_begin, shard_end, n);
+        return HN_E_INVALID;
+    }
+    if (!h->comm && (shard_begin != 0 || shard_end != n)) {
+        set_error("hn_learn_states_sharded: a proper shard needs a communicator (hn_comm_attach)");
+        return HN_E_STATE;
+    }
+    HN_TRY(set_device(h));
+    return learn_states_impl(h, states_packed, n, shard_begin, shard_end, rule, method, epochs, noise_method, noise_scale,
+                             rng, learn_cap, learn_epoch_out, learn_index_out, learn_stable_out, learn_energy_out, n_learn_rows);
 }
 
 int hn_relax_batch(hn_handle h, const uint64_t* probes_packed, int32_t n_probes, const uint16_t* perm_pool,
@@ -1208,6 +1386,12 @@ int hn_last_relax_timing(hn_handle h, hn_relax_timing* t) {
     *t = h->timing;
     return HN_OK;
 }
+int hn_unique_table_stats(hn_handle h, int64_t* verified_merges, int64_t* refuted_merges) {
+    if (!check_handle(h, "hn_unique_table_stats")) return HN_E_INVALID;
+    if (verified_merges) *verified_merges = h->verified_pairs;
+    if (refuted_merges) *refuted_merges = h->refuted_pairs;
+    return HN_OK;
+}
 int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip) {
     if (!check_handle(h, "hn_get_margin")) return HN_E_INVALID;
     HN_TRY(set_device(h));
@@ -1282,7 +1466,8 @@ int hn_broadcast_weights(hn_handle h, int32_t root) {
     HN_NCCL_TRY(g_nccl.Broadcast(h->W, h->W, (size_t)h->N * h->ldw, NCCL_FLOAT64, root, h->comm, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     weights_changed(h);
-    return detect_symmetry(h);
+    HN_TRY(detect_symmetry(h));
+    return detect_integer_structure(h);
 }
 
 }  // extern "C"

@@ -191,6 +191,31 @@ __global__ void to_i16_kernel(const double* __restrict__ w, int16_t* __restrict_
     }
 }
 
+// ---- integer structure of caller-supplied weights (hn_set_weights: resume from matrix.bin, SetMatrix) ----
+// smallest non-zero |W_ij| (positive doubles order like their bit patterns); out starts at +inf bits
+__global__ void min_nonzero_abs_kernel(const double* __restrict__ w, int64_t total, unsigned long long* out) {
+    unsigned long long m = 0x7FF0000000000000ULL;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = fabs(w[i]);
+        if (x > 0.0) m = min(m, (unsigned long long)__double_as_longlong(x));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(out, m);
+}
+// hypothesis W = fl(c * K) with K integer: K = rint(W / c) into kout (as float64); flag <- 1 where fl(c*K) != W bit for
+// bit or |K| leaves the int16 image's range.  One rounding per element is exactly what Scale(1/norm) produced.
+__global__ void recover_integer_kernel(const double* __restrict__ w, double* __restrict__ kout, int64_t total, double c,
+                                       int32_t* flag) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = w[i];
+        const double k = rint(x / c);
+        if (__dmul_rn(c, k) != x || fabs(k) > 16383.0) bad = true;
+        kout[i] = k;
+    }
+    if (bad) *flag = 1;
+}
+
 // ---- inverse permutations: inv[row][perm[row][i]] = i -----------------------
 __global__ void invert_perm_kernel(const uint16_t* __restrict__ perm, uint16_t* __restrict__ inv, int n,
                                    int ldp, int rows) {
@@ -276,6 +301,28 @@ energy_epilogue_kernel(const double* __restrict__ H, int ldh, const uint64_t* __
     }
 }
 
+// ---- UnitEnergy: the reference's scalar loop (API surface, not used by its main) ----
+// BipolarDomainManager.go:29-37:  energy += -0.5 * W_ij * s_i * s_j            (left to right, sequential over j)
+// BinaryDomainManager.go:43-52:   energy += -0.5 * W_ij * s_i * (2 s_j - 1) - 1 (sic: one -1 per term)
+// One thread per state: the summation order IS the contract (no FMA, no tree).
+__global__ void unit_energy_kernel(const double* __restrict__ W, int ldw, const uint64_t* __restrict__ states, int words,
+                                   int n, int count, int domain, int unit, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    const uint64_t* bits = states + (size_t)s * words;
+    const double* row = W + (size_t)unit * ldw;
+    const bool binary = domain == HN_DOMAIN_BINARY;
+    const double si = ((bits[unit >> 6] >> (unit & 63)) & 1ULL) ? 1.0 : (binary ? 0.0 : -1.0);
+    double energy = 0.0;
+    for (int j = 0; j < n; j++) {
+        const double sj = ((bits[j >> 6] >> (j & 63)) & 1ULL) ? 1.0 : -1.0;   // binary: the mapped vector 2 s_j - 1
+        double term = __dmul_rn(__dmul_rn(__dmul_rn(-0.5, row[j]), si), sj);
+        if (binary) term = __dsub_rn(term, 1.0);
+        energy = __dadd_rn(energy, term);
+    }
+    out[s] = energy;
+}
+
 // ---- unique-attractor table (datacollector/UniqueRelaxedStateHandler.go:41-73) ----
 // key: sign-canonical packed final state (== identical energy profile, the
 // reference's key); 128-bit hash picks the bucket, the full state decides equality.
@@ -296,35 +343,94 @@ __device__ __forceinline__ bool same_canonical(const uint64_t* a, const uint64_t
     }
     return true;
 }
-// table[slot] = representative probe index or -1. rep[p] = representative of p.
-__global__ void dedup_insert_kernel(const uint64_t* __restrict__ finals, const uint64_t* __restrict__ hash,
+// Level 1: table[slot] = representative probe index or -1; rep[p] = representative of p.  Key: the canonical-state hash
+// (keys[p][0..1]) picks the bucket, the sign-canonical packed state decides — exact by construction.
+__global__ void dedup_insert_kernel(const uint64_t* __restrict__ finals, const uint64_t* __restrict__ keys,
                                     int B, int words, int n, int domain, int32_t* table, int cap_mask,
-                                    int32_t* __restrict__ rep, const uint8_t* __restrict__ zero_field, int hash_is_key) {
+                                    int32_t* __restrict__ rep, const uint8_t* __restrict__ zero_field) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
-    uint32_t slot = (uint32_t)(hash[(size_t)p * 2] ^ (hash[(size_t)p * 2 + 1] >> 17)) & cap_mask;
+    const uint64_t k0 = keys[(size_t)p * 4], k1 = keys[(size_t)p * 4 + 1];
+    uint32_t slot = (uint32_t)(k0 ^ (k1 >> 17)) & cap_mask;
     for (;;) {
         int32_t cur = atomicCAS(&table[slot], -1, p);
         if (cur == -1) { rep[p] = p; return; }
-        // hash_is_key: the 128 bits hash the exact energy profile (relax.cuh) and ARE the key; else they pick the bucket
-        // and the sign-canonical state decides
-        if (hash[(size_t)cur * 2] == hash[(size_t)p * 2] && hash[(size_t)cur * 2 + 1] == hash[(size_t)p * 2 + 1] &&
-            (hash_is_key ||
+        if (keys[(size_t)cur * 4] == k0 && keys[(size_t)cur * 4 + 1] == k1 &&
             same_canonical(finals + (size_t)cur * words, finals + (size_t)p * words, words, n, domain,
-                           zero_field[cur] != 0, zero_field[p] != 0))) {
+                           zero_field[cur] != 0, zero_field[p] != 0)) {
             rep[p] = cur;
             return;
         }
         slot = (slot + 1) & cap_mask;
     }
 }
-// first[rep] = min member index, hits[rep] = #members
-__global__ void dedup_count_kernel(const int32_t* __restrict__ rep, int B, int32_t* first, int32_t* hits) {
+// Level 2 (only where the exact-profile key exists): the level-1 representatives are grouped by their profile key
+// (keys[p][2..3]).  Equal profiles always give equal keys; every representative that joins an existing group is a
+// DIFFERENT state with the same key, so the pair is recorded and its float profiles are compared by dedup_verify_kernel.
+__global__ void dedup_insert_profile_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ rep1, int B,
+                                            int32_t* table, int cap_mask, int32_t* __restrict__ rep2,
+                                            int2* __restrict__ pairs, int32_t* n_pairs) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B || rep1[p] != p) return;
+    const uint64_t k2 = keys[(size_t)p * 4 + 2], k3 = keys[(size_t)p * 4 + 3];
+    uint32_t slot = (uint32_t)(k2 ^ (k3 >> 17)) & cap_mask;
+    for (;;) {
+        int32_t cur = atomicCAS(&table[slot], -1, p);
+        if (cur == -1) { rep2[p] = p; return; }
+        if (keys[(size_t)cur * 4 + 2] == k2 && keys[(size_t)cur * 4 + 3] == k3) {
+            rep2[p] = cur;
+            pairs[atomicAdd(n_pairs, 1)] = make_int2(p, cur);
+            return;
+        }
+        slot = (slot + 1) & cap_mask;
+    }
+}
+// One CTA per recorded pair (a, b): the reference's key is the printed energy profile (UniqueRelaxedStateHandler.go:44),
+// e_i = -0.5 * (h_i * v_i) with h_i the float64 row dot product in gonum's summation order.  Both profiles are computed
+// in that order and compared bit for bit; if they differ (a 128-bit key collision, or integer profiles that coincide
+// while the rounded float profiles do not) the key of `a` is salted so that the next insertion pass separates it.
+__global__ void __launch_bounds__(256)
+dedup_verify_kernel(const int2* __restrict__ pairs, const uint64_t* __restrict__ finals, int words,
+                    const double* __restrict__ W, int ldw, int n, int domain, uint64_t* __restrict__ keys,
+                    uint64_t salt, int32_t* n_bad) {
+    __shared__ int s_bad;
+    const int2 pr = pairs[blockIdx.x];
+    const uint32_t* ba = reinterpret_cast<const uint32_t*>(finals + (size_t)pr.x * words);
+    const uint32_t* bb = reinterpret_cast<const uint32_t*>(finals + (size_t)pr.y * words);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    for (int i = warp; i < n; i += 8) {
+        const double ha = exact_field_warp(W + (size_t)i * ldw, ba, n, domain, lane);
+        const double hb = exact_field_warp(W + (size_t)i * ldw, bb, n, domain, lane);
+        if (lane == 0) {
+            const double va = ((ba[i >> 5] >> (i & 31)) & 1u) ? 1.0 : -1.0, vb = ((bb[i >> 5] >> (i & 31)) & 1u) ? 1.0 : -1.0;
+            const double ea = -0.5 * (ha * va), eb = -0.5 * (hb * vb);
+            if (__double_as_longlong(ea) != __double_as_longlong(eb)) s_bad = 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bad) {
+        keys[(size_t)pr.x * 4 + 2] ^= mix64(salt);
+        keys[(size_t)pr.x * 4 + 3] += mix64(salt ^ 0x9E3779B97F4A7C15ULL);
+        atomicAdd(n_bad, 1);
+    }
+}
+// rep[p] = representative of p's final group: level 2 of its level-1 representative where level 2 ran
+__global__ void dedup_compose_kernel(const int32_t* __restrict__ rep1, const int32_t* __restrict__ rep2, int B,
+                                     int32_t* __restrict__ rep) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    rep[p] = rep2 ? rep2[rep1[p]] : rep1[p];
+}
+// first[rep] = min member index, hits[rep] = #members (or the sum of the members' own hit counts: merge of tables)
+__global__ void dedup_count_kernel(const int32_t* __restrict__ rep, int B, int32_t* first, int32_t* hits,
+                                   const int32_t* __restrict__ weight) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     const int r = rep[p];
     atomicMin(&first[r], p);
-    atomicAdd(&hits[r], 1);
+    atomicAdd(&hits[r], weight ? weight[p] : 1);
 }
 // flag[p] = 1 iff p is the first-seen member of its group
 __global__ void dedup_flag_kernel(const int32_t* __restrict__ rep, const int32_t* __restrict__ first, int B,
@@ -374,6 +480,19 @@ __global__ void dedup_finalize_kernel(const int32_t* __restrict__ rep, const int
     const int id = rank[f];
     attractor_id[p] = id;
     if (f == p) { ufirst[id] = f; uhits[id] = hits[r]; }
+}
+
+// totals of the per-probe counters of a batch: flips, sweeps (= NumSteps - 1), margin hits
+__global__ void sum_counters_kernel(const int32_t* __restrict__ flips, const int32_t* __restrict__ steps,
+                                    const int32_t* __restrict__ margin, int B, unsigned long long* __restrict__ tot) {
+    unsigned long long f = 0, s = 0, m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+        f += (unsigned)flips[i]; s += (unsigned)(steps[i] - 1); m += (unsigned)margin[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        f += __shfl_xor_sync(0xFFFFFFFFu, f, o); s += __shfl_xor_sync(0xFFFFFFFFu, s, o); m += __shfl_xor_sync(0xFFFFFFFFu, m, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&tot[0], f); atomicAdd(&tot[1], s); atomicAdd(&tot[2], m); }
 }
 
 // ---- f64 -> packed with activation (x <= 0 -> 0 bit) -------------------------
@@ -456,7 +575,7 @@ __global__ void zero_matrix_relax_kernel(const uint64_t* __restrict__ probes, in
         }
     if (lane == 0) {
         steps[p] = 2; stable[p] = 1; flips[p] = f; margin[p] = 0;
-        if (hash) { hash[(size_t)p * 2] = 0x5A45524F4D415452ULL; hash[(size_t)p * 2 + 1] = 0x4958414C4C4C4F57ULL; }   // one attractor
+        if (hash) { hash[(size_t)p * 4] = 0x5A45524F4D415452ULL; hash[(size_t)p * 4 + 1] = 0x4958414C4C4C4F57ULL; }   // one attractor (equal states)
         if (zero_field) zero_field[p] = 1;
     }
 }

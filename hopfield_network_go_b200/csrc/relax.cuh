@@ -66,7 +66,7 @@ struct RelaxParams {
     int32_t* distances;      // [B][P] or nullptr
     const uint64_t* targets; // [P][words]
     int P;
-    uint64_t* hash;          // [B][2] canonical-state hash or nullptr
+    uint64_t* hash;          // [B][4] unique-table keys (zeroed by the host): [0..1] canonical-state hash, [2..3] exact-profile key; or nullptr
     uint8_t* zero_field;     // [B] 1 iff the final state has a unit with an exactly zero field (dedup key, see same_canonical)
     uint64_t* history;       // [B][max_iter+1][words] or nullptr
     int32_t* work_counter;   // dynamic probe scheduler
@@ -367,8 +367,12 @@ relax_kernel(RelaxParams p) {
                 uint32_t nb = ob ^ 1u;
                 if (fl & 2) {  // inside the margin: decide exactly, in the reference's summation order
                     margin++;
-                    if (p.exact_arith) nb = 0u;   // the reference's field is this exact zero too: h <= 0 selects the low value
-                    else nb = exact_field(k) > 0.0 ? 1u : 0u;
+                    if (p.exact_arith) {
+                        nb = 0u;   // the reference's field is this exact zero too: h <= 0 selects the low value
+                        // no flip: every thread must have read s_flag before the next owner may overwrite it (the
+                        // other tie path passes exact_field's two barriers, a flip passes the barrier after the update)
+                        if (RELAX_WARPS > 1 && nb == ob) __syncthreads();
+                    } else nb = exact_field(k) > 0.0 ? 1u : 0u;
                 }
                 if (nb == ob) continue;  // exact decision: no flip; nothing was written, keep scanning
 
@@ -568,19 +572,22 @@ relax_kernel(RelaxParams p) {
                 }
             }
         }
-        // 128-bit unique-table key.  The reference keys on the printed energy profile
-        // (UniqueRelaxedStateHandler.go:44).  Where the profile is known EXACTLY — integer stream: v*g per unit;
-        // exact float arithmetic: the float64 values themselves — the key is a hash of the profile (plus, on the integer
-        // stream, a mark for every unit whose re-evaluated float field is +0: its energy is a zero whose sign follows
-        // v), so distinct states with identical profiles share a key exactly as in the reference (two stored patterns of
-        // a P=2 network do) and s / -s separate exactly when a zero energy changes sign.  Otherwise: hash of the
-        // sign-canonical final state (s and -s share a profile bit for bit unless a field is an exact zero).
+        // Unique-table keys (UniqueRelaxedStateHandler.go:44 keys on the printed energy profile), four words per probe:
+        //  [0..1] hash of the sign-canonical final state (s and -s share a profile bit for bit unless a field is an
+        //         exact zero, whose energy is a zero with the sign of v): level 1 of the table, equality decided on
+        //         the full packed state;
+        //  [2..3] where the profile is known EXACTLY — integer stream: v*g per unit; exact float arithmetic: the float64
+        //         values themselves; known integer structure on a float stream: rint(key_scale*h) — a hash of the
+        //         profile itself plus a mark for every unit whose re-evaluated float field is +0.  Equal profiles imply
+        //         equal keys, so DISTINCT states with identical profiles (the two stored patterns of a P=2 network)
+        //         meet at level 2 of the table, where the candidates' float profiles are compared bit for bit in the
+        //         reference's summation order (dedup_verify_kernel).
         if (p.hash) {
-            uint64_t h0 = 0, h1 = 0;
+            uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
             if (INTF || p.exact_arith || p.key_scale != 0.0) {
                 // 128 key bits: four multilinear hashes  sum_u value_u * c_j(u)  mod 2^32  with unit-dependent odd constants
                 // (a universal family: distinct profiles collide with probability ~2^-32 per hash), per thread; threads are
-                // combined by XOR.  No 64-bit arithmetic in this kernel's epilogue.
+                // combined by XOR.  No 64-bit arithmetic in this part of the epilogue.
                 uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
                 auto mix_in = [&](uint32_t uk, uint32_t v) {
                     k0 += v * (uk | 1u);
@@ -612,30 +619,34 @@ relax_kernel(RelaxParams p) {
                 k1 ^= k1 >> 15; k1 *= 0x846CA68Bu; k1 ^= k1 >> 16;
                 k2 ^= k2 >> 17; k2 *= 0xC2B2AE35u; k2 ^= k2 >> 13;
                 k3 ^= k3 >> 14; k3 *= 0x85EBCA6Bu; k3 ^= k3 >> 16;
-                h0 = ((uint64_t)k1 << 32) | k0;
-                h1 = ((uint64_t)k3 << 32) | k2;
-                if (!p.exact_arith && tid == 0) { h0 ^= s_tz[0]; h1 ^= s_tz[1]; }   // units whose re-evaluated float field is +0
-            } else {
-            const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !s_zero_field;
-            for (int w = tid; w < nbw; w += RELAX_THREADS) {
-                uint32_t x = s_bits[w];
-                if (inv) {
-                    x = ~x;
-                    if (w == nbw - 1 && (N & 31)) x &= (1u << (N & 31)) - 1u;
-                }
-                const uint64_t y = ((uint64_t)(w + 1) << 32) | x;
-                h0 ^= mix64(y ^ 0x9E3779B97F4A7C15ULL);
-                h1 ^= mix64(y * 0xD6E8FEB86659FD93ULL + 0x2545F4914F6CDD1DULL);
+                h2 = ((uint64_t)k1 << 32) | k0;
+                h3 = ((uint64_t)k3 << 32) | k2;
+                if (!p.exact_arith && tid == 0) { h2 ^= s_tz[0]; h3 ^= s_tz[1]; }   // units whose re-evaluated float field is +0
             }
+            {
+                const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !s_zero_field;
+                for (int w = tid; w < nbw; w += RELAX_THREADS) {
+                    uint32_t x = s_bits[w];
+                    if (inv) {
+                        x = ~x;
+                        if (w == nbw - 1 && (N & 31)) x &= (1u << (N & 31)) - 1u;
+                    }
+                    const uint64_t y = ((uint64_t)(w + 1) << 32) | x;
+                    h0 ^= mix64(y ^ 0x9E3779B97F4A7C15ULL);
+                    h1 ^= mix64(y * 0xD6E8FEB86659FD93ULL + 0x2545F4914F6CDD1DULL);
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 h0 ^= __shfl_xor_sync(0xFFFFFFFFu, h0, o);
                 h1 ^= __shfl_xor_sync(0xFFFFFFFFu, h1, o);
+                h2 ^= __shfl_xor_sync(0xFFFFFFFFu, h2, o);
+                h3 ^= __shfl_xor_sync(0xFFFFFFFFu, h3, o);
             }
             if (lane == 0) {
-                atomicXor(reinterpret_cast<unsigned long long*>(&p.hash[(size_t)pi * 2]), (unsigned long long)h0);
-                atomicXor(reinterpret_cast<unsigned long long*>(&p.hash[(size_t)pi * 2 + 1]), (unsigned long long)h1);
+                unsigned long long* hp = reinterpret_cast<unsigned long long*>(&p.hash[(size_t)pi * 4]);
+                if (RELAX_WARPS == 1) { hp[0] = h0; hp[1] = h1; hp[2] = h2; hp[3] = h3; }
+                else { atomicXor(hp, h0); atomicXor(hp + 1, h1); atomicXor(hp + 2, h2); atomicXor(hp + 3, h3); }
             }
         }
     }

@@ -193,6 +193,12 @@ class HopfieldNetwork:
         check(capi.load().hn_get_margin(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def unique_table_stats(self):
+        """(verified, refuted) merges of DIFFERENT states in the unique table (hn_unique_table_stats)."""
+        a, b = C.c_int64(), C.c_int64()
+        check(capi.load().hn_unique_table_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def _packed(self, states) -> np.ndarray:
         s = np.asarray(states)
         if s.dtype == np.uint64:
@@ -223,7 +229,11 @@ class HopfieldNetwork:
         return float(self.energy_profiles(np.asarray(state).reshape(1, -1), False)[3][0])
 
     def UnitEnergy(self, state, unit_index: int) -> float:
-        return float(self.AllUnitEnergies(state)[unit_index])
+        """HopfieldNetwork.go:185-187: the reference's scalar loop (Binary: -1 per term), hn_unit_energy."""
+        p = self._packed(np.asarray(state).reshape(1, -1))
+        out = np.empty(1)
+        check(capi.load().hn_unit_energy(self._h, ptr(p), 1, int(unit_index), ptr(out)))
+        return float(out[0])
 
     # ---- learning
     def hebbian_epoch(self, states) -> None:
@@ -252,8 +262,11 @@ class HopfieldNetwork:
         check(capi.load().hn_normalize_frobenius(self._h, C.byref(nrm)))
         return nrm.value
 
-    def LearnStates(self, states, want_energies: bool = False, cap: Optional[int] = None) -> List[LearnStateData]:
-        """HopfieldNetwork.go:254-262. `states`: float64 [P][N] (activated here) or packed uint64."""
+    def LearnStates(self, states, want_energies: bool = False, cap: Optional[int] = None,
+                    shard: Optional[tuple] = None) -> List[LearnStateData]:
+        """HopfieldNetwork.go:254-262. `states`: float64 [P][N] (activated here) or packed uint64.
+        shard=(begin, end): this replica learns targets [begin, end) of `states` and the attached communicator
+        all-reduces dW and the all-stable flag (hn_learn_states_sharded); rows returned are this shard's."""
         p = self._packed(states)
         n = p.shape[0]
         if cap is None:
@@ -263,9 +276,15 @@ class HopfieldNetwork:
         st = np.zeros(max(cap, 1), dtype=np.uint8)
         en = np.zeros((max(cap, 1), self.dimension)) if want_energies else None
         rows = C.c_int32()
-        check(capi.load().hn_learn_states(self._h, ptr(p), n, self.rule, self.method, self.epochs,
-                                          self.noise_method, self.noise_scale, self.randomGenerator._h, cap,
-                                          ptr(ep), ptr(ix), ptr(st), ptr(en), C.byref(rows)))
+        if shard is None:
+            check(capi.load().hn_learn_states(self._h, ptr(p), n, self.rule, self.method, self.epochs,
+                                              self.noise_method, self.noise_scale, self.randomGenerator._h, cap,
+                                              ptr(ep), ptr(ix), ptr(st), ptr(en), C.byref(rows)))
+        else:
+            check(capi.load().hn_learn_states_sharded(self._h, ptr(p), n, int(shard[0]), int(shard[1]), self.rule,
+                                                      self.method, self.epochs, self.noise_method, self.noise_scale,
+                                                      self.randomGenerator._h, cap, ptr(ep), ptr(ix), ptr(st), ptr(en),
+                                                      C.byref(rows)))
         k = min(rows.value, cap)
         return [LearnStateData(int(ep[i]), int(ix[i]), en[i] if want_energies else None, bool(st[i]))
                 for i in range(k)]

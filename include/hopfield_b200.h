@@ -209,6 +209,14 @@ int hn_energy_profiles(hn_handle h, const uint64_t* states_packed, int32_t n,
                        double* energies_out, int32_t* unstable_out, uint8_t* stable_out,
                        double* state_energy_out);
 
+/* UnitEnergy (HopfieldNetwork.go:185-187) for unit `unit_index` of each of n states: the reference's SCALAR loop,
+ * which is not AllUnitEnergies(state)[i]:
+ *   bipolar (domain/BipolarDomainManager.go:29-37): sum_j ((-0.5 * W_ij) * s_i) * s_j, accumulated in index order;
+ *   binary  (domain/BinaryDomainManager.go:43-52):  sum_j (((-0.5 * W_ij) * s_i) * (2 s_j - 1) - 1)  — the reference
+ *   subtracts 1 PER TERM (so the value is offset by -N); reproduced as written.
+ *   energy_out : [n] float64                                                                                      */
+int hn_unit_energy(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t unit_index, double* energy_out);
+
 /* Whole LearnStates (HopfieldNetwork.go:254-262) with the learning-method
  * loop of LearningMethod.go:38-89 run by the library, drawing noise and
  * permutations from `rng` (see hn_rng_*) in the reference's draw order.
@@ -226,6 +234,26 @@ int hn_learn_states(hn_handle h, const uint64_t* states_packed, int32_t n,
                     int32_t learn_cap, int32_t* learn_epoch_out, int32_t* learn_index_out,
                     uint8_t* learn_stable_out, double* learn_energy_out,
                     int32_t* n_learn_rows);
+
+/* LearnStates with the TARGETS SHARDED over the ranks of the attached communicator (config 5).
+ * Every rank passes the same n states and an identically seeded rng and names its shard [shard_begin, shard_end):
+ *   - noise and update orders are drawn for ALL n targets in the reference's order (LearningRule.go:98-104), so the
+ *     random stream — and therefore W — is bit-identical to the single-process hn_learn_states;
+ *   - each epoch's dW is all-reduced inside the library (exact integers: order independent) and every rank applies the
+ *     same update, so the replicas of W stay bitwise equal;
+ *   - the all-stable early exit (LearningMethod.go:56-58) is ncclAllReduce(min) of the per-rank flags: every rank runs
+ *     the same number of epochs (a rank whose shard of an iterative-batch prefix is empty contributes a zero dW);
+ *   - the LearnStateData rows returned are those of this rank's targets (TargetStateIndex is global); all n states
+ *     are appended to the target list of every replica.
+ * Without a communicator only the whole range [0, n) is accepted (then it IS hn_learn_states).
+ * hn_learn_states itself returns HN_E_STATE while a communicator is attached.                                    */
+int hn_learn_states_sharded(hn_handle h, const uint64_t* states_packed, int32_t n,
+                            int32_t shard_begin, int32_t shard_end,
+                            int32_t rule, int32_t method, int32_t epochs,
+                            int32_t noise_method, double noise_scale, hn_rng rng,
+                            int32_t learn_cap, int32_t* learn_epoch_out, int32_t* learn_index_out,
+                            uint8_t* learn_stable_out, double* learn_energy_out,
+                            int32_t* n_learn_rows);
 
 /* ---- relaxation --------------------------------------------------------
  * flags for hn_relax_batch */
@@ -253,8 +281,9 @@ typedef struct hn_relax_out {
     int32_t   n_unique;       /* out */
     /* history (HN_RELAX_HISTORY): packed state after every step incl. step 0 */
     uint64_t* history;        /* [B][max_relax_iterations+1][hn_words(N)]                            */
-    /* 128-bit hash of the sign-canonical final state (HN_RELAX_DEDUP): lets several GPUs merge their
-       unique tables without shipping the states (hopfield_network_go_b200/multigpu.py)               */
+    /* 128-bit key the unique table was grouped on (HN_RELAX_DEDUP): the exact-profile key where the library knows the
+       profile exactly, else the hash of the sign-canonical final state; lets a host merge per-GPU tables without
+       shipping the states (hn_merge_unique; hn_merge_unique_device compares the states too)            */
     uint64_t* state_hash;     /* [B][2]                                                              */
     /* totals (out) */
     int64_t   total_flips;
@@ -304,6 +333,14 @@ typedef struct hn_relax_timing {
     int32_t reserved;
 } hn_relax_timing;
 int hn_last_relax_timing(hn_handle h, hn_relax_timing* t);
+
+/* Unique-attractor table, exactness evidence (lifetime totals of the handle).  Equal sign-canonical states are merged
+ * by comparing the packed states; DIFFERENT states are merged only when their exact-profile keys coincide AND their
+ * float64 energy profiles, recomputed in the reference's summation order, are equal bit for bit
+ * (UniqueRelaxedStateHandler.go:44 keys on the printed profile).  verified_merges counts those comparisons,
+ * refuted_merges the ones that failed (a 128-bit key collision, or integer profiles that coincide where the rounded
+ * float profiles do not) and were separated again.                                                              */
+int hn_unique_table_stats(hn_handle h, int64_t* verified_merges, int64_t* refuted_merges);
 
 /* Decision margin tau = tau_base + tau_per_flip * flips currently in force
  * (DESIGN.md "margin").                                                      */

@@ -44,12 +44,12 @@ def test_auto_uses_integer_stream_after_learning(built, rule, domain, n):
     net.close()
 
 
-def test_auto_falls_back_for_supplied_and_thermal_weights(built):
+def test_auto_for_supplied_weights_and_fallback_for_thermal_weights(built):
     n, p, b = 256, 20, 64
     onet, k2, pool, probes, targets = make_problem(n, p, b, 41)
     net = gpu_net(n, SetColumnStream=AUTO)
-    net.SetMatrix(onet.w)                                  # caller-supplied weights: no integer structure known
-    assert not net.integer_stream_active()
+    net.SetMatrix(onet.w)                                  # caller-supplied weights: W = fl(c*K) is recovered from the bits
+    assert net.integer_stream_active()
     net.SetLearnedStates(orc.pack(targets))
     res = net.relax_batch(probes, pool)
     assert_relax_equal(res, onet.relax_batch(probes.copy(), pool, threads=8), n)

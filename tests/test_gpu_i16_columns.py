@@ -20,8 +20,8 @@ def test_i16_stream_matches_oracle(built, n, p, b, seed, domain):
     ores = onet.relax_batch(probes.copy(), pool, threads=8, want_energies=n <= 1024, fast_k2=k2 if n > 1024 else None)
     net = gpu_net(n, domain, SetColumnStream=I16)
     net.SetMatrix(onet.w)
-    assert not net.integer_stream_active()              # caller-supplied weights: structure unknown -> float64 stream
-    net.SetIntegerStructure(k2 * 0.5)
+    assert net.integer_stream_active()                  # caller-supplied weights: W = fl(c*K) recovered from the matrix itself
+    net.SetIntegerStructure(k2 * 0.5)                   # the explicit declaration still works
     assert net.integer_stream_active()
     net.SetLearnedStates(orc.pack(targets))
     res = net.relax_batch(probes, pool, dedup=True, want_energies=n <= 1024)
@@ -70,7 +70,7 @@ def test_i16_rejects_wrong_structure(built):
         net.SetIntegerStructure(bad)                      # not proportional to W
     with pytest.raises(capi.HopfieldError):
         net.SetIntegerStructure(onet.w)                   # proportional, but 4*matrix is not integer valued
-    assert not net.integer_stream_active()
+    assert net.integer_stream_active()                    # a refused declaration leaves the recovered structure in force
     net.close()
 
 

@@ -1,0 +1,193 @@
+// igemm_tc05.cuh — the exact integer fields contraction on the Blackwell tensor path (tcgen05 + TMEM + TMA):
+//   G[B x N] (int32) = S[B x N] (states as +-1 / 0-1 int8, expanded from packed bits) * M8[N x N]^T (int8)
+// i.e. the initial exact integer fields of a probe batch on the integer stream (HN_COLUMNS_I16 / AUTO) whenever the
+// int16 image of the weights fits a signed byte (|M| <= 127: every Hebbian / Delta matrix of the BASELINE configs).
+// Replaces the mma.sync kernel of igemm_s8.cuh on that path (which stays for images that need two byte planes).
+//
+// One persistent CTA per SM, 128 probes x 256 units per tile, K streamed in 128-byte steps through a 4-stage ring:
+//   warp 0      TMA producer: the M8 tile (256 rows x 128 B, 128-byte swizzle) of every K step;
+//   warp 1      allocates TMEM (2 accumulators of 256 columns) and issues tcgen05.mma.kind::i8 (M=128, N=256, K=32);
+//   warps 2-5   expand the probes' bits into the int8 A tile in the same swizzled layout (generic proxy + proxy fence);
+//   warps 6-9   epilogue: tcgen05.ld of the finished accumulator (one TMEM sub-partition per warp) -> global int32,
+//               overlapped with the next tile's MMAs through the second accumulator.
+// Everything is exact integer arithmetic: the result is bit-identical to igemm_fields_kernel and to the float64 GEMM.
+#pragma once
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace hn {
+
+constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 128, TG_STAGES = 4;
+constexpr int TG_A_BYTES = TG_BM * TG_BK, TG_B_BYTES = TG_BN * TG_BK;
+constexpr int TG_THREADS = 320;
+constexpr size_t TG_SMEM = (size_t)TG_STAGES * (TG_A_BYTES + TG_B_BYTES) + 256 + 1024;   // + barriers + alignment slack
+
+// 4 state bits -> 4 int8 in one word: bipolar +1 / -1 (0x01 / 0xFF), binary 1 / 0
+__device__ __forceinline__ uint32_t tg_expand4(uint32_t nib, bool bipolar) {
+    const uint32_t spread = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+    return bipolar ? (0xFFFFFFFFu ^ (spread * 0xFEu)) : spread;
+}
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
+igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_b, const uint64_t* __restrict__ states, int words, int B, int N,
+                  int bipolar, int32_t* __restrict__ G, int ldg) {
+    using namespace tc05;
+    extern __shared__ unsigned char tg_smem_raw[];
+    const uint32_t raw = smem_u32(tg_smem_raw);
+    unsigned char* smem = tg_smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + TG_STAGES * TG_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * (TG_A_BYTES + TG_B_BYTES));
+    uint64_t* full = bars;                    // [stages] 1 TMA arrive(+tx) + 4 producer warps
+    uint64_t* empty = bars + TG_STAGES;       // [stages] tcgen05.commit
+    uint64_t* acc_full = bars + 2 * TG_STAGES;       // [2] tcgen05.commit after the last K step of a tile
+    uint64_t* acc_empty = bars + 2 * TG_STAGES + 2;  // [2] 4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TG_STAGES + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m_tiles = (B + TG_BM - 1) / TG_BM, n_tiles = (N + TG_BN - 1) / TG_BN;
+    const int tiles = m_tiles * n_tiles;
+    const int kblocks = (N + TG_BK - 1) / TG_BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < TG_STAGES; s++) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * TG_BN;
+                for (int kb = 0; kb < kblocks; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full[stage], TG_B_BYTES);
+                    tma_load_2d(sB + (size_t)stage * TG_B_BYTES, &map_b, kb * TG_BK, n0, &full[stage]);
+                    if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = idesc_i8(TG_BM, TG_BN, true, true);
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+            const int acc = it & 1;
+            const uint32_t use = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&acc_empty[acc], use ^ 1u);      // the epilogue has drained this accumulator
+            tc_fence_after_sync();
+            for (int kb = 0; kb < kblocks; kb++) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    const uint64_t da = smem_desc_k128(smem_u32(sA + (size_t)stage * TG_A_BYTES));
+                    const uint64_t db = smem_desc_k128(smem_u32(sB + (size_t)stage * TG_B_BYTES));
+#pragma unroll
+                    for (int j = 0; j < TG_BK / 32; j++)   // K = 32 bytes per instruction: +32 B on the start address (>>4)
+                        mma_i8(tmem_base + (uint32_t)acc * TG_BN, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
+                               (uint32_t)((kb | j) != 0));
+                    mma_commit(&empty[stage]);             // frees the stage when these MMAs have read it
+                    if (kb == kblocks - 1) mma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp < 6) {
+        // ===== A producers: bits -> int8, 128-byte swizzled K-major tile =====
+        const int a = tid - 64;   // 0..127
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * TG_BM;
+            for (int kb = 0; kb < kblocks; kb++) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                unsigned char* dst = sA + (size_t)stage * TG_A_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int q = a + 128 * j;
+                    const int row = q >> 2, quarter = q & 3;
+                    const int probe = m0 + row, unit0 = kb * TG_BK + quarter * 32;
+                    uint32_t bits = 0;
+                    if (probe < B && unit0 < N)
+                        bits = (uint32_t)(__ldg(states + (size_t)probe * words + (unit0 >> 6)) >> (unit0 & 63));
+                    uint32_t w[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) w[e] = tg_expand4((bits >> (4 * e)) & 0xFu, bipolar != 0);
+                    if (unit0 + 32 > N) {   // ragged tail: units >= N contribute nothing
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            uint32_t mask = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; b++) if (unit0 + 4 * e + b < N) mask |= 0xFFu << (8 * b);
+                            w[e] &= mask;
+                        }
+                    }
+                    const uint32_t rbase = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+                    const uint32_t c0 = (uint32_t)quarter * 2u, sw = (uint32_t)(row & 7);
+                    *reinterpret_cast<uint4*>(dst + rbase + (((c0) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(dst + rbase + (((c0 + 1u) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+                if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int sub = warp & 3;   // TMEM sub-partition this warp may read
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+            const int acc = it & 1;
+            const uint32_t use = (uint32_t)(it >> 1) & 1u;
+            const int m0 = (tile / n_tiles) * TG_BM, n0 = (tile % n_tiles) * TG_BN;
+            mbar_wait(&acc_full[acc], use);
+            tc_fence_after_sync();
+            const int row = m0 + sub * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < TG_BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TG_BN + c * 32), r);
+                tmem_ld_wait();
+                const int col = n0 + c * 32;
+                if (row < B) {
+                    int32_t* out = G + (size_t)row * ldg + col;
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+                        if (col + 4 * v < ldg)   // ldg is a multiple of 16: whole vectors
+                            *reinterpret_cast<int4*>(out + 4 * v) = make_int4((int)r[4 * v], (int)r[4 * v + 1], (int)r[4 * v + 2], (int)r[4 * v + 3]);
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// M8: row-major int8 [N][ld8] (ld8 multiple of 16), row k = column k of the integer image (symmetric weights)
+static inline int launch_igemm_tc05(const uint64_t* states, int words, int B, const int8_t* M8, int ld8, int N, bool bipolar,
+                                    int32_t* G, int ldg, int sms, cudaStream_t st) {
+    if (B <= 0) return HN_OK;
+    CUtensorMap map;
+    const int rc = tc05::make_map_bytes_2d(&map, M8, (uint64_t)ld8, (uint64_t)N, (uint64_t)ld8, TG_BN);
+    if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
+    HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+    const int tiles = ((B + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
+    igemm_tc05_kernel<<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, states, words, B, N, bipolar ? 1 : 0, G, ldg);
+    HN_CUDA_TRY(cudaGetLastError());
+    return HN_OK;
+}
+
+}  // namespace hn

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "hn_get_weights", "hn_set_integer_structure", "hn_integer_stream_active", "hn_set_targets", "hn_num_targets", "hn_get_targets", "hn_hebbian_epoch",
     "hn_delta_epoch", "hn_thermal_delta_epoch", "hn_enforce_constraints", "hn_normalize_frobenius", "hn_energy_profiles",
     "hn_learn_states", "hn_learn_states_sharded", "hn_unit_energy", "hn_relax_batch", "hn_update_states", "hn_upload_perm_pool", "hn_upload_probes",
-    "hn_generate_probes", "hn_download_probes", "hn_relax_resident", "hn_download_results", "hn_last_relax_timing", "hn_get_margin", "hn_unique_table_stats",
+    "hn_generate_probes", "hn_download_probes", "hn_relax_resident", "hn_download_results", "hn_last_relax_timing", "hn_get_margin", "hn_unique_table_stats", "hn_debug_integer_fields",
     "hn_merge_unique", "hn_host_alloc", "hn_host_free", "hn_pack_states_f64", "hn_unpack_states_f64", "hn_comm_unique_id", "hn_comm_attach", "hn_comm_detach",
     "hn_broadcast_weights", "hn_rng_create", "hn_rng_destroy", "hn_rng_uint64", "hn_rng_uint64n",
     "hn_rng_float64", "hn_rng_norm_float64", "hn_rng_advance", "hn_rng_shuffle_u16", "hn_rng_perm_pool", "hn_rng_apply_noise", "hn_rng_generate_states",
@@ -116,6 +116,7 @@ def load():
     L.hn_download_results.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_last_relax_timing.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_get_margin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hn_debug_integer_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.hn_unique_table_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hn_merge_unique.argtypes = [C.c_int64] + [C.c_void_p] * 7
     L.hn_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

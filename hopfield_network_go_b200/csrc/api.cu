@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_f64.cuh"
 #include "igemm_s8.cuh"
+#include "igemm_tc05.cuh"
 #include "kernels_misc.cuh"
 #include "relax.cuh"
 
@@ -102,6 +103,9 @@ struct hn_handle_s {
     double* dW = nullptr;
     float* W32 = nullptr;       // float32 shadow of the column matrix (HN_COLUMNS_F32)
     double* Wraw = nullptr;     // un-normalised W captured at normalisation (HN_COLUMNS_I16): W = c * Wraw
+    int8_t* K8 = nullptr;       // the same image as signed bytes while every |M| <= 127 (tcgen05 fields GEMM); row-major [N][ldw]
+    bool k8_valid = false;
+    bool use_tc05 = true;       // HN_IGEMM=mma_sync in the environment selects the mma.sync kernel instead (A/B comparison)
     int16_t* K16 = nullptr;     // int16 image M = 2*int_scale*Wraw (+ self-correction on the diagonal, to_i16_kernel), column matrix layout
     bool int_ok = false;        // the integer structure of the CURRENT W is known and fits int16
     double int_maxabs = 0.0;    // max |K16 entry|
@@ -190,7 +194,7 @@ int ensure_margin(hn_handle h) {
     return HN_OK;
 }
 
-void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; h->int_ok = false; h->key_scale = 0.0; }
+void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; h->int_ok = false; h->key_scale = 0.0; h->k8_valid = false; }
 
 // exact symmetry test of the resident W (decides whether column k can be read as row k)
 int detect_symmetry(hn_handle h) {
@@ -254,6 +258,13 @@ int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W =
     h->int_ok = (f == 0) && exact && m > 0.0;
     h->int_maxabs = 2.0 * h->int_scale * m + 2.0;   // bound on |M| = |2K + diagonal term|
     h->key_scale = (h->int_ok && c > 0.0) ? h->int_scale / c : 0.0;   // K s = key_scale * (W s), to the nearest integer
+    h->k8_valid = false;
+    if (h->int_ok && symmetric && h->int_maxabs <= 127.0) {   // byte image for the tcgen05 fields GEMM
+        if (!h->K8) HN_CUDA_TRY(cudaMalloc(&h->K8, (size_t)total));
+        i16_to_i8_kernel<<<grid_for(total / 4, 256, h->sms), 256, 0, h->st>>>(h->K16, h->K8, total / 4);
+        HN_CUDA_TRY(cudaGetLastError());
+        h->k8_valid = true;
+    }
     return HN_OK;
 }
 
@@ -408,6 +419,15 @@ int validate_pool_host(hn_handle h, const uint16_t* pool, int rows) {
     return HN_OK;
 }
 
+// G = S * M^T, exact int32 (the integer stream's initial fields; W symmetric): tcgen05 / TMEM / TMA kernel on the byte
+// image, the mma.sync kernel where the image needs two byte planes
+int integer_fields(hn_handle h, const uint64_t* d_states, int count, int32_t* d_G) {
+    const bool bipolar = h->cfg.domain == HN_DOMAIN_BIPOLAR;
+    if (h->use_tc05 && h->k8_valid)
+        return launch_igemm_tc05(d_states, h->words, count, h->K8, h->ldw, h->N, bipolar, d_G, h->ldw, h->sms, h->st);
+    return launch_igemm_fields(d_states, h->words, count, h->K16, h->ldw, h->N, bipolar, d_G, h->ldw, h->int_maxabs <= 127.0, h->st);
+}
+
 // Unique-attractor table over `count` final states on the device (datacollector/UniqueRelaxedStateHandler.go:41-73).
 // Level 1 groups equal sign-canonical states (exact); where the exact-profile key exists, level 2 groups the level-1
 // representatives by that key and every such merge is verified on the float energy profiles in the reference's
@@ -527,8 +547,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     // symmetric (K's rows are its columns), else S * Wraw^T in float64 (half/quarter-integers: exact)
     const bool int_fields = integer_stream(h) && h->w_symmetric;
     if (int_fields)
-        HN_TRY(launch_igemm_fields(d_probes, h->words, B, h->K16, h->ldw, N, h->cfg.domain == HN_DOMAIN_BIPOLAR,
-                                   reinterpret_cast<int32_t*>(h->H.as<double>()), h->ldw, h->int_maxabs <= 127.0, h->st));
+        HN_TRY(integer_fields(h, d_probes, B, reinterpret_cast<int32_t*>(h->H.as<double>())));
     else
         HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
     launches++;
@@ -928,6 +947,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
         return rc;
     }
     h->w_symmetric = true;  // the zero matrix
+    if (const char* e = getenv("HN_IGEMM")) h->use_tc05 = std::strcmp(e, "mma_sync") != 0;
     *out = h;
     return HN_OK;
 }
@@ -948,6 +968,7 @@ int hn_destroy(hn_handle h) {
     if (h->W32) cudaFree(h->W32);
     if (h->Wraw) cudaFree(h->Wraw);
     if (h->K16) cudaFree(h->K16);
+    if (h->K8) cudaFree(h->K8);
     if (h->dW) cudaFree(h->dW);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
@@ -1384,6 +1405,20 @@ int hn_download_results(hn_handle h, hn_relax_out* out) {
 int hn_last_relax_timing(hn_handle h, hn_relax_timing* t) {
     if (!check_handle(h, "hn_last_relax_timing") || !t) return HN_E_INVALID;
     *t = h->timing;
+    return HN_OK;
+}
+int hn_debug_integer_fields(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t* fields_out, int32_t* kernel_used) {
+    if (!check_handle(h, "hn_debug_integer_fields")) return HN_E_INVALID;
+    if (n <= 0 || !states_packed || !fields_out) { set_error("hn_debug_integer_fields: bad argument"); return HN_E_INVALID; }
+    if (!integer_stream(h) || !h->w_symmetric) { set_error("hn_debug_integer_fields: the integer stream is not active"); return HN_E_STATE; }
+    HN_TRY(set_device(h));
+    HN_TRY(upload_states(h, h->bitsA, states_packed, n));
+    HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_TRY(integer_fields(h, h->bitsA.as<uint64_t>(), n, reinterpret_cast<int32_t*>(h->H.as<double>())));
+    HN_CUDA_TRY(cudaMemcpy2DAsync(fields_out, sizeof(int32_t) * h->N, h->H.p, sizeof(int32_t) * h->ldw, sizeof(int32_t) * h->N, n,
+                                  cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (kernel_used) *kernel_used = (h->use_tc05 && h->k8_valid) ? 1 : 0;
     return HN_OK;
 }
 int hn_unique_table_stats(hn_handle h, int64_t* verified_merges, int64_t* refuted_merges) {

@@ -191,6 +191,14 @@ __global__ void to_i16_kernel(const double* __restrict__ w, int16_t* __restrict_
     }
 }
 
+// byte image of the int16 image (every |M| <= 127), four entries per thread
+__global__ void i16_to_i8_kernel(const int16_t* __restrict__ k16, int8_t* __restrict__ k8, int64_t quads) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (int64_t)gridDim.x * blockDim.x) {
+        const short4 v = reinterpret_cast<const short4*>(k16)[i];
+        reinterpret_cast<char4*>(k8)[i] = make_char4((signed char)v.x, (signed char)v.y, (signed char)v.z, (signed char)v.w);
+    }
+}
+
 // ---- integer structure of caller-supplied weights (hn_set_weights: resume from matrix.bin, SetMatrix) ----
 // smallest non-zero |W_ij| (positive doubles order like their bit patterns); out starts at +inf bits
 __global__ void min_nonzero_abs_kernel(const double* __restrict__ w, int64_t total, unsigned long long* out) {

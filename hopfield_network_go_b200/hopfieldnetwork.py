@@ -193,6 +193,14 @@ class HopfieldNetwork:
         check(capi.load().hn_get_margin(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def debug_integer_fields(self, states):
+        """(fields int32 [n][N], kernel) of hn_debug_integer_fields: kernel 1 = tcgen05/TMEM/TMA, 0 = mma.sync."""
+        p = self._packed(states)
+        out = np.empty((p.shape[0], self.dimension), dtype=np.int32)
+        k = C.c_int32()
+        check(capi.load().hn_debug_integer_fields(self._h, ptr(p), p.shape[0], ptr(out), C.byref(k)))
+        return out, k.value
+
     def unique_table_stats(self):
         """(verified, refuted) merges of DIFFERENT states in the unique table (hn_unique_table_stats)."""
         a, b = C.c_int64(), C.c_int64()

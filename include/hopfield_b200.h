@@ -342,6 +342,12 @@ int hn_last_relax_timing(hn_handle h, hn_relax_timing* t);
  * float profiles do not) and were separated again.                                                              */
 int hn_unique_table_stats(hn_handle h, int64_t* verified_merges, int64_t* refuted_merges);
 
+/* Diagnostic: the exact integer fields (M s) of n states as the integer stream's contraction kernel computes them
+ * (tcgen05 / TMEM / TMA kernel on the byte image: *kernel_used = 1; mma.sync kernel: 0).  M is the int16 image of the
+ * weights (2K with the self term on the diagonal).  fields_out: [n][N] int32.  HN_E_STATE unless the integer stream is
+ * active and W is symmetric.                                                                                    */
+int hn_debug_integer_fields(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t* fields_out, int32_t* kernel_used);
+
 /* Decision margin tau = tau_base + tau_per_flip * flips currently in force
  * (DESIGN.md "margin").                                                      */
 int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip);

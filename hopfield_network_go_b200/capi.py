@@ -22,8 +22,8 @@ EXPORTED_SYMBOLS = [
     "hn_get_weights", "hn_set_integer_structure", "hn_integer_stream_active", "hn_set_targets", "hn_num_targets", "hn_get_targets", "hn_hebbian_epoch",
     "hn_delta_epoch", "hn_thermal_delta_epoch", "hn_enforce_constraints", "hn_normalize_frobenius", "hn_energy_profiles",
     "hn_learn_states", "hn_learn_states_sharded", "hn_unit_energy", "hn_relax_batch", "hn_update_states", "hn_upload_perm_pool", "hn_upload_probes",
-    "hn_generate_probes", "hn_download_probes", "hn_relax_resident", "hn_download_results", "hn_last_relax_timing", "hn_get_margin", "hn_unique_table_stats", "hn_debug_integer_fields",
-    "hn_merge_unique", "hn_host_alloc", "hn_host_free", "hn_pack_states_f64", "hn_unpack_states_f64", "hn_comm_unique_id", "hn_comm_attach", "hn_comm_detach",
+    "hn_generate_probes", "hn_download_probes", "hn_relax_resident", "hn_download_results", "hn_last_relax_timing", "hn_last_learn_timing", "hn_get_margin", "hn_unique_table_stats", "hn_debug_integer_fields",
+    "hn_merge_unique", "hn_export_unique_device", "hn_merge_unique_device", "hn_host_alloc", "hn_host_free", "hn_pack_states_f64", "hn_unpack_states_f64", "hn_comm_unique_id", "hn_comm_attach", "hn_comm_detach",
     "hn_broadcast_weights", "hn_rng_create", "hn_rng_destroy", "hn_rng_uint64", "hn_rng_uint64n",
     "hn_rng_float64", "hn_rng_norm_float64", "hn_rng_advance", "hn_rng_shuffle_u16", "hn_rng_perm_pool", "hn_rng_apply_noise", "hn_rng_generate_states",
 ]
@@ -43,6 +43,13 @@ class HnRelaxOut(C.Structure):
                 ("unique_hits", C.c_void_p), ("unique_cap", C.c_int32), ("n_unique", C.c_int32),
                 ("history", C.c_void_p), ("state_hash", C.c_void_p), ("total_flips", C.c_int64), ("total_sweeps", C.c_int64),
                 ("total_margin_hits", C.c_int64), ("device_ms", C.c_double)]
+
+
+class HnLearnTiming(C.Structure):
+    _fields_ = [("sweep_fields_ms", C.c_double), ("sweep_ms", C.c_double), ("dw_gemm_ms", C.c_double),
+                ("allreduce_ms", C.c_double), ("update_ms", C.c_double), ("energy_gemm_ms", C.c_double),
+                ("energy_epilogue_ms", C.c_double), ("targets", C.c_int32), ("reserved", C.c_int32),
+                ("sweep_flips", C.c_int64)]
 
 
 class HnRelaxTiming(C.Structure):
@@ -115,10 +122,13 @@ def load():
     L.hn_relax_resident.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.hn_download_results.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_last_relax_timing.argtypes = [C.c_void_p, C.c_void_p]
+    L.hn_last_learn_timing.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_get_margin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hn_debug_integer_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.hn_unique_table_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hn_merge_unique.argtypes = [C.c_int64] + [C.c_void_p] * 7
+    L.hn_export_unique_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+    L.hn_merge_unique_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int32] + [C.c_void_p] * 4
     L.hn_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.hn_host_free.argtypes = [C.c_void_p]
     L.hn_pack_states_f64.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]

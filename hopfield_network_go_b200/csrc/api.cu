@@ -131,7 +131,10 @@ struct hn_handle_s {
     int resident_B = 0, resident_pool = 0, result_B = 0, result_P = 0, result_unique = 0;
     uint32_t result_flags = 0;
     bool result_profile_keyed = false;
+    bool sweep_timed = false;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t lev[8] = {};   // learning-epoch stage events
+    hn_learn_timing ltiming = {};
     hn_relax_timing timing = {};
     int64_t tot_flips = 0, tot_sweeps = 0, tot_margin = 0;
     void* comm = nullptr;
@@ -772,7 +775,9 @@ int sweep_once(hn_handle h, int n, const uint16_t* perms) {
     HN_CUDA_TRY(cudaMemcpyAsync(h->offsets.p, off.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));  // `off` must outlive the copy
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[0], h->st));
     HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[1], h->st));
     HN_TRY(h->small.reserve(sizeof(Scratch)));
     Scratch* sc = h->scratch();
     HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));
@@ -784,8 +789,16 @@ int sweep_once(hn_handle h, int n, const uint16_t* perms) {
     p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.max_unstable = 0; p.domain = h->cfg.domain;
     p.check_stability = 0; p.serial_stream = 0;
     p.final_states = h->bitsC.as<uint64_t>();
+    HN_TRY(h->flips.reserve(sizeof(int32_t) * (size_t)n));
+    p.flips = h->flips.as<int32_t>();   // counter only (roofline of the sweep: one column per flip)
     p.work_counter = &sc->work_counter; p.status = sc->status;
-    return launch_relax(h, p);
+    HN_TRY(launch_relax(h, p));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[2], h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(sc->totals, 0, sizeof(sc->totals), h->st));
+    sum_counters_kernel<<<std::min((n + 255) / 256, h->sms * 4), 256, 0, h->st>>>(h->flips.as<int32_t>(), nullptr, nullptr, n, sc->totals);
+    HN_CUDA_TRY(cudaGetLastError());
+    h->sweep_timed = true;
+    return HN_OK;
 }
 
 int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised, const uint16_t* perms, int n,
@@ -793,6 +806,7 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
     const int N = h->N, words = h->words;
     HN_TRY(upload_states(h, h->bitsA, states, n));
     HN_TRY(upload_states(h, h->bitsB, noised, n));
+    h->sweep_timed = false;
     HN_TRY(sweep_once(h, n, perms));   // one sweep per noised copy in its own fresh order (HopfieldNetwork.go:281-282)
     if (relaxed_out)
         HN_CUDA_TRY(cudaMemcpyAsync(relaxed_out, h->bitsC.p, sizeof(uint64_t) * (size_t)n * words, cudaMemcpyDeviceToHost, h->st));
@@ -826,10 +840,33 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
                   thermal ? 1.0 : 0.5, kscale};
     OpBits b{h->bitsAT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi};
     EpiStore e{h->dW, h->ldw, N, N};
+    HN_CUDA_TRY(cudaEventRecord(h->lev[3], h->st));
     HN_TRY(launch_gemm_f64(a, b, e, N, N, n, h->st));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[4], h->st));
     HN_TRY(all_reduce_dw(h));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[5], h->st));
     HN_TRY(apply_update_and_constraints(h));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[6], h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    {
+        float t = 0;
+        hn_learn_timing& lt = h->ltiming;
+        lt.sweep_fields_ms = lt.sweep_ms = 0;
+        if (h->sweep_timed) {
+            cudaEventElapsedTime(&t, h->lev[0], h->lev[1]); lt.sweep_fields_ms = t;
+            cudaEventElapsedTime(&t, h->lev[1], h->lev[2]); lt.sweep_ms = t;
+        }
+        cudaEventElapsedTime(&t, h->lev[3], h->lev[4]); lt.dw_gemm_ms = t;
+        cudaEventElapsedTime(&t, h->lev[4], h->lev[5]); lt.allreduce_ms = t;
+        cudaEventElapsedTime(&t, h->lev[5], h->lev[6]); lt.update_ms = t;
+        lt.targets = n;
+        lt.sweep_flips = 0;
+        if (h->sweep_timed) {
+            unsigned long long f = 0;
+            HN_CUDA_TRY(cudaMemcpy(&f, &h->scratch()->totals[0], 8, cudaMemcpyDeviceToHost));
+            lt.sweep_flips = (int64_t)f;
+        }
+    }
     return HN_OK;
 }
 
@@ -838,7 +875,9 @@ int energy_profiles_impl(hn_handle h, const uint64_t* d_states, int n, double* e
     const int N = h->N;
     HN_TRY(ensure_margin(h));
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[7], h->st));
     HN_TRY(launch_fields(h, d_states, n, h->H.as<double>(), domain_values(h->cfg.domain)));
+    HN_CUDA_TRY(cudaEventRecord(h->lev[0], h->st));
     if (energies_out) HN_TRY(h->energies.reserve(sizeof(double) * (size_t)n * N));
     HN_TRY(h->eunst.reserve(sizeof(int32_t) * (size_t)n));
     HN_TRY(h->estab.reserve((size_t)n));
@@ -849,11 +888,17 @@ int energy_profiles_impl(hn_handle h, const uint64_t* d_states, int n, double* e
                                                         h->eunst.as<int32_t>(), h->estab.as<uint8_t>(), h->esum.as<double>(),
                                                         nullptr);
     HN_CUDA_TRY(cudaGetLastError());
+    HN_CUDA_TRY(cudaEventRecord(h->lev[1], h->st));
     if (energies_out) HN_CUDA_TRY(cudaMemcpyAsync(energies_out, h->energies.p, sizeof(double) * (size_t)n * N, cudaMemcpyDeviceToHost, h->st));
     if (unstable_out) HN_CUDA_TRY(cudaMemcpyAsync(unstable_out, h->eunst.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
     if (stable_out) HN_CUDA_TRY(cudaMemcpyAsync(stable_out, h->estab.p, (size_t)n, cudaMemcpyDeviceToHost, h->st));
     if (state_energy_out) HN_CUDA_TRY(cudaMemcpyAsync(state_energy_out, h->esum.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    {
+        float t = 0;
+        cudaEventElapsedTime(&t, h->lev[7], h->lev[0]); h->ltiming.energy_gemm_ms = t;
+        cudaEventElapsedTime(&t, h->lev[0], h->lev[1]); h->ltiming.energy_epilogue_ms = t;
+    }
     return HN_OK;
 }
 
@@ -938,6 +983,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
         if (cudaMemsetAsync(h->W, 0, wb, h->st) != cudaSuccess) { rc = HN_E_CUDA; break; }  // matrix.Zero(), :248-250
         if (cudaMemsetAsync(h->dW, 0, wb, h->st) != cudaSuccess) { rc = HN_E_CUDA; break; }
         for (auto& e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) { rc = HN_E_CUDA; break; }
+        for (auto& e : h->lev) if (cudaEventCreate(&e) != cudaSuccess) { rc = HN_E_CUDA; break; }
         if (rc != HN_OK) break;
         if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = HN_E_CUDA; break; }
     } while (0);
@@ -971,6 +1017,7 @@ int hn_destroy(hn_handle h) {
     if (h->K8) cudaFree(h->K8);
     if (h->dW) cudaFree(h->dW);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->lev) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return HN_OK;
@@ -1407,6 +1454,59 @@ int hn_last_relax_timing(hn_handle h, hn_relax_timing* t) {
     *t = h->timing;
     return HN_OK;
 }
+int hn_export_unique_device(hn_handle h, int64_t index_offset, int64_t* d_first, int32_t* d_hits, uint64_t* d_keys,
+                            uint64_t* d_states, uint8_t* d_zero_field, int32_t* n_unique, int32_t* profile_keyed) {
+    if (!check_handle(h, "hn_export_unique_device")) return HN_E_INVALID;
+    if (!(h->result_flags & HN_RELAX_DEDUP) || h->result_B <= 0) { set_error("hn_export_unique_device: no unique table on the device (HN_RELAX_DEDUP)"); return HN_E_STATE; }
+    if (n_unique) *n_unique = h->result_unique;
+    if (profile_keyed) *profile_keyed = h->result_profile_keyed ? 1 : 0;
+    if (!d_first) return HN_OK;   // size query
+    if (!d_hits || !d_keys || !d_states || !d_zero_field) { set_error("hn_export_unique_device: NULL output"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    const int nu = h->result_unique;
+    if (nu > 0) {
+        export_unique_kernel<<<grid_for((int64_t)nu * (h->words + 4), 256, h->sms), 256, 0, h->st>>>(
+            h->ufirst.as<int32_t>(), h->uhits.as<int32_t>(), nu, h->finals.as<uint64_t>(), h->words, h->hash.as<uint64_t>(),
+            h->zf.as<uint8_t>(), (long long)index_offset, reinterpret_cast<long long*>(d_first), d_hits, d_keys, d_states, d_zero_field);
+        HN_CUDA_TRY(cudaGetLastError());
+    }
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    return HN_OK;
+}
+
+int hn_merge_unique_device(hn_handle h, int64_t n, const int64_t* d_first, const int32_t* d_hits, uint64_t* d_keys,
+                           const uint64_t* d_states, const uint8_t* d_zero_field, int32_t profile_keyed,
+                           int64_t* first_out, int64_t* hits_out, int64_t* rep_out, int64_t* n_groups_out) {
+    if (!check_handle(h, "hn_merge_unique_device")) return HN_E_INVALID;
+    if (n < 0 || n > 0x7FFFFFFF || !n_groups_out || (n > 0 && (!d_first || !d_hits || !d_keys || !d_states || !d_zero_field || !first_out || !hits_out))) {
+        set_error("hn_merge_unique_device: bad argument");
+        return HN_E_INVALID;
+    }
+    *n_groups_out = 0;
+    if (n == 0) return HN_OK;
+    HN_TRY(set_device(h));
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    HN_CUDA_TRY(cudaMemsetAsync(&h->scratch()->unique_total, 0, 4, h->st));
+    // entries arrive in ascending global first index (rank by rank, each rank's table in first-seen order): position
+    // order IS first-seen order, exactly what run_dedup's flag + scan produce
+    HN_TRY(run_dedup(h, d_states, d_keys, d_zero_field, (int)n, profile_keyed != 0, d_hits, nullptr));
+    int32_t nu = 0;
+    HN_CUDA_TRY(cudaMemcpyAsync(&nu, &h->scratch()->unique_total, 4, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    HN_TRY(h->partial.reserve(sizeof(long long) * 3 * (size_t)std::max(nu, 1)));
+    long long* out = h->partial.as<long long>();
+    merge_rows_kernel<<<(nu + 255) / 256, 256, 0, h->st>>>(h->ufirst.as<int32_t>(), h->uhits.as<int32_t>(), nu,
+                                                          reinterpret_cast<const long long*>(d_first), out, out + nu, out + 2 * (size_t)nu);
+    HN_CUDA_TRY(cudaGetLastError());
+    HN_CUDA_TRY(cudaMemcpyAsync(first_out, out, sizeof(long long) * (size_t)nu, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaMemcpyAsync(hits_out, out + nu, sizeof(long long) * (size_t)nu, cudaMemcpyDeviceToHost, h->st));
+    if (rep_out) HN_CUDA_TRY(cudaMemcpyAsync(rep_out, out + 2 * (size_t)nu, sizeof(long long) * (size_t)nu, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    *n_groups_out = nu;
+    h->result_flags &= ~HN_RELAX_DEDUP;   // the handle's own table buffers were reused by the merge
+    return HN_OK;
+}
+
 int hn_debug_integer_fields(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t* fields_out, int32_t* kernel_used) {
     if (!check_handle(h, "hn_debug_integer_fields")) return HN_E_INVALID;
     if (n <= 0 || !states_packed || !fields_out) { set_error("hn_debug_integer_fields: bad argument"); return HN_E_INVALID; }
@@ -1425,6 +1525,11 @@ int hn_unique_table_stats(hn_handle h, int64_t* verified_merges, int64_t* refute
     if (!check_handle(h, "hn_unique_table_stats")) return HN_E_INVALID;
     if (verified_merges) *verified_merges = h->verified_pairs;
     if (refuted_merges) *refuted_merges = h->refuted_pairs;
+    return HN_OK;
+}
+int hn_last_learn_timing(hn_handle h, hn_learn_timing* t) {
+    if (!check_handle(h, "hn_last_learn_timing") || !t) return HN_E_INVALID;
+    *t = h->ltiming;
     return HN_OK;
 }
 int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip) {

@@ -490,12 +490,42 @@ __global__ void dedup_finalize_kernel(const int32_t* __restrict__ rep, const int
     if (f == p) { ufirst[id] = f; uhits[id] = hits[r]; }
 }
 
+// unique entries of a batch gathered into caller-owned DEVICE arrays (cross-GPU merge of tables: the entries travel
+// between GPUs, not through the host): entry j = the first occurrence ufirst[j] of attractor j
+__global__ void export_unique_kernel(const int32_t* __restrict__ ufirst, const int32_t* __restrict__ uhits, int nu,
+                                     const uint64_t* __restrict__ finals, int words, const uint64_t* __restrict__ keys,
+                                     const uint8_t* __restrict__ zf, long long offset, long long* __restrict__ first_out,
+                                     int32_t* __restrict__ hits_out, uint64_t* __restrict__ keys_out,
+                                     uint64_t* __restrict__ states_out, uint8_t* __restrict__ zf_out) {
+    const int per = words + 4;
+    const long long total = (long long)nu * per;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t / per), w = (int)(t % per);
+        const int p = ufirst[j];
+        if (w < words) states_out[(size_t)j * words + w] = finals[(size_t)p * words + w];
+        else keys_out[(size_t)j * 4 + (w - words)] = keys[(size_t)p * 4 + (w - words)];
+        if (w == 0) { first_out[j] = offset + p; hits_out[j] = uhits[j]; zf_out[j] = zf[p]; }
+    }
+}
+// merged table rows: first = the global index carried by the group's earliest entry, hits = summed
+__global__ void merge_rows_kernel(const int32_t* __restrict__ ufirst, const int32_t* __restrict__ uhits, int nu,
+                                  const long long* __restrict__ first_in, long long* __restrict__ first_out,
+                                  long long* __restrict__ hits_out, long long* __restrict__ rep_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nu) return;
+    first_out[j] = first_in[ufirst[j]];
+    hits_out[j] = uhits[j];
+    rep_out[j] = ufirst[j];
+}
+
 // totals of the per-probe counters of a batch: flips, sweeps (= NumSteps - 1), margin hits
 __global__ void sum_counters_kernel(const int32_t* __restrict__ flips, const int32_t* __restrict__ steps,
                                     const int32_t* __restrict__ margin, int B, unsigned long long* __restrict__ tot) {
     unsigned long long f = 0, s = 0, m = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
-        f += (unsigned)flips[i]; s += (unsigned)(steps[i] - 1); m += (unsigned)margin[i];
+        f += (unsigned)flips[i];
+        if (steps) s += (unsigned)(steps[i] - 1);
+        if (margin) m += (unsigned)margin[i];
     }
     for (int o = 16; o > 0; o >>= 1) {
         f += __shfl_xor_sync(0xFFFFFFFFu, f, o); s += __shfl_xor_sync(0xFFFFFFFFu, s, o); m += __shfl_xor_sync(0xFFFFFFFFu, m, o);

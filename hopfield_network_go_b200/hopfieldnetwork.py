@@ -376,6 +376,11 @@ class HopfieldNetwork:
         check(capi.load().hn_relax_resident(self._h, capi.HN_RELAX_DEDUP if dedup else 0, C.byref(ms)))
         return ms.value
 
+    def last_learn_timing(self) -> capi.HnLearnTiming:
+        t = capi.HnLearnTiming()
+        check(capi.load().hn_last_learn_timing(self._h, C.byref(t)))
+        return t
+
     def last_timing(self) -> capi.HnRelaxTiming:
         t = capi.HnRelaxTiming()
         check(capi.load().hn_last_relax_timing(self._h, C.byref(t)))

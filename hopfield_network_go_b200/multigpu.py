@@ -157,3 +157,62 @@ def gather_unique_tables(local: dict, group=None) -> Optional[dict]:
         tables.append({"offset": int(heads[r][1]), "first": (t[:, 0] & 0xFFFFFFFF).astype(np.int32),
                        "hits": (t[:, 0] >> 32).astype(np.int32), "hash": np.ascontiguousarray(t[:, 1:]).view(np.uint64)})
     return merge_unique_tables(tables)
+
+
+def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[dict]:
+    """Cross-GPU merge of unique tables WITHOUT the host in the data path (nccl backend): every rank exports its table
+    — global first index, hits, key words, packed final states, zero-field marks — into device tensors
+    (hn_export_unique_device), the tensors are gathered on rank 0's GPU, and rank 0 runs the library's two-level
+    unique table over the concatenation (hn_merge_unique_device: equal states compared as states, different states
+    merged only after the float-profile comparison).  All ranks call; rank 0 returns {"first", "hits", "rank_of",
+    "local_id"} (numpy), the others None."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    lib = capi.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nu, pk = C.c_int32(), C.c_int32()
+    capi.check(lib.hn_export_unique_device(net._h, 0, None, None, None, None, None, C.byref(nu), C.byref(pk)))
+    u, w = nu.value, capi.words(net.dimension)
+    head = torch.tensor([u, pk.value], dtype=torch.int64, device=dev)
+    heads = [torch.zeros_like(head) for _ in range(world)]
+    dist.all_gather(heads, head, group=group)
+    heads = torch.stack(heads).cpu().numpy()
+    counts = heads[:, 0].astype(np.int64)
+    umax = max(1, int(counts.max()))
+    # one int64 payload per rank: [first | hits | zero-field | 4 key words | packed state]
+    pay = torch.zeros((umax, 7 + w), dtype=torch.int64, device=dev)
+    first = torch.zeros(umax, dtype=torch.int64, device=dev)
+    hits = torch.zeros(umax, dtype=torch.int32, device=dev)
+    keys = torch.zeros((umax, 4), dtype=torch.int64, device=dev)
+    states = torch.zeros((umax, w), dtype=torch.int64, device=dev)
+    zf = torch.zeros(umax, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    capi.check(lib.hn_export_unique_device(net._h, int(index_offset), first.data_ptr(), hits.data_ptr(), keys.data_ptr(),
+                                           states.data_ptr(), zf.data_ptr(), C.byref(nu), C.byref(pk)))
+    pay[:, 0], pay[:, 1], pay[:, 2] = first, hits.to(torch.int64), zf.to(torch.int64)
+    pay[:, 3:7], pay[:, 7:] = keys, states
+    bufs = [torch.empty_like(pay) for _ in range(world)] if rank == 0 else None
+    dist.gather(pay, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    allp = torch.cat([bufs[r][:int(counts[r])] for r in range(world)]).contiguous()
+    n = allp.shape[0]
+    F = allp[:, 0].contiguous()
+    H = allp[:, 1].to(torch.int32).contiguous()
+    Z = allp[:, 2].to(torch.uint8).contiguous()
+    K = allp[:, 3:7].contiguous()
+    S = allp[:, 7:].contiguous()
+    torch.cuda.synchronize()
+    f_out, h_out, r_out = np.empty(max(n, 1), np.int64), np.empty(max(n, 1), np.int64), np.empty(max(n, 1), np.int64)
+    ng = C.c_int64()
+    capi.check(lib.hn_merge_unique_device(net._h, n, F.data_ptr(), H.data_ptr(), K.data_ptr(), S.data_ptr(), Z.data_ptr(),
+                                          int(heads[0, 1]), capi.ptr(f_out), capi.ptr(h_out), capi.ptr(r_out), C.byref(ng)))
+    g = ng.value
+    starts = np.concatenate(([0], np.cumsum(counts)))
+    rep = r_out[:g]
+    rank_of = np.searchsorted(starts[1:], rep, side="right").astype(np.int32)
+    return {"first": f_out[:g].astype(np.int64), "hits": h_out[:g].astype(np.int64), "rank_of": rank_of,
+            "local_id": (rep - starts[rank_of]).astype(np.int32)}

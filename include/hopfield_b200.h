@@ -348,6 +348,22 @@ int hn_unique_table_stats(hn_handle h, int64_t* verified_merges, int64_t* refute
  * active and W is symmetric.                                                                                    */
 int hn_debug_integer_fields(hn_handle h, const uint64_t* states_packed, int32_t n, int32_t* fields_out, int32_t* kernel_used);
 
+/* Device-time breakdown (CUDA events, ms) of the last hn_delta_epoch / hn_thermal_delta_epoch (first five fields)
+ * and of the last hn_energy_profiles (last two): where a Delta-rule epoch spends its time.                        */
+typedef struct hn_learn_timing {
+    double sweep_fields_ms;     /* fields of the noised copies: FP64 tensor-core GEMM, 2 N^2 P flop          */
+    double sweep_ms;            /* the P one-sweep relaxations (UpdateState)                                  */
+    double dw_gemm_ms;          /* dW = sum 0.5 (t - r) t^T: FP64 tensor-core GEMM, 2 N^2 P flop              */
+    double allreduce_ms;        /* NCCL all-reduce of dW (0 without a communicator)                           */
+    double update_ms;           /* W += lr dW, zero diagonal, symmetrise                                      */
+    double energy_gemm_ms;      /* fields of the states given to hn_energy_profiles: 2 N^2 n flop             */
+    double energy_epilogue_ms;  /* energies, unstable counts, stability flags                                 */
+    int32_t targets;            /* states in the epoch                                                        */
+    int32_t reserved;
+    int64_t sweep_flips;        /* units flipped by the P sweeps (one weight column streamed per flip)        */
+} hn_learn_timing;
+int hn_last_learn_timing(hn_handle h, hn_learn_timing* t);
+
 /* Decision margin tau = tau_base + tau_per_flip * flips currently in force
  * (DESIGN.md "margin").                                                      */
 int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip);
@@ -363,6 +379,22 @@ int hn_get_margin(hn_handle h, double* tau_base, double* tau_per_flip);
  * rep_out[j] = index of the entry that supplied first_out[j].  Outputs hold up to n entries.  Pure host code.   */
 int hn_merge_unique(int64_t n, const int64_t* first, const int32_t* hits, const uint64_t* hash /* [n][2] */,
                     int64_t* first_out, int64_t* hits_out, int64_t* rep_out, int64_t* n_groups_out);
+
+/* Merge of per-GPU unique tables ON A GPU, exact (the probes are sharded, the tables meet on one rank).
+ * hn_export_unique_device gathers this handle's table (after a relaxation with HN_RELAX_DEDUP) into caller-owned
+ * DEVICE arrays — per unique attractor: global first index (index_offset + local), hits, the four key words, the packed
+ * final state and its zero-field mark — so that the entries can travel GPU to GPU (NCCL gather) instead of through the
+ * host.  Called with d_first == NULL it only reports *n_unique / *profile_keyed.
+ * hn_merge_unique_device takes the concatenation of such exports in ascending rank order (DEVICE pointers; d_keys is
+ * scratch and may be modified) and runs the same two-level table over it as a single-GPU batch does: equal
+ * sign-canonical states are merged by comparing the states, different states only after the float-profile comparison.
+ * Outputs (HOST, capacity n): the merged table in first-seen order — first index, summed hits, and rep_out[j] = which
+ * input entry supplied first_out[j] (may be NULL).  The handle's own unique table is consumed by the call.        */
+int hn_export_unique_device(hn_handle h, int64_t index_offset, int64_t* d_first, int32_t* d_hits, uint64_t* d_keys,
+                            uint64_t* d_states, uint8_t* d_zero_field, int32_t* n_unique, int32_t* profile_keyed);
+int hn_merge_unique_device(hn_handle h, int64_t n, const int64_t* d_first, const int32_t* d_hits, uint64_t* d_keys,
+                           const uint64_t* d_states, const uint8_t* d_zero_field, int32_t profile_keyed,
+                           int64_t* first_out, int64_t* hits_out, int64_t* rep_out, int64_t* n_groups_out);
 
 /* Page-locked host staging buffers (additive extension): every host pointer of this API may be pageable, but
  * probes / results in buffers from hn_host_alloc move at PCIe speed and without a staging copy (a Go binding

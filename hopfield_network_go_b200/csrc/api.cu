@@ -132,6 +132,8 @@ struct hn_handle_s {
     uint32_t result_flags = 0;
     bool result_profile_keyed = false;
     bool sweep_timed = false;
+    bool fused_flags_valid = false;   // Scratch::maxabs_bits / not_quarters describe the current W (update_constraints_i32_kernel)
+    DevBuf opA8, opB8;                // int8 operands of the learning contractions (tcgen05 path)
     cudaEvent_t ev[6] = {};
     cudaEvent_t lev[8] = {};   // learning-epoch stage events
     hn_learn_timing ltiming = {};
@@ -172,6 +174,23 @@ int ensure_margin(hn_handle h) {
     if (h->margin_valid) return HN_OK;
     HN_TRY(h->small.reserve(sizeof(Scratch)));
     Scratch* sc = h->scratch();
+    if (h->fused_flags_valid) {   // the fused update kernel already scanned the new W (max |W|, quarter test)
+        h->fused_flags_valid = false;
+        double mx = 0; int32_t nq = 1;
+        HN_CUDA_TRY(cudaMemcpyAsync(&mx, &sc->maxabs_bits, 8, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaMemcpyAsync(&nq, &sc->not_quarters, 4, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (!nq && 4.0 * (double)h->N * mx < 2251799813685248.0) {
+            // exact arithmetic (see below): no margin is ever consulted; keep a valid upper bound in tau anyway
+            const double u = 1.1102230246251565e-16, r = (double)h->N * mx;
+            h->maxabs = mx;
+            h->tau_base = 2.0 * (1.25 * h->N + 4.0) * u * r;
+            h->tau_flip = 2.0 * u * r;
+            h->exact_arith = true;
+            h->margin_valid = true;
+            return HN_OK;
+        }
+    }
     HN_CUDA_TRY(cudaMemsetAsync(&sc->rowabs_bits, 0, 16, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(&sc->not_quarters, 0, 4, h->st));
     rowabs_max_kernel<<<h->N, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, &sc->rowabs_bits);
@@ -197,7 +216,7 @@ int ensure_margin(hn_handle h) {
     return HN_OK;
 }
 
-void weights_changed(hn_handle h) { h->margin_valid = false; h->w32_valid = false; h->int_ok = false; h->key_scale = 0.0; h->k8_valid = false; }
+void weights_changed(hn_handle h) { h->fused_flags_valid = false; h->margin_valid = false; h->w32_valid = false; h->int_ok = false; h->key_scale = 0.0; h->k8_valid = false; }
 
 // exact symmetry test of the resident W (decides whether column k can be read as row k)
 int detect_symmetry(hn_handle h) {
@@ -693,6 +712,43 @@ struct OpBitsDiffG {  // scale * kscale[k] * (val_a(bitA) - val_b(bitB)); kscale
     }
 };
 
+// dW on the integer tensor path (tcgen05): the unit-major bit matrices are expanded to int8 operands A = t - r (or t),
+// B = t, and dWi = A B^T is the exact int32 contraction; the reference's updatedMatrix is s * dWi (s = 0.5 for the Delta
+// rule's 0.5 (t - r), 1 for Hebbian).  dWi overwrites the front of the float64 dW buffer.
+int contraction_int(hn_handle h, const uint64_t* bitsT, const uint64_t* bitsR, int n, ValueMap tvm, ValueMap rvm) {
+    const int N = h->N, pwords = (n + 63) / 64, pitch = round_up(n, 128);
+    HN_TRY(h->opA8.reserve((size_t)N * pitch));
+    HN_TRY(h->opB8.reserve((size_t)N * pitch));
+    const int g = grid_for((int64_t)N * (pitch / 8), 256, h->sms);
+    expand_units_i8_kernel<<<g, 256, 0, h->st>>>(bitsT, bitsR, N, pwords, n, pitch, (int)tvm.lo, (int)tvm.hi, (int)rvm.lo, (int)rvm.hi,
+                                                 h->opA8.as<int8_t>());
+    if (bitsR)
+        expand_units_i8_kernel<<<g, 256, 0, h->st>>>(bitsT, nullptr, N, pwords, n, pitch, (int)tvm.lo, (int)tvm.hi, 0, 0, h->opB8.as<int8_t>());
+    HN_CUDA_TRY(cudaGetLastError());
+    const int8_t* B8 = bitsR ? h->opB8.as<int8_t>() : h->opA8.as<int8_t>();
+    return launch_igemm_tc05_mats(h->opA8.as<int8_t>(), N, B8, N, n, pitch, reinterpret_cast<int32_t*>(h->dW), h->ldw, h->sms, h->st);
+}
+int all_reduce_dwi(hn_handle h) {   // exact integers: half the NVLink bytes of the float64 all-reduce
+    if (!h->comm) return HN_OK;
+    int32_t* d = reinterpret_cast<int32_t*>(h->dW);
+    HN_NCCL_TRY(g_nccl.AllReduce(d, d, (size_t)h->N * h->ldw, NCCL_INT32, NCCL_SUM, h->comm, h->st));
+    return HN_OK;
+}
+int apply_update_and_constraints_int(hn_handle h, double s) {
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    Scratch* sc = h->scratch();
+    HN_CUDA_TRY(cudaMemsetAsync(&sc->maxabs_bits, 0, 8, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(&sc->not_quarters, 0, 4, h->st));
+    dim3 g((h->N + 31) / 32, (h->N + 31) / 32), b(32, 8);
+    update_constraints_i32_kernel<<<g, b, 0, h->st>>>(h->W, reinterpret_cast<const int32_t*>(h->dW), h->N, h->ldw, h->cfg.learning_rate, s,
+                                                     h->cfg.force_zero_diagonal, h->cfg.force_symmetric, &sc->maxabs_bits, &sc->not_quarters);
+    HN_CUDA_TRY(cudaGetLastError());
+    h->w_symmetric = h->cfg.force_symmetric != 0;
+    weights_changed(h);
+    h->fused_flags_valid = true;
+    return HN_OK;
+}
+
 int all_reduce_dw(hn_handle h) {
     if (!h->comm) return HN_OK;
     HN_NCCL_TRY(g_nccl.AllReduce(h->dW, h->dW, (size_t)h->N * h->ldw, NCCL_FLOAT64, NCCL_SUM, h->comm, h->st));
@@ -716,10 +772,15 @@ int all_reduce_min_flag(hn_handle h, bool* flag) {
 int apply_update_and_constraints(hn_handle h);
 // a rank whose shard of this epoch's targets is empty still takes part in the all-reduce (with a zero dW) and applies
 // the same update, so replicas stay identical (iterative-batch prefixes can leave late ranks without targets)
-int empty_shard_epoch(hn_handle h) {
+int empty_shard_epoch(hn_handle h, bool integer_path, double s) {
     HN_CUDA_TRY(cudaMemsetAsync(h->dW, 0, sizeof(double) * (size_t)h->N * h->ldw, h->st));
-    HN_TRY(all_reduce_dw(h));
-    HN_TRY(apply_update_and_constraints(h));
+    if (integer_path) {
+        HN_TRY(all_reduce_dwi(h));
+        HN_TRY(apply_update_and_constraints_int(h, s));
+    } else {
+        HN_TRY(all_reduce_dw(h));
+        HN_TRY(apply_update_and_constraints(h));
+    }
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     return HN_OK;
 }
@@ -746,6 +807,16 @@ int upload_states(hn_handle h, DevBuf& buf, const uint64_t* host, int n) {
 
 int hebbian_epoch_impl(hn_handle h, const uint64_t* states, int n, ValueMap vm) {
     HN_TRY(upload_states(h, h->bitsA, states, n));
+    if (h->use_tc05) {   // exact integer contraction on the tcgen05 path, int32 all-reduce, fused update
+        const int pwords = (n + 63) / 64;
+        HN_TRY(h->bitsAT.reserve(sizeof(uint64_t) * (size_t)h->N * pwords));
+        transpose_bits_kernel<<<grid_for((int64_t)h->N * pwords, 256, h->sms), 256, 0, h->st>>>(
+            h->bitsA.as<uint64_t>(), h->bitsAT.as<uint64_t>(), h->N, h->words, n, pwords);
+        HN_CUDA_TRY(cudaGetLastError());
+        HN_TRY(contraction_int(h, h->bitsAT.as<uint64_t>(), nullptr, n, vm, vm));
+        HN_TRY(all_reduce_dwi(h));
+        return apply_update_and_constraints_int(h, 1.0);
+    }
     HN_TRY(contraction_hebbian(h, h->bitsA.as<uint64_t>(), n, vm));
     HN_TRY(all_reduce_dw(h));
     return apply_update_and_constraints(h);
@@ -836,16 +907,24 @@ int delta_epoch_impl(hn_handle h, const uint64_t* states, const uint64_t* noised
         HN_CUDA_TRY(cudaGetLastError());
         kscale = part + np + 2;
     }
-    OpBitsDiffG a{h->bitsAT.as<uint64_t>(), h->bitsCT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi, rvm.lo, rvm.hi,
-                  thermal ? 1.0 : 0.5, kscale};
-    OpBits b{h->bitsAT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi};
-    EpiStore e{h->dW, h->ldw, N, N};
     HN_CUDA_TRY(cudaEventRecord(h->lev[3], h->st));
-    HN_TRY(launch_gemm_f64(a, b, e, N, N, n, h->st));
-    HN_CUDA_TRY(cudaEventRecord(h->lev[4], h->st));
-    HN_TRY(all_reduce_dw(h));
-    HN_CUDA_TRY(cudaEventRecord(h->lev[5], h->st));
-    HN_TRY(apply_update_and_constraints(h));
+    if (!thermal && h->use_tc05) {   // dW_ij = 0.5 * sum_mu (t - r)_i t_j with the integer sum on the tcgen05 path
+        HN_TRY(contraction_int(h, h->bitsAT.as<uint64_t>(), h->bitsCT.as<uint64_t>(), n, tvm, rvm));
+        HN_CUDA_TRY(cudaEventRecord(h->lev[4], h->st));
+        HN_TRY(all_reduce_dwi(h));
+        HN_CUDA_TRY(cudaEventRecord(h->lev[5], h->st));
+        HN_TRY(apply_update_and_constraints_int(h, 0.5));
+    } else {
+        OpBitsDiffG a{h->bitsAT.as<uint64_t>(), h->bitsCT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi, rvm.lo, rvm.hi,
+                      thermal ? 1.0 : 0.5, kscale};
+        OpBits b{h->bitsAT.as<uint64_t>(), pwords, N, n, tvm.lo, tvm.hi};
+        EpiStore e{h->dW, h->ldw, N, N};
+        HN_TRY(launch_gemm_f64(a, b, e, N, N, n, h->st));
+        HN_CUDA_TRY(cudaEventRecord(h->lev[4], h->st));
+        HN_TRY(all_reduce_dw(h));
+        HN_CUDA_TRY(cudaEventRecord(h->lev[5], h->st));
+        HN_TRY(apply_update_and_constraints(h));
+    }
     HN_CUDA_TRY(cudaEventRecord(h->lev[6], h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     {
@@ -1005,7 +1084,7 @@ int hn_destroy(hn_handle h) {
     if (h->st) cudaStreamSynchronize(h->st);
     DevBuf* bufs[] = {&h->targets, &h->probes, &h->pool, &h->offsets, &h->H, &h->finals, &h->steps, &h->stable,
                       &h->flips, &h->margin, &h->dist, &h->hash, &h->energies, &h->history, &h->rep, &h->first, &h->hits,
-                      &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
+                      &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->opA8, &h->opB8, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
                       &h->bitsA, &h->bitsB, &h->bitsC, &h->bitsAT, &h->bitsCT, &h->perms, &h->eunst, &h->estab, &h->esum,
                       &h->emargin};
     for (DevBuf* b : bufs) b->release();
@@ -1226,7 +1305,7 @@ static int learn_states_impl(hn_handle h, const uint64_t* states_packed, int32_t
         for (int epoch = 0; epoch < epochs; epoch++) {
             if (!is_delta) {
                 if (mine > 0) HN_TRY(hebbian_epoch_impl(h, my_states, mine, tvm));
-                else HN_TRY(empty_shard_epoch(h));
+                else HN_TRY(empty_shard_epoch(h, h->use_tc05, 1.0));
             } else {
                 noised.assign((size_t)std::max(mine, 1) * words, 0);
                 perms.resize((size_t)std::max(mine, 1) * N);
@@ -1245,7 +1324,7 @@ static int learn_states_impl(hn_handle h, const uint64_t* states_packed, int32_t
                     HN_TRY(hn_rng_shuffle_u16(rng, pr, N));
                 }
                 if (mine > 0) HN_TRY(delta_epoch_impl(h, my_states, noised.data(), perms.data(), mine, nullptr, tvm, is_thermal));
-                else HN_TRY(empty_shard_epoch(h));
+                else HN_TRY(empty_shard_epoch(h, h->use_tc05 && !is_thermal, 0.5));
             }
             // per-target diagnostics (LearningMethod.go:45-53) on the ORIGINAL states in the network domain
             bool all_stable = true;

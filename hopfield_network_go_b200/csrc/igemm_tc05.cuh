@@ -28,8 +28,12 @@ __device__ __forceinline__ uint32_t tg_expand4(uint32_t nib, bool bipolar) {
     return bipolar ? (0xFFFFFFFFu ^ (spread * 0xFEu)) : spread;
 }
 
+// A_BITS: the A operand (rows = probes) is expanded from packed state bits by warps 2-5 (the fields contraction);
+// otherwise both operands are int8 matrices fetched by TMA (the learning contractions dW = X^T X, D^T T) and K = Kdim.
+template <bool A_BITS>
 __global__ void __launch_bounds__(TG_THREADS, 1)
-igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_b, const uint64_t* __restrict__ states, int words, int B, int N,
+igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const uint64_t* __restrict__ states, int words, int B, int N, int Kdim,
                   int bipolar, int32_t* __restrict__ G, int ldg) {
     using namespace tc05;
     extern __shared__ unsigned char tg_smem_raw[];
@@ -47,10 +51,10 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_b, const uint64_t* __r
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m_tiles = (B + TG_BM - 1) / TG_BM, n_tiles = (N + TG_BN - 1) / TG_BN;
     const int tiles = m_tiles * n_tiles;
-    const int kblocks = (N + TG_BK - 1) / TG_BK;
+    const int kblocks = (Kdim + TG_BK - 1) / TG_BK;
 
     if (tid == 0) {
-        for (int s = 0; s < TG_STAGES; s++) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TG_STAGES; s++) { mbar_init(&full[s], A_BITS ? 5 : 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         mbar_fence_init();
         tma_prefetch_desc(&map_b);
@@ -66,11 +70,12 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_b, const uint64_t* __r
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int n0 = (tile % n_tiles) * TG_BN;
+                const int n0 = (tile % n_tiles) * TG_BN, m0 = (tile / n_tiles) * TG_BM;
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full[stage], TG_B_BYTES);
+                    mbar_arrive_expect_tx(&full[stage], A_BITS ? TG_B_BYTES : TG_A_BYTES + TG_B_BYTES);
                     tma_load_2d(sB + (size_t)stage * TG_B_BYTES, &map_b, kb * TG_BK, n0, &full[stage]);
+                    if constexpr (!A_BITS) tma_load_2d(sA + (size_t)stage * TG_A_BYTES, &map_a, kb * TG_BK, m0, &full[stage]);
                     if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -102,6 +107,7 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_b, const uint64_t* __r
             }
         }
     } else if (warp < 6) {
+        if constexpr (A_BITS) {
         // ===== A producers: bits -> int8, 128-byte swizzled K-major tile =====
         const int a = tid - 64;   // 0..127
         int stage = 0; uint32_t phase = 0;
@@ -140,6 +146,7 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_b, const uint64_t* __r
                 if (lane == 0) mbar_arrive(&full[stage]);
                 if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
             }
+        }
         }
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
@@ -183,9 +190,26 @@ static inline int launch_igemm_tc05(const uint64_t* states, int words, int B, co
     CUtensorMap map;
     const int rc = tc05::make_map_bytes_2d(&map, M8, (uint64_t)ld8, (uint64_t)N, (uint64_t)ld8, TG_BN);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
-    HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+    HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     const int tiles = ((B + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-    igemm_tc05_kernel<<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, states, words, B, N, bipolar ? 1 : 0, G, ldg);
+    igemm_tc05_kernel<true><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, map, states, words, B, N, N, bipolar ? 1 : 0, G, ldg);
+    HN_CUDA_TRY(cudaGetLastError());
+    return HN_OK;
+}
+
+// C[M x N] (int32, leading dimension ldc) = A8[M x K] * B8[N x K]^T, both operands row-major int8 with pitch `pitch`
+// (a multiple of 16 bytes, K <= pitch, bytes k >= K zero).  Exact: the learning contractions' operands are in
+// {-2, .., 2}, so |C| <= 4K.
+static inline int launch_igemm_tc05_mats(const int8_t* A8, int M, const int8_t* B8, int N, int K, int pitch, int32_t* C, int ldc,
+                                         int sms, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return HN_OK;
+    CUtensorMap ma, mb;
+    int rc = tc05::make_map_bytes_2d(&ma, A8, (uint64_t)pitch, (uint64_t)M, (uint64_t)pitch, TG_BM);
+    if (rc == 0) rc = tc05::make_map_bytes_2d(&mb, B8, (uint64_t)pitch, (uint64_t)N, (uint64_t)pitch, TG_BN);
+    if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
+    HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+    const int tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
+    igemm_tc05_kernel<false><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(ma, mb, nullptr, 0, M, N, K, 0, C, ldc);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }

@@ -21,6 +21,79 @@ __global__ void apply_update_kernel(double* __restrict__ w, const double* __rest
     }
 }
 
+// ---- int8 operands of the learning contractions (tcgen05 path) ---------------------------------------------------
+// out[unit][mu] = va(bitA[unit][mu]) - (bitB ? vb(bitB[unit][mu]) : 0) for mu < P, 0 up to the pitch.  The bit matrices
+// are unit-major ([N][pwords], transpose_bits_kernel); the value maps are integers in {-1, 0, 1}, so the entries are
+// integers in [-2, 2]: t (Hebbian / the t^T factor) or t - r (twice the Delta rule's 0.5 (t - r)).
+__global__ void expand_units_i8_kernel(const uint64_t* __restrict__ bitsA, const uint64_t* __restrict__ bitsB, int n, int pwords,
+                                       int P, int pitch, int alo, int ahi, int blo, int bhi, int8_t* __restrict__ out) {
+    const int64_t total = (int64_t)n * (pitch / 8);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int unit = (int)(t / (pitch / 8)), m0 = (int)(t % (pitch / 8)) * 8;
+        uint64_t pack = 0;
+        if (m0 < P) {
+            const unsigned a = (unsigned)((bitsA[(size_t)unit * pwords + (m0 >> 6)] >> (m0 & 63)) & 0xFFu);
+            const unsigned b = bitsB ? (unsigned)((bitsB[(size_t)unit * pwords + (m0 >> 6)] >> (m0 & 63)) & 0xFFu) : 0u;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                int v = 0;
+                if (m0 + e < P) v = (((a >> e) & 1u) ? ahi : alo) - (bitsB ? (((b >> e) & 1u) ? bhi : blo) : 0);
+                pack |= (uint64_t)(uint8_t)(int8_t)v << (8 * e);
+            }
+        }
+        reinterpret_cast<uint64_t*>(out)[t] = pack;
+    }
+}
+
+// ---- W <- W + lr*(s*dWi), then enforceConstraints, in ONE pass over tile pairs (LearningRule.go:72-74 / :111-113) ----
+// dWi: the exact integer contraction (all-reduced over the ranks), s = 1 (Hebbian) or 0.5 (Delta): s*dWi is the
+// reference's updatedMatrix entry exactly, fl(lr * .) its Scale, fl(W + .) its Add; zero diagonal, then 0.5*(W + W^T)
+// from the updated values.  Also the max |W| and the "every entry a multiple of 1/4" flag ensure_margin needs.
+__global__ void update_constraints_i32_kernel(double* __restrict__ w, const int32_t* __restrict__ dwi, int n, int ld, double lr,
+                                              double s, int zero_diag, int symmetric, unsigned long long* maxabs_bits,
+                                              int32_t* not_quarters) {
+    __shared__ double ta[32][33], tb[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        double a = 0.0;
+        if (i < n && j < n) a = __dadd_rn(w[(size_t)i * ld + j], __dmul_rn(lr, s * (double)dwi[(size_t)i * ld + j]));
+        if (zero_diag && i == j) a = 0.0;
+        ta[r][tx] = a;
+        const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+        double b = 0.0;
+        if (i2 < n && j2 < n) b = __dadd_rn(w[(size_t)i2 * ld + j2], __dmul_rn(lr, s * (double)dwi[(size_t)i2 * ld + j2]));
+        if (zero_diag && i2 == j2) b = 0.0;
+        tb[r][tx] = b;
+    }
+    __syncthreads();
+    double m = 0.0;
+    bool off = false;
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        if (i < n && j < n) {
+            const double a = ta[r][tx];
+            const double v = symmetric ? __dmul_rn(0.5, __dadd_rn(a, tb[tx][r])) : a;
+            w[(size_t)i * ld + j] = v;
+            m = fmax(m, fabs(v)); off |= rint(4.0 * v) != 4.0 * v;
+        }
+        if (bi != bj) {
+            const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+            if (i2 < n && j2 < n) {
+                const double b = tb[r][tx];
+                const double v = symmetric ? __dmul_rn(0.5, __dadd_rn(b, ta[tx][r])) : b;
+                w[(size_t)i2 * ld + j2] = v;
+                m = fmax(m, fabs(v)); off |= rint(4.0 * v) != 4.0 * v;
+            }
+        }
+    }
+    if (off) *not_quarters = 1;
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if (tx == 0) atomicMax(maxabs_bits, (unsigned long long)__double_as_longlong(m));
+}
+
 // ---- enforceConstraints (HopfieldNetwork.go:55-67) --------------------------
 // zero diagonal first, then W <- 0.5*(W + W^T) from the OLD values (gonum's Add
 // against the transposed view goes through an aliasing workspace).

@@ -20,7 +20,7 @@ from oracle import orc  # noqa: E402
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("gloo")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     n, p, b = 192, 24, 120
     rng = orc.Rng(2024)
@@ -62,9 +62,16 @@ def main():
         ores = onet.relax_batch(probes.copy(), pool, threads=4)
         _, first, hits = orc.unique_table(ores["energies"])
         assert merged["first"].tolist() == first.tolist() and merged["hits"].tolist() == hits.tolist()
-        print(f"MULTI_GPU_OK world={world} unique={len(first)}")
     dist.barrier()
     net.close()
+    # the same checks bench.py runs before its timed region at n_gpus > 1 (sharded explicit epochs, sharded LearnStates
+    # with the all-reduce(min) early exit, unique tables merged on rank 0's GPU)
+    import bench
+    verdict = bench.multi_gpu_parity(hn, dist, rank, world, local)
+    assert verdict == "ok", verdict
+    if rank == 0:
+        print(f"MULTI_GPU_OK world={world} unique={len(first)} parity={verdict}")
+    dist.barrier()
     dist.destroy_process_group()
 
 

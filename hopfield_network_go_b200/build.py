@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhopfield_b200.so")
 SOURCES = ["api.cu", "host_rng.cpp"]
-HEADERS = ["common.cuh", "gemm_f64.cuh", "igemm_s8.cuh", "igemm_tc05.cuh", "tc05.cuh", "relax.cuh", "kernels_misc.cuh", "../../include/hopfield_b200.h"]
+HEADERS = ["common.cuh", "gemm_f64.cuh", "igemm_s8.cuh", "igemm_tc05.cuh", "tc05.cuh", "dense.cuh", "relax.cuh", "kernels_misc.cuh", "../../include/hopfield_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -54,7 +54,7 @@ class HnLearnTiming(C.Structure):
 
 class HnRelaxTiming(C.Structure):
     _fields_ = [("fields_ms", C.c_double), ("relax_ms", C.c_double), ("post_ms", C.c_double),
-                ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("launches", C.c_int32), ("dense_sweeps", C.c_int32), ("dense_ms", C.c_double)]
 
 
 _lib = None

@@ -14,6 +14,7 @@
 #include "gemm_f64.cuh"
 #include "igemm_s8.cuh"
 #include "igemm_tc05.cuh"
+#include "dense.cuh"
 #include "kernels_misc.cuh"
 #include "relax.cuh"
 
@@ -90,6 +91,9 @@ struct Scratch {
     unsigned long long rowabs_bits;    // ensure_margin: max_i sum_k |W_ik| (double bits)
     unsigned long long maxabs_bits;    // ensure_margin: max |W_ij|
     unsigned long long maxabs_raw_bits;  // build_integer_structure: max |Wraw_ij|
+    int32_t dense_unfinished;          // dense sweeps: probes not yet stable after the last scan
+    int32_t dense_pad;
+    unsigned long long dense_flips;    // dense sweeps: flips of the last sweep
     int32_t pair_count[2];             // dedup level 2: [0] merges of different states recorded, [1] refuted by the float profiles
     unsigned long long totals[3];      // relax: sum of flips, sweeps, margin hits over the batch (sum_counters_kernel)
 };
@@ -132,6 +136,15 @@ struct hn_handle_s {
     uint32_t result_flags = 0;
     bool result_profile_keyed = false;
     bool sweep_timed = false;
+    // dense lockstep sweeps (dense.cuh)
+    DevBuf d_mperm, d_mbb, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished;
+    CUtensorMap dense_map;
+    int dense_rows = 0;
+    uint64_t w_version = 1, pool_version = 1, dense_w_version = 0, dense_pool_version = 0;
+    bool use_dense = true;
+    int dense_max_rows = 6, dense_min_n = 2048;
+    double dense_min_flips = 110.0;   // keep sweeping densely while the last sweep flipped more than this per unfinished probe
+    int last_dense_sweeps = 0;
     bool fused_flags_valid = false;   // Scratch::maxabs_bits / not_quarters describe the current W (update_constraints_i32_kernel)
     DevBuf opA8, opB8;                // int8 operands of the learning contractions (tcgen05 path)
     cudaEvent_t ev[6] = {};
@@ -216,7 +229,7 @@ int ensure_margin(hn_handle h) {
     return HN_OK;
 }
 
-void weights_changed(hn_handle h) { h->fused_flags_valid = false; h->margin_valid = false; h->w32_valid = false; h->int_ok = false; h->key_scale = 0.0; h->k8_valid = false; }
+void weights_changed(hn_handle h) { h->w_version++; h->fused_flags_valid = false; h->margin_valid = false; h->w32_valid = false; h->int_ok = false; h->key_scale = 0.0; h->k8_valid = false; }
 
 // exact symmetry test of the resident W (decides whether column k can be read as row k)
 int detect_symmetry(hn_handle h) {
@@ -520,6 +533,82 @@ int run_dedup(hn_handle h, const uint64_t* finals, uint64_t* keys, const uint8_t
     return HN_OK;
 }
 
+// ---- dense lockstep sweeps (dense.cuh) ------------------------------------------------------------------------------
+bool dense_applicable(hn_handle h, bool serial, bool hist, const int32_t* d_offsets, int n_pool) {
+    return h->use_dense && h->use_tc05 && integer_stream(h) && h->w_symmetric && h->k8_valid && !serial && !hist && !d_offsets &&
+           h->N >= h->dense_min_n && h->N <= 4096 && n_pool >= 1 && h->cfg.max_relax_iterations >= 1;
+}
+// images of the first `rows` schedule rows: weight rows in visiting order, in-block matrices, per-position state offsets
+int prepare_dense(hn_handle h, const uint16_t* d_pool, int rows) {
+    if (h->dense_rows >= rows && h->dense_w_version == h->w_version && h->dense_pool_version == h->pool_version) return HN_OK;
+    const int N = h->N, np = ds_np(N), rp = ds_rows(N);
+    HN_TRY(h->d_mperm.reserve((size_t)rows * rp * np));
+    HN_TRY(h->d_mbb.reserve((size_t)rows * rp * DS_BLK));
+    HN_TRY(h->d_info.reserve(sizeof(DsPos) * (size_t)rows * rp));
+    for (int r = 0; r < rows; r++) {
+        const uint16_t* perm = d_pool + (size_t)r * h->ldp;
+        dense_prep_rows_kernel<<<rp, 256, 0, h->st>>>(h->K8, h->ldw, perm, N, np, h->d_mperm.as<int8_t>() + (size_t)r * rp * np);
+        dense_prep_blocks_kernel<<<(rp * DS_BLK + 255) / 256, 256, 0, h->st>>>(h->K8, h->ldw, perm, N, np, rp,
+                                                                             h->d_mbb.as<int8_t>() + (size_t)r * rp * DS_BLK,
+                                                                             h->d_info.as<DsPos>() + (size_t)r * rp);
+    }
+    HN_CUDA_TRY(cudaGetLastError());
+    const int rc = tc05::make_map_bytes_2d(&h->dense_map, h->d_mperm.p, (uint64_t)np, (uint64_t)rows * rp, (uint64_t)np, DS_BLK);
+    if (rc != 0) { set_error("cuTensorMapEncodeTiled (dense sweeps) failed (%d)", rc); return HN_E_CUDA; }
+    h->dense_rows = rows; h->dense_w_version = h->w_version; h->dense_pool_version = h->pool_version;
+    return HN_OK;
+}
+// Up to dense_max_rows lockstep sweeps over the B probes; leaves the current states in d_state, their exact fields in
+// h->H (int32) and the per-probe counters in d_sweeps / d_dflips / d_dmargin for the sparse kernel.
+int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d_pool, int n_pool, int* launches) {
+    const int N = h->N, words = h->words, np = ds_np(N), rp = ds_rows(N);
+    const int rows = std::min(std::min(h->dense_max_rows, n_pool), h->cfg.max_relax_iterations);
+    HN_TRY(prepare_dense(h, d_pool, rows));
+    HN_TRY(h->d_state.reserve(sizeof(uint64_t) * (size_t)B * words));
+    HN_TRY(h->d_sweeps.reserve(sizeof(int32_t) * (size_t)B));
+    HN_TRY(h->d_dflips.reserve(sizeof(int32_t) * (size_t)B));
+    HN_TRY(h->d_dmargin.reserve(sizeof(int32_t) * (size_t)B));
+    HN_TRY(h->d_finished.reserve((size_t)B));
+    HN_CUDA_TRY(cudaMemcpyAsync(h->d_state.p, d_probes, sizeof(uint64_t) * (size_t)B * words, cudaMemcpyDeviceToDevice, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(h->d_sweeps.p, 0, sizeof(int32_t) * (size_t)B, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(h->d_dflips.p, 0, sizeof(int32_t) * (size_t)B, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(h->d_dmargin.p, 0, sizeof(int32_t) * (size_t)B, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(h->d_finished.p, 0, (size_t)B, h->st));
+    Scratch* sc = h->scratch();
+    const size_t smem = ds_smem_bytes(N);
+    HN_CUDA_TRY(cudaFuncSetAttribute(dense_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (B + DS_T - 1) / DS_T;
+    h->last_dense_sweeps = 0;
+    for (int r = 0; r < rows; r++) {
+        HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_unfinished, 0, 16, h->st));   // unfinished, pad, flips
+        DenseParams dp{};
+        dp.N = N; dp.np = np; dp.rows_p = rp; dp.words = words; dp.B = B; dp.domain = h->cfg.domain; dp.ldw = h->ldw;
+        dp.mbb = h->d_mbb.as<int8_t>() + (size_t)r * rp * DS_BLK;
+        dp.info = h->d_info.as<DsPos>() + (size_t)r * rp;
+        dp.row_base = r * rp;
+        dp.states = h->d_state.as<uint64_t>();
+        dp.finished = h->d_finished.as<uint8_t>();
+        dp.sweeps_done = h->d_sweeps.as<int32_t>(); dp.flips_done = h->d_dflips.as<int32_t>(); dp.margin_done = h->d_dmargin.as<int32_t>();
+        dp.Wrow = h->W; dp.sweep_index = r; dp.flips_total = &sc->dense_flips;
+        dense_sweep_kernel<<<std::min(tiles, h->sms), DS_THREADS, smem, h->st>>>(h->dense_map, dp);
+        HN_CUDA_TRY(cudaGetLastError());
+        HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, reinterpret_cast<int32_t*>(h->H.as<double>())));
+        dense_scan_kernel<<<(B * 32 + 255) / 256, 256, 0, h->st>>>(reinterpret_cast<const int32_t*>(h->H.as<double>()), h->ldw,
+                                                                   h->d_state.as<uint64_t>(), words, N, B, h->cfg.domain, h->W, h->ldw,
+                                                                   h->cfg.max_relax_unstable_units, h->d_finished.as<uint8_t>(),
+                                                                   h->d_dmargin.as<int32_t>(), &sc->dense_unfinished);
+        HN_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 3;
+        h->last_dense_sweeps = r + 1;
+        int32_t unf = 0; unsigned long long fl = 0;
+        HN_CUDA_TRY(cudaMemcpyAsync(&unf, &sc->dense_unfinished, 4, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaMemcpyAsync(&fl, &sc->dense_flips, 8, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (unf == 0 || (double)fl < h->dense_min_flips * (double)unf) break;   // the sparse kernel is cheaper from here on
+    }
+    return HN_OK;
+}
+
 // The whole relaxation of B probes already on the device.
 int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d_pool, const uint16_t* d_inv,
                  int n_pool, const int32_t* d_offsets, uint32_t flags, bool want_energies, bool want_dist) {
@@ -553,6 +642,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     RelaxParams p{};
     bool profile_keyed = false;
     if (zero_matrix) {
+        HN_CUDA_TRY(cudaEventRecord(h->ev[4], h->st));
         HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
         const int wpb = 8;
         zero_matrix_relax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, h->st>>>(
@@ -568,18 +658,29 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     // initial fields: S * W^T (FP64 tensor pipe); exact integer stream: G = S * K^T on the integer tensor pipe when W is
     // symmetric (K's rows are its columns), else S * Wraw^T in float64 (half/quarter-integers: exact)
     const bool int_fields = integer_stream(h) && h->w_symmetric;
-    if (int_fields)
-        HN_TRY(integer_fields(h, d_probes, B, reinterpret_cast<int32_t*>(h->H.as<double>())));
-    else
-        HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
-    launches++;
+    const bool dense = dense_applicable(h, serial, hist, d_offsets, n_pool);
+    const uint64_t* relax_probes = d_probes;
+    h->last_dense_sweeps = 0;
+    if (dense) {   // the flip-dense first sweeps in lockstep on the tensor path; leaves states, fields and counters
+        HN_TRY(run_dense_sweeps(h, d_probes, B, d_pool, n_pool, &launches));
+        relax_probes = h->d_state.as<uint64_t>();
+        HN_CUDA_TRY(cudaEventRecord(h->ev[4], h->st));
+    } else {
+        HN_CUDA_TRY(cudaEventRecord(h->ev[4], h->st));
+        if (int_fields)
+            HN_TRY(integer_fields(h, d_probes, B, reinterpret_cast<int32_t*>(h->H.as<double>())));
+        else
+            HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
+        launches++;
+    }
     HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
 
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wrow = h->W;
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
     p.H0i = int_fields ? reinterpret_cast<const int32_t*>(h->H.as<double>()) : nullptr;
-    p.probes = d_probes; p.perm_pool = d_pool; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n_pool;
+    p.probes = relax_probes; p.perm_pool = d_pool; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n_pool;
+    if (dense) { p.sweeps_done = h->d_sweeps.as<int32_t>(); p.flips_done = h->d_dflips.as<int32_t>(); p.margin_done = h->d_dmargin.as<int32_t>(); }
     p.offsets = serial ? nullptr : d_offsets;
     p.B = B; p.max_iter = h->cfg.max_relax_iterations; p.max_unstable = h->cfg.max_relax_unstable_units;
     p.domain = h->cfg.domain; p.check_stability = 1; p.serial_stream = serial ? 1 : 0;
@@ -628,11 +729,13 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     }
     h->result_unique = dedup ? host_sc.unique_total : 0;
     h->result_profile_keyed = profile_keyed;
-    float f = 0, r = 0, q = 0;
-    cudaEventElapsedTime(&f, h->ev[0], h->ev[1]);
+    float f = 0, r = 0, q = 0, d = 0;
+    cudaEventElapsedTime(&d, h->ev[0], h->ev[4]);
+    cudaEventElapsedTime(&f, h->ev[4], h->ev[1]);
     cudaEventElapsedTime(&r, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&q, h->ev[2], h->ev[3]);
     h->timing.fields_ms = f; h->timing.relax_ms = r; h->timing.post_ms = q; h->timing.launches = launches;
+    h->timing.dense_ms = d; h->timing.dense_sweeps = h->last_dense_sweeps;
     h->result_B = B; h->result_P = want_dist ? h->P : 0; h->result_flags = flags | (want_energies ? 0x100u : 0u);
     return HN_OK;
 }
@@ -679,7 +782,7 @@ int download_results(hn_handle h, hn_relax_out* out) {
     }
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     out->total_flips = h->tot_flips; out->total_sweeps = h->tot_sweeps; out->total_margin_hits = h->tot_margin;   // summed on the device
-    out->device_ms = h->timing.fields_ms + h->timing.relax_ms + h->timing.post_ms;
+    out->device_ms = h->timing.dense_ms + h->timing.fields_ms + h->timing.relax_ms + h->timing.post_ms;
     return HN_OK;
 }
 
@@ -1073,6 +1176,10 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     }
     h->w_symmetric = true;  // the zero matrix
     if (const char* e = getenv("HN_IGEMM")) h->use_tc05 = std::strcmp(e, "mma_sync") != 0;
+    if (const char* e = getenv("HN_DENSE")) h->use_dense = std::atoi(e) != 0;
+    if (const char* e = getenv("HN_DENSE_ROWS")) h->dense_max_rows = std::max(1, std::atoi(e));
+    if (const char* e = getenv("HN_DENSE_MIN_N")) h->dense_min_n = std::max(32, std::atoi(e));
+    if (const char* e = getenv("HN_DENSE_MIN_FLIPS")) h->dense_min_flips = std::atof(e);
     *out = h;
     return HN_OK;
 }
@@ -1084,7 +1191,8 @@ int hn_destroy(hn_handle h) {
     if (h->st) cudaStreamSynchronize(h->st);
     DevBuf* bufs[] = {&h->targets, &h->probes, &h->pool, &h->offsets, &h->H, &h->finals, &h->steps, &h->stable,
                       &h->flips, &h->margin, &h->dist, &h->hash, &h->energies, &h->history, &h->rep, &h->first, &h->hits,
-                      &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->opA8, &h->opB8, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
+                      &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->opA8, &h->opB8, &h->d_mperm, &h->d_mbb, &h->d_info,
+                      &h->d_state, &h->d_sweeps, &h->d_dflips, &h->d_dmargin, &h->d_finished, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
                       &h->bitsA, &h->bitsB, &h->bitsC, &h->bitsAT, &h->bitsCT, &h->perms, &h->eunst, &h->estab, &h->esum,
                       &h->emargin};
     for (DevBuf* b : bufs) b->release();
@@ -1434,6 +1542,7 @@ int hn_relax_batch(hn_handle h, const uint64_t* probes_packed, int32_t n_probes,
     HN_TRY(validate_pool_host(h, perm_pool, n_pool));
     HN_TRY(upload_states(h, h->probes, probes_packed, n_probes));
     HN_TRY(upload_pool(h, perm_pool, n_pool, h->pool, &h->d_pool, &h->d_inv));
+    h->pool_version++;
     h->resident_B = n_probes; h->resident_pool = n_pool;
     const int32_t* d_off = nullptr;
     if (offsets && !(flags & HN_RELAX_SERIAL_STREAM)) {
@@ -1467,6 +1576,7 @@ int hn_upload_perm_pool(hn_handle h, const uint16_t* perm_pool, int32_t n_pool) 
     HN_TRY(set_device(h));
     HN_TRY(validate_pool_host(h, perm_pool, n_pool));
     HN_TRY(upload_pool(h, perm_pool, n_pool, h->pool, &h->d_pool, &h->d_inv));
+    h->pool_version++;
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     h->resident_pool = n_pool;
     return HN_OK;
@@ -1520,7 +1630,7 @@ int hn_relax_resident(hn_handle h, uint32_t flags, double* device_ms) {
     HN_TRY(set_device(h));
     HN_TRY(relax_device(h, h->probes.as<uint64_t>(), h->resident_B, h->d_pool, h->d_inv,
                         h->resident_pool, nullptr, flags, false, true));
-    if (device_ms) *device_ms = h->timing.fields_ms + h->timing.relax_ms + h->timing.post_ms;
+    if (device_ms) *device_ms = h->timing.dense_ms + h->timing.fields_ms + h->timing.relax_ms + h->timing.post_ms;
     return HN_OK;
 }
 int hn_download_results(hn_handle h, hn_relax_out* out) {

@@ -69,6 +69,9 @@ struct RelaxParams {
     uint64_t* hash;          // [B][4] unique-table keys (zeroed by the host): [0..1] canonical-state hash, [2..3] exact-profile key; or nullptr
     uint8_t* zero_field;     // [B] 1 iff the final state has a unit with an exactly zero field (dedup key, see same_canonical)
     uint64_t* history;       // [B][max_iter+1][words] or nullptr
+    const int32_t* sweeps_done;   // [B] or nullptr: sweeps already done by the dense lockstep kernel (dense.cuh)
+    const int32_t* flips_done;    // [B] or nullptr: flips counted so far
+    const int32_t* margin_done;   // [B] or nullptr: exact ties counted so far
     int32_t* work_counter;   // dynamic probe scheduler
     int32_t* status;         // [0]: set to 1 when the pool was exhausted; [1]: rows needed
 };
@@ -306,10 +309,18 @@ relax_kernel(RelaxParams p) {
             for (int w = tid; w < p.words * 2; w += RELAX_THREADS) hw[w] = w < nbw ? s_bits[w] : 0u;
         }
 
-        int flips = 0, margin = 0, sweeps = 0, is_stable = 0, pool_fail = 0;
+        int flips = p.flips_done ? p.flips_done[pi] : 0, margin = p.margin_done ? p.margin_done[pi] : 0;
+        int sweeps = p.sweeps_done ? p.sweeps_done[pi] : 0, is_stable = 0, pool_fail = 0;
         if (tid == 0) { s_zero_field = 0; s_tz[0] = s_tz[1] = 0ULL; }   // rare-path state lives in shared memory, not registers
-        for (int sweep = 0; sweep < p.max_iter; sweep++) {
-            const long long row = rowbase + sweep;
+        // A probe handed over by the dense lockstep sweeps (dense.cuh) arrives with `sweeps` sweeps done and the fields of
+        // its current state: the stability test that follows its last sweep comes first (its exact ties were already
+        // counted by the scan that handed it over), then the sweeps continue at pool row rowbase + sweeps.
+        bool precheck = sweeps > 0 && p.check_stability;
+        for (;;) {
+            const bool count_margin = !precheck;
+            if (!precheck) {
+            if (sweeps >= p.max_iter) break;
+            const long long row = rowbase + sweeps;
             if (row >= p.n_pool || row < 0) { pool_fail = 1; break; }
             const uint16_t* permrow = p.perm_pool + (size_t)row * p.ldp;
             const uint16_t* invrow = p.inv_pool + (size_t)row * p.ldp;
@@ -486,6 +497,8 @@ relax_kernel(RelaxParams p) {
                 for (int w = tid; w < p.words * 2; w += RELAX_THREADS) hw[w] = w < nbw ? s_bits[w] : 0u;
             }
             if (!p.check_stability) continue;
+            }
+            precheck = false;
 
             // ---- stability: #{i : e_i > 0}, e_i = -0.5 h_i v_i  (HopfieldNetwork.go:214-225) ----
             uint32_t cnt = 0;
@@ -505,7 +518,7 @@ relax_kernel(RelaxParams p) {
                 for (int r = 0; r < UPT; r++)
                     if ((__double2hiint(h[r]) & 0x7FFFFFFF) < T) z++;
                 const int nz = (int)block_sum(z);
-                margin += nz;
+                if (count_margin) margin += nz;
                 if (tid == 0) s_zero_field = nz > 0;
                 if ((int)cnt <= p.max_unstable) { is_stable = 1; break; }
                 continue;
@@ -526,7 +539,7 @@ relax_kernel(RelaxParams p) {
                 if (cmin == RELAX_NONE) break;
                 last = (int)cmin;
                 const double hx = exact_field(last);
-                margin++;
+                if (count_margin) margin++;
                 const uint32_t ob = (s_bits[last >> 5] >> (last & 31)) & 1u;
                 if (hx == 0.0 && tid == 0) {   // unit energy -0.5*(+0*v): a zero whose sign follows v
                     s_zero_field = 1;

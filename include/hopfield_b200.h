@@ -326,11 +326,12 @@ int hn_download_results(hn_handle h, hn_relax_out* out);
 
 /* Timing breakdown of the last relaxation (CUDA events, ms) and kernel count */
 typedef struct hn_relax_timing {
-    double fields_ms;   /* initial fields GEMM  */
+    double fields_ms;   /* initial fields GEMM (0 when the dense sweeps supplied the fields) */
     double relax_ms;    /* relaxation kernel    */
     double post_ms;     /* energies / dedup     */
     int32_t launches;   /* kernels launched     */
-    int32_t reserved;
+    int32_t dense_sweeps; /* sweeps taken by the dense lockstep kernel (tcgen05 path) before the hand-over */
+    double dense_ms;    /* those sweeps, with the fields contraction and stability scan after each of them */
 } hn_relax_timing;
 int hn_last_relax_timing(hn_handle h, hn_relax_timing* t);
 

@@ -575,6 +575,8 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
     HN_CUDA_TRY(cudaMemsetAsync(h->d_dmargin.p, 0, sizeof(int32_t) * (size_t)B, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(h->d_finished.p, 0, (size_t)B, h->st));
     Scratch* sc = h->scratch();
+    const bool prof = getenv("HN_DENSE_PROF") != nullptr;
+    if (prof) { HN_TRY(h->partial.reserve(64)); HN_CUDA_TRY(cudaMemsetAsync(h->partial.p, 0, 64, h->st)); }
     const size_t smem = ds_smem_bytes(N);
     HN_CUDA_TRY(cudaFuncSetAttribute(dense_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (B + DS_T - 1) / DS_T;
@@ -590,6 +592,7 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         dp.finished = h->d_finished.as<uint8_t>();
         dp.sweeps_done = h->d_sweeps.as<int32_t>(); dp.flips_done = h->d_dflips.as<int32_t>(); dp.margin_done = h->d_dmargin.as<int32_t>();
         dp.Wrow = h->W; dp.sweep_index = r; dp.flips_total = &sc->dense_flips;
+        dp.prof = prof ? h->partial.as<unsigned long long>() : nullptr;
         dense_sweep_kernel<<<std::min(tiles, h->sms), DS_THREADS, smem, h->st>>>(h->dense_map, dp);
         HN_CUDA_TRY(cudaGetLastError());
         HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, reinterpret_cast<int32_t*>(h->H.as<double>())));
@@ -604,6 +607,15 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         HN_CUDA_TRY(cudaMemcpyAsync(&unf, &sc->dense_unfinished, 4, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaMemcpyAsync(&fl, &sc->dense_flips, 8, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (prof) {   // clock cycles of CTA 0 by phase, per block of 32 positions (diagnostic)
+            unsigned long long pc[8];
+            HN_CUDA_TRY(cudaMemcpy(pc, h->partial.p, 64, cudaMemcpyDeviceToHost));
+            HN_CUDA_TRY(cudaMemsetAsync(h->partial.p, 0, 64, h->st));
+            const double nb = (double)(rp / DS_BLK) * (double)((tiles + h->sms - 1) / h->sms);
+            fprintf(stderr, "[dense prof] sweep %d flips/probe %.0f | per block (clk): wait MMA %.0f, tmem->smem %.0f, gather %.0f, decide %.0f, "
+                            "end barrier %.0f | MMA warp: wait decisions %.0f, issue+stream %.0f\n", r + 1, (double)fl / std::max(1, B),
+                    pc[0] / nb, pc[1] / nb, pc[2] / nb, pc[3] / nb, pc[4] / nb, pc[5] / nb, pc[6] / nb);
+        }
         if (unf == 0 || (double)fl < h->dense_min_flips * (double)unf) break;   // the sparse kernel is cheaper from here on
     }
     return HN_OK;
@@ -1315,6 +1327,28 @@ int hn_thermal_delta_epoch(hn_handle h, const uint64_t* states_packed, const uin
     HN_TRY(set_device(h));
     HN_TRY(validate_pool_host(h, perms, n));
     return delta_epoch_impl(h, states_packed, noised_packed, perms, n, relaxed_out, domain_values(h->cfg.domain), true);
+}
+
+int hn_rule_epoch(hn_handle h, int32_t rule, const uint64_t* states_packed, const uint64_t* noised_packed,
+                  const uint16_t* perms, int32_t n, uint64_t* relaxed_out) {
+    if (!check_handle(h, "hn_rule_epoch")) return HN_E_INVALID;
+    if (rule < 0 || rule > 5 || n <= 0 || !states_packed) { set_error("hn_rule_epoch: bad argument (rule %d, n %d)", rule, n); return HN_E_INVALID; }
+    const bool is_thermal = rule == HN_RULE_THERMAL_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA;
+    const bool is_delta = rule == HN_RULE_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_DELTA || is_thermal;
+    if (is_delta && (!noised_packed || !perms)) { set_error("hn_rule_epoch: the delta rules need the noised copies and the update orders"); return HN_E_INVALID; }
+    HN_TRY(set_device(h));
+    // value map the rule sees (see learn_states_impl): mapped Hebbian re-activates with the BINARY manager (sic,
+    // LearningRule.go:80), the mapped delta rules with the Bipolar manager (:119, :163)
+    ValueMap tvm = domain_values(h->cfg.domain);
+    if (rule == HN_RULE_BIPOLAR_MAPPED_HEBBIAN) tvm = ValueMap{0.0, 1.0};
+    if (rule == HN_RULE_BIPOLAR_MAPPED_DELTA || rule == HN_RULE_BIPOLAR_MAPPED_THERMAL_DELTA) tvm = ValueMap{-1.0, 1.0};
+    if (!is_delta) {
+        HN_TRY(hebbian_epoch_impl(h, states_packed, n, tvm));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        return HN_OK;
+    }
+    HN_TRY(validate_pool_host(h, perms, n));
+    return delta_epoch_impl(h, states_packed, noised_packed, perms, n, relaxed_out, tvm, is_thermal);
 }
 
 int hn_enforce_constraints(hn_handle h) {

@@ -11,10 +11,12 @@
 //     To fill the 128-row MMA with 32 probes, K is cut in four quarters: row (q, p) of A holds quarter q of probe p's
 //     state, row (q', i) of B quarter q' of position i's weight row; the four diagonal 32x32 blocks of the 128x128
 //     result are the partial fields and are summed after tcgen05.ld (one TMEM sub-partition per quarter).
-//   * one warp then takes the 32 decisions of the block in order, one probe per lane: a flip at position i corrects the
-//     fields of the later positions of the block with the 32x32 in-block matrix (dp4a against a byte selector), is
-//     written into S8 (so the next block's contraction sees it) and into the packed state in global memory.
-//     An exact tie (integer field 0) is decided as the sparse kernel decides it: the float64 row in gonum's order.
+//   * four warps then take the 32 decisions of the block in order, four threads per probe (each owns eight positions):
+//     a flip at position i is told to the probe's threads by one width-4 shuffle and corrects the fields of the later
+//     positions of the block with the 32x32 in-block matrix (dp4a against a byte selector); it is written into S8 (so
+//     the next block's contraction sees it) and into the packed state in global memory.  An exact tie (integer field
+//     0) stops the probe; the warp then decides it as the sparse kernel does — the float64 row in gonum's order — and
+//     the probe resumes from that position.
 //   * after the sweep the exact fields of all probes are recomputed by the integer fields GEMM (igemm_tc05.cuh) and a scan
 //     (dense_scan_kernel) takes the reference's stability test, counts its ties, and freezes the probes that are stable.
 // After a few such sweeps the probes are handed to the sparse kernel with their sweep / flip / tie counters
@@ -37,7 +39,7 @@ constexpr uint32_t DS_NULL = 0x80000000u;
 static inline int ds_np(int n) { return (n + 511) / 512 * 512; }        // padded K: four quarters of whole 128-byte chunks
 static inline int ds_rows(int n) { return (n + 31) / 32 * 32; }         // padded positions
 static inline size_t ds_smem_bytes(int n) {
-    return (size_t)DS_T * ds_np(n) + (size_t)DS_STAGES * DS_STAGE_BYTES + 3 * 32 * 33 * 4 + 1024 + 256 + 1024;
+    return (size_t)DS_T * ds_np(n) + (size_t)DS_STAGES * DS_STAGE_BYTES + 4 * 32 * 33 * 4 + 1024 + 256 + 256 + 1024;
 }
 
 // Per schedule row: the byte image with its rows in visiting order (zero padded to [rowsP][Np]), the in-block 32x32
@@ -90,6 +92,7 @@ struct DenseParams {
     const double* Wrow;        // float64 W (exact ties)
     int sweep_index;           // this is sweep number sweep_index + 1
     unsigned long long* flips_total;   // sum of this sweep's flips
+    unsigned long long* prof;          // optional [8]: clock cycles of CTA 0 by phase (HN_DENSE_PROF=1), else nullptr
 };
 
 // exact field of unit k for probe row p of the tile (DotUnitary order, see exact_field_warp) with the state read from S8
@@ -121,9 +124,11 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
     const int kq = p.np / 4, KC = kq / 128, nblk = p.rows_p / DS_BLK;
     unsigned char* s8 = smem;                                              // KC panels of 128 rows x 128 B
     unsigned char* ring = smem + (size_t)DS_T * p.np;                     // == KC * 16384
-    int* part = reinterpret_cast<int*>(ring + DS_STAGES * DS_STAGE_BYTES); // [3][32][33]
-    uint32_t* mbb_s = reinterpret_cast<uint32_t*>(part + 3 * 32 * 33);     // [32][8] words: in-block matrix of the current block
-    uint64_t* bars = reinterpret_cast<uint64_t*>(mbb_s + 256);
+    int* part = reinterpret_cast<int*>(ring + DS_STAGES * DS_STAGE_BYTES); // [4][32][33] partial fields [quarter][probe][position]
+    uint32_t* mbb_s = reinterpret_cast<uint32_t*>(part + 4 * 32 * 33);     // [32][8] words: in-block matrix of the current block
+    uint32_t* pos_off = mbb_s + 256;                                       // [32] state-byte offsets of the block's positions
+    uint32_t* pos_unit = pos_off + 32;                                     // [32] their units
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pos_unit + 32);
     uint64_t* full = bars;                  // [stages] TMA
     uint64_t* empty = bars + DS_STAGES;     // [stages] tcgen05.commit
     uint64_t* d_full = bars + 2 * DS_STAGES;        // block's fields are in TMEM
@@ -202,10 +207,15 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
         } else if (warp == 1) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc = idesc_i8(128, 128, true, true);
+            const bool prof = p.prof && blockIdx.x == 0 && lane == 0;
+            long long pm_wait = 0, pm_issue = 0;
             for (int b = 0; b < nblk; b++) {
+                const long long m0 = prof ? clock64() : 0;
                 mbar_wait(s8_ready, s8_par);
                 s8_par ^= 1u;
                 tc_fence_after_sync();
+                const long long m1 = prof ? clock64() : 0;
+                pm_wait += m1 - m0;
                 for (int kc = 0; kc < KC; kc++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after_sync();
@@ -221,24 +231,27 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                     __syncwarp();
                     if (++stage == DS_STAGES) { stage = 0; phase ^= 1u; }
                 }
+                if (prof) pm_issue += clock64() - m1;
             }
+            if (prof) { atomicAdd(p.prof + 5, (unsigned long long)pm_wait); atomicAdd(p.prof + 6, (unsigned long long)pm_issue); }
             mbar_wait(s8_ready, s8_par);   // the arrival that follows the last block's decisions: keeps the parity in step
             s8_par ^= 1u;
         } else if (warp >= 4) {
-            // ===== partial fields out of TMEM (warp 4+q: quarter q), decisions (warp 4) =====
+            // ===== warps 4-7: partial fields out of TMEM (warp 4+q reads quarter q), then the block's 32 decisions =====
+            // Decisions: 4 threads per probe (8 probes per warp), thread (probe, slice) owns positions 8*slice .. +7 of the
+            // block.  Step i: the owning thread decides and tells the probe's four threads (one width-4 shuffle); every
+            // thread then corrects ITS eight fields with the in-block matrix row (8 dp4a).  Fields of positions already
+            // decided are dead, so nothing is masked.
             const int q = warp - 4;
-            const int pg = p0 + lane;                                  // this lane's probe (warp 4)
-            bool active = false;
-            int flips = 0, ties = 0;
-            uint32_t* gbits = nullptr;
-            if (q == 0) {
-                active = pg < p.B && !p.finished[pg];
-                gbits = reinterpret_cast<uint32_t*>(p.states + (size_t)(pg < p.B ? pg : 0) * p.words);
-            }
-            const uint32_t prow = (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u;
+            const int pl = 8 * q + (lane >> 2), sl = lane & 3;       // tile-local probe and slice of this thread
+            const int pg = p0 + pl;
+            const bool active = pg < p.B && !p.finished[pg];
+            uint32_t* gbits = reinterpret_cast<uint32_t*>(p.states + (size_t)(pg < p.B ? pg : 0) * p.words);
+            const uint32_t prow = (uint32_t)(pl >> 3) * 1024u + (uint32_t)(pl & 7) * 128u;
             const int delta = bipolar ? 2 : 1, bias = bipolar ? 1 : 0;
             const int low_byte = bipolar ? 0xFF : 0x00;
-            // next block's in-block matrix row and position info, fetched one block ahead (warp 4 only)
+            int flips = 0, ties = 0;
+            // warp 4: the next block's in-block matrix row and position info, fetched one block ahead (lane = row)
             uint4 mrow0 = make_uint4(0, 0, 0, 0), mrow1 = mrow0;
             DsPos pinfo{DS_NULL, 0xFFFFu};
             if (q == 0) {
@@ -246,92 +259,125 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 mrow0 = __ldg(src); mrow1 = __ldg(src + 1);
                 pinfo = p.info[lane];
             }
+            const bool prof = p.prof && blockIdx.x == 0 && tid == 128;
+            long long pd[5] = {0, 0, 0, 0, 0};
             for (int b = 0; b < nblk; b++) {
+                const long long t0 = prof ? clock64() : 0;
                 mbar_wait(d_full, d_par);
                 d_par ^= 1u;
                 tc_fence_after_sync();
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q), r);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                if (q > 0) {
-                    int* dst = part + ((q - 1) * 32 + lane) * 33;
+                const long long t1 = prof ? clock64() : 0;
+                {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q), r);
+                    tmem_ld_wait();
+                    tc_fence_before_sync();
+                    int* dst = part + (q * 32 + lane) * 33;   // [quarter][probe][position]
 #pragma unroll
                     for (int i = 0; i < 32; i++) dst[i] = (int)r[i];
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // warps 4-7: the partials are in shared memory
-                if (q > 0) continue;
+                if (q == 0) {
+                    mbb_s[lane * 8 + 0] = mrow0.x; mbb_s[lane * 8 + 1] = mrow0.y; mbb_s[lane * 8 + 2] = mrow0.z; mbb_s[lane * 8 + 3] = mrow0.w;
+                    mbb_s[lane * 8 + 4] = mrow1.x; mbb_s[lane * 8 + 5] = mrow1.y; mbb_s[lane * 8 + 6] = mrow1.z; mbb_s[lane * 8 + 7] = mrow1.w;
+                    pos_off[lane] = pinfo.off; pos_unit[lane] = pinfo.unit;
+                    if (b + 1 < nblk) {   // prefetch; lands while the tensor core works on the next block
+                        const uint4* src = reinterpret_cast<const uint4*>(p.mbb + ((size_t)(b + 1) * 32 + lane) * 32);
+                        mrow0 = __ldg(src); mrow1 = __ldg(src + 1);
+                        pinfo = p.info[(b + 1) * DS_BLK + lane];
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // partials, matrix and position info are in shared memory
+                const long long t2 = prof ? clock64() : 0;
 
-                // ---- warp 4: one probe per lane, the block's 32 decisions in order ----
-                int u[32];
+                int u8[8];
+                uint32_t soff[8], unit8[8], sb = 0, vm = 0;
 #pragma unroll
-                for (int i = 0; i < 32; i++)
-                    u[i] = (int)r[i] + part[lane * 33 + i] + part[(32 + lane) * 33 + i] + part[(64 + lane) * 33 + i] - bias;
-                mbb_s[lane * 8 + 0] = mrow0.x; mbb_s[lane * 8 + 1] = mrow0.y; mbb_s[lane * 8 + 2] = mrow0.z; mbb_s[lane * 8 + 3] = mrow0.w;
-                mbb_s[lane * 8 + 4] = mrow1.x; mbb_s[lane * 8 + 5] = mrow1.y; mbb_s[lane * 8 + 6] = mrow1.z; mbb_s[lane * 8 + 7] = mrow1.w;
-                const DsPos cur = pinfo;
-                if (b + 1 < nblk) {   // prefetch the next block's row / info; lands while the tensor core works on it
-                    const uint4* src = reinterpret_cast<const uint4*>(p.mbb + ((size_t)(b + 1) * 32 + lane) * 32);
-                    mrow0 = __ldg(src); mrow1 = __ldg(src + 1);
-                    pinfo = p.info[(b + 1) * DS_BLK + lane];
+                for (int e = 0; e < 8; e++) {
+                    const int idx = 8 * sl + e;
+                    u8[e] = part[pl * 33 + idx] + part[(32 + pl) * 33 + idx] + part[(64 + pl) * 33 + idx] + part[(96 + pl) * 33 + idx] - bias;
+                    const uint32_t o = pos_off[idx];
+                    const bool valid = o != DS_NULL;
+                    soff[e] = valid ? (o & 0xFFFFFFu) + prow + ((((o >> 24) ^ (uint32_t)pl) & 7u) << 4) : 0u;
+                    unit8[e] = pos_unit[idx];
+                    const int sv = (int)(signed char)s8[soff[e]];
+                    sb |= (uint32_t)(valid && sv > 0) << e;
+                    vm |= (uint32_t)valid << e;
                 }
-                __syncwarp();
+                if (!active) vm = 0;
+                // the in-block matrix entries this thread needs, all 32 rows up front: nothing in the decision chain
+                // below waits for memory (a warp issues in order: one exposed load latency per step would triple it)
+                uint2 wv[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const uint32_t off_i = __shfl_sync(0xFFFFFFFFu, cur.off, i);
-                    if (off_i == DS_NULL) continue;   // padding position (uniform)
-                    const uint32_t chunk = off_i >> 24;
-                    unsigned char* sp = s8 + (off_i & 0xFFFFFFu) + prow + (((chunk ^ (uint32_t)lane) & 7u) << 4);
-                    const int sv = (int)(signed char)*sp;
-                    const int bit = sv > 0 ? 1 : 0;
-                    const int U = u[i];
-                    bool cand = active && (bit ? (U < 0) : (U >= 0));
-                    const bool tie = active && (U + 2 * bit == 0);
-                    int nb = bit ^ 1;
-                    const uint32_t tmask = __ballot_sync(0xFFFFFFFFu, tie);
-                    if (tmask) {   // exact tie of the true field: the reference's float64 dot product decides (rare)
-                        const int k = (int)__shfl_sync(0xFFFFFFFFu, cur.unit, i);
-                        uint32_t m = tmask;
-                        __syncwarp();   // the lanes' earlier flips in S8 are read by lanes 0-3 below
-                        while (m) {
-                            const int pl = __ffs((int)m) - 1;
-                            m &= m - 1;
-                            const double hx = ds_exact_field(p.Wrow + (size_t)k * p.ldw, s8, pl, p.N, kq, lane);
-                            if (lane == pl) { nb = hx > 0.0 ? 1 : 0; ties++; }
-                        }
-                    }
-                    const bool flip = cand && (nb != bit);
-                    const int ds = flip ? (bit ? -delta : delta) : 0;
-                    if (flip) *sp = (unsigned char)(bit ? low_byte : 0x01);
-                    if (__ballot_sync(0xFFFFFFFFu, flip)) {
-                        const uint4 w0 = *reinterpret_cast<const uint4*>(mbb_s + i * 8);
-                        const uint4 w1 = *reinterpret_cast<const uint4*>(mbb_s + i * 8 + 4);
-                        const uint32_t wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                        const uint32_t d8 = (uint32_t)ds & 0xFFu;
-                        const uint32_t sel[4] = {d8, d8 << 8, d8 << 16, d8 << 24};
+                for (int i = 0; i < 32; i++) wv[i] = *reinterpret_cast<const uint2*>(mbb_s + i * 8 + 2 * sl);
+                int start = 0, res_nb = 0;
+                bool have_res = false;
+                uint32_t fm = 0, applied = 0;   // flips of my eight positions: decided / already written out
+                const long long t3 = prof ? clock64() : 0;
+                for (;;) {
+                    bool stalled = false;
 #pragma unroll
-                        for (int j = i + 1; j < 32; j++) u[j] = __dp4a((int)wv[j >> 2], (int)sel[j & 3], u[j]);
+                    for (int i = 0; i < 32; i++) {
+                        const int so = i >> 3, e = i & 7;
+                        const int U = u8[e], bit = (int)((sb >> e) & 1u);
+                        const bool elig = sl == so && ((vm >> e) & 1u) && !stalled && i >= start;
+                        const bool cand = bit ? (U < 0) : (U >= 0);
+                        const bool pre = have_res && i == start;            // an exact tie resolved before this pass
+                        const bool stall_now = elig && (U + 2 * bit == 0) && !pre;   // exact tie of the true field: stop here
+                        const int nb = pre ? res_nb : (bit ^ 1);
+                        const bool flip = elig && !stall_now && cand && nb != bit;
+                        int msg = (flip ? (bit ? -delta : delta) : 0) & 0xFF;
+                        if (stall_now) msg |= 0x100;
+                        fm |= (uint32_t)flip << e;
+                        msg = __shfl_sync(0xFFFFFFFFu, msg, so, 4);          // the owner's verdict to the probe's four threads
+                        if (msg & 0x100) { stalled = true; start = i; }
+                        const uint32_t d8 = (uint32_t)msg & 0xFFu;
+                        const int s0 = (int)d8, s1 = (int)(d8 << 8), s2 = (int)(d8 << 16), s3 = (int)(d8 << 24);
+                        u8[0] = __dp4a((int)wv[i].x, s0, u8[0]); u8[1] = __dp4a((int)wv[i].x, s1, u8[1]);
+                        u8[2] = __dp4a((int)wv[i].x, s2, u8[2]); u8[3] = __dp4a((int)wv[i].x, s3, u8[3]);
+                        u8[4] = __dp4a((int)wv[i].y, s0, u8[4]); u8[5] = __dp4a((int)wv[i].y, s1, u8[5]);
+                        u8[6] = __dp4a((int)wv[i].y, s2, u8[6]); u8[7] = __dp4a((int)wv[i].y, s3, u8[7]);
                     }
-                    if (flip) flips++;
-                    // packed state in global memory: fire-and-forget toggle of this probe's bit
+                    // write this pass's flips into S8 (next block's contraction, exact ties below) and the packed state
                     {
-                        const uint32_t k = __shfl_sync(0xFFFFFFFFu, cur.unit, i);
-                        if (flip) atomicXor(gbits + (k >> 5), 1u << (k & 31));
+                        const uint32_t pend = fm & ~applied;
+                        applied = fm;
+#pragma unroll
+                        for (int e = 0; e < 8; e++)
+                            if ((pend >> e) & 1u) {
+                                s8[soff[e]] = (unsigned char)(((sb >> e) & 1u) ? low_byte : 0x01);
+                                atomicXor(gbits + (unit8[e] >> 5), 1u << (unit8[e] & 31));   // fire and forget
+                            }
+                        flips += __popc(pend);
+                    }
+                    if (!stalled) start = 32;
+                    uint32_t m = __ballot_sync(0xFFFFFFFFu, stalled && sl == 0);
+                    if (!m) break;
+                    __syncwarp();   // this block's flips already written into S8 are read by lanes 0-3 below
+                    while (m) {     // exact ties: the reference's float64 dot product decides (rare)
+                        const int l0 = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        const int pos = __shfl_sync(0xFFFFFFFFu, start, l0);
+                        const int k = (int)pos_unit[pos];
+                        const double hx = ds_exact_field(p.Wrow + (size_t)k * p.ldw, s8, 8 * q + (l0 >> 2), p.N, kq, lane);
+                        if ((lane & ~3) == l0) { have_res = true; res_nb = hx > 0.0 ? 1 : 0; if (sl == 0) ties++; }
                     }
                 }
+                const long long t4 = prof ? clock64() : 0;
                 fence_proxy_async_smem();   // the flips written into S8 must be visible to the next block's MMAs
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s8_ready);
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // all four warps are done with the block
+                if (tid == 128) mbar_arrive(s8_ready);
+                if (prof) { const long long t5 = clock64(); pd[0] += t1 - t0; pd[1] += t2 - t1; pd[2] += t3 - t2; pd[3] += t4 - t3; pd[4] += t5 - t4; }
             }
-            if (q == 0 && pg < p.B && active) {
+            if (prof) for (int i = 0; i < 5; i++) atomicAdd(p.prof + i, (unsigned long long)pd[i]);
+            flips += __shfl_xor_sync(0xFFFFFFFFu, flips, 1); flips += __shfl_xor_sync(0xFFFFFFFFu, flips, 2);
+            ties += __shfl_xor_sync(0xFFFFFFFFu, ties, 1); ties += __shfl_xor_sync(0xFFFFFFFFu, ties, 2);
+            if (sl == 0 && active) {
                 p.sweeps_done[pg] = p.sweep_index + 1;
                 p.flips_done[pg] += flips;
                 p.margin_done[pg] += ties;
             }
-            if (q == 0) {
-                unsigned long long f = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)flips);
-                if (lane == 0 && f) atomicAdd(p.flips_total, f);
-            }
+            const unsigned wf = __reduce_add_sync(0xFFFFFFFFu, sl == 0 ? (unsigned)flips : 0u);
+            if (lane == 0 && wf) atomicAdd(p.flips_total, (unsigned long long)wf);
         }
         __syncthreads();   // every role has finished the tile: S8 may be rewritten
     }

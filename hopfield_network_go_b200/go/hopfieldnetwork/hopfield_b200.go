@@ -1,14 +1,15 @@
 // Package hopfieldnetwork — cgo drop-in for hmcalister/hopfield/hopfieldnetwork.
 //
-// This file replaces HopfieldNetwork.go, LearningRule.go and LearningMethod.go of the reference
-// (the enum declarations of LearningRule.go:32-39 / LearningMethod.go:22-25 and the whole of
-// HopfieldNetworkBuilder.go are kept as they are, except that Build() calls newDeviceNetwork below
-// instead of allocating a gonum matrix).  Every method forwards to libhopfield_b200.so
+// This file replaces HopfieldNetwork.go, LearningRule.go and LearningMethod.go of the reference (the enum
+// declarations of LearningRule.go:32-39 / LearningMethod.go:22-25 are kept as they are); the edited
+// HopfieldNetworkBuilder.go next to it keeps every setter and the four Build panics and calls newDeviceNetwork
+// below instead of allocating a gonum matrix.  Every method forwards to libhopfield_b200.so
 // (include/hopfield_b200.h); the sub-packages domain, noiseapplication, distancemeasure, datacollector,
 // states and hopfieldutils are used unchanged.
 //
-// NOT COMPILED in the build environment of this repository (no Go toolchain there): it documents the
-// binding a maintainer adds.  INTEGRATION.md walks through it.
+// UNVERIFIED: NOT COMPILED in the build environment of this repository (no Go toolchain there, and the gonum /
+// x-exp module sources are absent).  It documents the binding a maintainer adds; every behaviour lives in the C
+// library, where the ctypes tests reach it.  INTEGRATION.md walks through it.
 package hopfieldnetwork
 
 /*
@@ -149,6 +150,29 @@ func (network *HopfieldNetwork) SetMatrix(m *mat.Dense) {
 func (network *HopfieldNetwork) GetDimension() int                 { return network.dimension }
 func (network *HopfieldNetwork) GetLearnedStates() []*mat.VecDense { return network.targetStates }
 
+// HopfieldNetworkSummary / GetNetworkSummary: HopfieldNetwork.go:124-149, consumed by main.go:262-279.
+type HopfieldNetworkSummary struct {
+	Matrix                         *mat.Dense
+	Dimension                      int
+	ForceSymmetric                 bool
+	ForceZeroDiagonal              bool
+	Epochs                         int
+	MaximumRelaxationUnstableUnits int
+	MaximumRelaxationIterations    int
+	LearningNoiseScale             float64
+	UnitsUpdatedPerStep            int
+}
+
+func (network *HopfieldNetwork) GetNetworkSummary() *HopfieldNetworkSummary {
+	return &HopfieldNetworkSummary{
+		Matrix: network.GetMatrix(), Dimension: network.dimension,
+		ForceSymmetric: network.forceSymmetric, ForceZeroDiagonal: network.forceZeroDiagonal,
+		Epochs: network.epochs, MaximumRelaxationUnstableUnits: network.maximumRelaxationUnstableUnits,
+		MaximumRelaxationIterations: network.maximumRelaxationIterations,
+		LearningNoiseScale: network.learningNoiseScale, UnitsUpdatedPerStep: network.unitsUpdatedPerStep,
+	}
+}
+
 func (network *HopfieldNetwork) String() string {
 	return fmt.Sprintf("Hopfield Network\n\tDomain: %s\n\tDimension: %d\n", network.domain, network.dimension)
 }
@@ -183,8 +207,14 @@ func (network *HopfieldNetwork) AllUnitEnergies(state *mat.VecDense) []float64 {
 	p, _, _ := network.energyProfiles([]*mat.VecDense{state}, true)
 	return p[0]
 }
+
+// UnitEnergy is the reference's SCALAR loop (BipolarDomainManager.go:29-37; BinaryDomainManager.go:43-52 with its
+// "-1" per term), not AllUnitEnergies(state)[unitIndex]: hn_unit_energy reproduces both.
 func (network *HopfieldNetwork) UnitEnergy(state *mat.VecDense, unitIndex int) float64 {
-	return network.AllUnitEnergies(state)[unitIndex]
+	packed := network.pack([]*mat.VecDense{state})
+	var e C.double
+	check(C.hn_unit_energy(network.handle, (*C.uint64_t)(unsafe.Pointer(&packed[0])), 1, C.int32_t(unitIndex), &e))
+	return float64(e)
 }
 func (network *HopfieldNetwork) StateEnergy(state *mat.VecDense) float64 {
 	_, _, t := network.energyProfiles([]*mat.VecDense{state}, false)
@@ -206,41 +236,46 @@ func (network *HopfieldNetwork) AllStatesAreStable(states []*mat.VecDense) bool 
 
 // ---- learning (HopfieldNetwork.go:254-262, LearningMethod.go:38-89, LearningRule.go:64-126) ----
 
-// learnEpoch applies the selected rule once.  Noise and update orders are drawn from the network RNG in
-// the reference's order (per target: noise draws, then the N-1 shuffle draws) and uploaded.
+// learnEpoch applies the selected rule once (all six of LearningRule.go:32-39) through hn_rule_epoch.  Noise and
+// update orders are drawn from the network RNG — the reference's own golang.org/x/exp/rand stream — in the reference's
+// order (per target: the noise draws, then the N-1 shuffle draws of UpdateState, LearningRule.go:98-104) and uploaded.
+// The bipolar-mapped rules re-activate copies of the targets with the manager the reference names before the noise is
+// applied (:78-87, :117-126, :161-170); the library applies the same value map on its side.
 func (network *HopfieldNetwork) learnEpoch(states []*mat.VecDense) {
 	packed := network.pack(states)
 	sp := (*C.uint64_t)(unsafe.Pointer(&packed[0]))
+	rule := C.int32_t(network.learningRuleEnum)
 	switch network.learningRuleEnum {
-	case HebbianLearningRule:
-		check(C.hn_hebbian_epoch(network.handle, sp, C.int32_t(len(states))))
-	case DeltaLearningRule, ThermalDeltaLearningRule:
-		noised := make([]*mat.VecDense, len(states))
-		perms := make([]uint16, len(states)*network.dimension)
-		for i, s := range states {
-			noised[i] = mat.VecDenseCopyOf(s)
-			network.learningNoiseMethod(network.randomGenerator, noised[i], network.learningNoiseScale)
-			network.domainManager.ActivationFunction(noised[i])
-			idx := make([]int, network.dimension)
-			for k := range idx {
-				idx[k] = k
-			}
-			hopfieldutils.ShuffleList(network.randomGenerator, idx)
-			for k, u := range idx {
-				perms[i*network.dimension+k] = uint16(u)
-			}
-		}
-		np := network.pack(noised)
-		if network.learningRuleEnum == ThermalDeltaLearningRule { // LearningRule.go:129-158
-			check(C.hn_thermal_delta_epoch(network.handle, sp, (*C.uint64_t)(unsafe.Pointer(&np[0])),
-				(*C.uint16_t)(unsafe.Pointer(&perms[0])), C.int32_t(len(states)), nil))
-		} else {
-			check(C.hn_delta_epoch(network.handle, sp, (*C.uint64_t)(unsafe.Pointer(&np[0])),
-				(*C.uint16_t)(unsafe.Pointer(&perms[0])), C.int32_t(len(states)), nil))
-		}
-	default:
-		panic("learning rule not available on the device path")
+	case HebbianLearningRule, BipolarMappedHebbianLearningRule:
+		check(C.hn_rule_epoch(network.handle, rule, sp, nil, nil, C.int32_t(len(states)), nil))
+		return
 	}
+	var mapper domain.DomainManager // nil: the rule sees the targets as they are
+	switch network.learningRuleEnum {
+	case BipolarMappedDeltaLearningRule, BipolarMappedThermalDeltaLearningRule:
+		mapper = &domain.BipolarDomainManager{}
+	}
+	noised := make([]*mat.VecDense, len(states))
+	perms := make([]uint16, len(states)*network.dimension)
+	idx := make([]int, network.dimension)
+	for i, s := range states {
+		noised[i] = mat.VecDenseCopyOf(s)
+		if mapper != nil {
+			mapper.ActivationFunction(noised[i])
+		}
+		network.learningNoiseMethod(network.randomGenerator, noised[i], network.learningNoiseScale)
+		network.domainManager.ActivationFunction(noised[i])
+		for k := range idx { // UpdateState rebuilds the identity list every call (HopfieldNetwork.go:281)
+			idx[k] = k
+		}
+		hopfieldutils.ShuffleList(network.randomGenerator, idx)
+		for k, u := range idx {
+			perms[i*network.dimension+k] = uint16(u)
+		}
+	}
+	np := network.pack(noised)
+	check(C.hn_rule_epoch(network.handle, rule, sp, (*C.uint64_t)(unsafe.Pointer(&np[0])),
+		(*C.uint16_t)(unsafe.Pointer(&perms[0])), C.int32_t(len(states)), nil))
 }
 
 func (network *HopfieldNetwork) fullSet(states []*mat.VecDense) []*datacollector.LearnStateData {

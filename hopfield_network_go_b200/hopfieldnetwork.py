@@ -262,6 +262,23 @@ class HopfieldNetwork:
         check(capi.load().hn_thermal_delta_epoch(self._h, ptr(p), ptr(q), ptr(pm), p.shape[0], ptr(rel)))
         return rel
 
+    def rule_epoch(self, rule: int, states, noised=None, perms=None) -> Optional[np.ndarray]:
+        """One application of any learning rule with explicit noised copies / update orders (hn_rule_epoch)."""
+        p = self._packed(states)
+        q = None if noised is None else self._packed(noised)
+        pm = None if perms is None else np.ascontiguousarray(perms, dtype=np.uint16)
+        rel = np.empty_like(p) if q is not None else None
+        check(capi.load().hn_rule_epoch(self._h, int(rule), ptr(p), ptr(q), ptr(pm), p.shape[0], ptr(rel)))
+        return rel
+
+    def GetNetworkSummary(self) -> dict:
+        """HopfieldNetworkSummary (HopfieldNetwork.go:124-149): the fields main.go:262-279 writes to networkSummary.pq."""
+        return {"Matrix": self.GetMatrix(), "Dimension": self.dimension, "ForceSymmetric": bool(self._cfg.force_symmetric),
+                "ForceZeroDiagonal": bool(self._cfg.force_zero_diagonal), "Epochs": self.epochs,
+                "MaximumRelaxationUnstableUnits": self._cfg.max_relax_unstable_units,
+                "MaximumRelaxationIterations": self._cfg.max_relax_iterations,
+                "LearningNoiseScale": self.noise_scale, "UnitsUpdatedPerStep": self.unitsUpdatedPerStep}
+
     def enforce_constraints(self) -> None:
         check(capi.load().hn_enforce_constraints(self._h))
 

@@ -190,6 +190,16 @@ int hn_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* n
 int hn_thermal_delta_epoch(hn_handle h, const uint64_t* states_packed, const uint64_t* noised_packed,
                            const uint16_t* perms, int32_t n, uint64_t* relaxed_out);
 
+/* One application of ANY of the six learning rules (LearningRule.go:32-39, getLearningRule :50-61) with the RNG-derived
+ * inputs explicit — what a host that owns the reference's own generator (the Go package: golang.org/x/exp/rand) calls
+ * once per epoch so that the random stream stays its own.  The bipolar-mapped rules (:78-87, :117-126, :161-170) see
+ * the targets re-activated by the manager the reference names (mapped Hebbian: the BINARY manager, as written there);
+ * noised copies and relaxed copies always carry the network domain's values.  noised_packed / perms are ignored by
+ * the Hebbian rules (may be NULL).  Same device work and all-reduce behaviour as hn_hebbian_epoch / hn_delta_epoch /
+ * hn_thermal_delta_epoch, which are the rule-0 / 2 / 4 cases.                                                     */
+int hn_rule_epoch(hn_handle h, int32_t rule, const uint64_t* states_packed, const uint64_t* noised_packed,
+                  const uint16_t* perms, int32_t n, uint64_t* relaxed_out);
+
 /* enforceConstraints (HopfieldNetwork.go:55-67) on the resident W. */
 int hn_enforce_constraints(hn_handle h);
 

@@ -137,7 +137,7 @@ struct hn_handle_s {
     bool result_profile_keyed = false;
     bool sweep_timed = false;
     // dense lockstep sweeps (dense.cuh)
-    DevBuf d_mperm, d_mbb, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished;
+    DevBuf d_mperm, d_mbb, d_mx, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished;
     CUtensorMap dense_map;
     int dense_rows = 0;
     uint64_t w_version = 1, pool_version = 1, dense_w_version = 0, dense_pool_version = 0;
@@ -544,12 +544,14 @@ int prepare_dense(hn_handle h, const uint16_t* d_pool, int rows) {
     const int N = h->N, np = ds_np(N), rp = ds_rows(N);
     HN_TRY(h->d_mperm.reserve((size_t)rows * rp * np));
     HN_TRY(h->d_mbb.reserve((size_t)rows * rp * DS_BLK));
+    HN_TRY(h->d_mx.reserve((size_t)rows * rp * DS_BLK));
     HN_TRY(h->d_info.reserve(sizeof(DsPos) * (size_t)rows * rp));
     for (int r = 0; r < rows; r++) {
         const uint16_t* perm = d_pool + (size_t)r * h->ldp;
         dense_prep_rows_kernel<<<rp, 256, 0, h->st>>>(h->K8, h->ldw, perm, N, np, h->d_mperm.as<int8_t>() + (size_t)r * rp * np);
         dense_prep_blocks_kernel<<<(rp * DS_BLK + 255) / 256, 256, 0, h->st>>>(h->K8, h->ldw, perm, N, np, rp,
                                                                              h->d_mbb.as<int8_t>() + (size_t)r * rp * DS_BLK,
+                                                                             h->d_mx.as<int8_t>() + (size_t)r * rp * DS_BLK,
                                                                              h->d_info.as<DsPos>() + (size_t)r * rp);
     }
     HN_CUDA_TRY(cudaGetLastError());
@@ -586,6 +588,7 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         DenseParams dp{};
         dp.N = N; dp.np = np; dp.rows_p = rp; dp.words = words; dp.B = B; dp.domain = h->cfg.domain; dp.ldw = h->ldw;
         dp.mbb = h->d_mbb.as<int8_t>() + (size_t)r * rp * DS_BLK;
+        dp.mx = h->d_mx.as<int8_t>() + (size_t)r * rp * DS_BLK;
         dp.info = h->d_info.as<DsPos>() + (size_t)r * rp;
         dp.row_base = r * rp;
         dp.states = h->d_state.as<uint64_t>();
@@ -1203,7 +1206,7 @@ int hn_destroy(hn_handle h) {
     if (h->st) cudaStreamSynchronize(h->st);
     DevBuf* bufs[] = {&h->targets, &h->probes, &h->pool, &h->offsets, &h->H, &h->finals, &h->steps, &h->stable,
                       &h->flips, &h->margin, &h->dist, &h->hash, &h->energies, &h->history, &h->rep, &h->first, &h->hits,
-                      &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->opA8, &h->opB8, &h->d_mperm, &h->d_mbb, &h->d_info,
+                      &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->opA8, &h->opB8, &h->d_mperm, &h->d_mbb, &h->d_mx, &h->d_info,
                       &h->d_state, &h->d_sweeps, &h->d_dflips, &h->d_dmargin, &h->d_finished, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
                       &h->bitsA, &h->bitsB, &h->bitsC, &h->bitsAT, &h->bitsCT, &h->perms, &h->eunst, &h->estab, &h->esum,
                       &h->emargin};

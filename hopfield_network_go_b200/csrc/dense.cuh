@@ -19,6 +19,8 @@
 //     the probe resumes from that position.
 //   * after the sweep the exact fields of all probes are recomputed by the integer fields GEMM (igemm_tc05.cuh) and a scan
 //     (dense_scan_kernel) takes the reference's stability test, counts its ties, and freezes the probes that are stable.
+//   * the contraction of block b+1 overlaps the decisions of block b: it reads S8 without block b's flips, whose effect on
+//     block b+1's fields is added afterwards from a precomputed 32x32 cross matrix (two TMEM accumulators alternate).
 // After a few such sweeps the probes are handed to the sparse kernel with their sweep / flip / tie counters
 // (RelaxParams::sweeps_done ...).  Every quantity is an exact integer: results are bit-identical to the sparse path.
 #pragma once
@@ -39,7 +41,7 @@ constexpr uint32_t DS_NULL = 0x80000000u;
 static inline int ds_np(int n) { return (n + 511) / 512 * 512; }        // padded K: four quarters of whole 128-byte chunks
 static inline int ds_rows(int n) { return (n + 31) / 32 * 32; }         // padded positions
 static inline size_t ds_smem_bytes(int n) {
-    return (size_t)DS_T * ds_np(n) + (size_t)DS_STAGES * DS_STAGE_BYTES + 4 * 32 * 33 * 4 + 1024 + 256 + 256 + 1024;
+    return (size_t)DS_T * ds_np(n) + (size_t)DS_STAGES * DS_STAGE_BYTES + 4 * 32 * 33 * 4 + 2 * 1024 + 256 + 256 + 1024;
 }
 
 // Per schedule row: the byte image with its rows in visiting order (zero padded to [rowsP][Np]), the in-block 32x32
@@ -58,14 +60,16 @@ __global__ void dense_prep_rows_kernel(const int8_t* __restrict__ k8, int ld8, c
     }
 }
 __global__ void dense_prep_blocks_kernel(const int8_t* __restrict__ k8, int ld8, const uint16_t* __restrict__ perm, int n, int np,
-                                         int rows_p, int8_t* __restrict__ mbb, DsPos* __restrict__ info) {
+                                         int rows_p, int8_t* __restrict__ mbb, int8_t* __restrict__ mx, DsPos* __restrict__ info) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows_p * DS_BLK) return;
     const int pos = t / DS_BLK, j = t % DS_BLK, b = pos / DS_BLK;
-    const int other = b * DS_BLK + j;
-    int8_t v = 0;
+    const int other = b * DS_BLK + j, prev = (b - 1) * DS_BLK + j;
+    int8_t v = 0, x = 0;
     if (pos < n && other < n) v = k8[(size_t)perm[pos] * ld8 + perm[other]];
+    if (pos < n && b > 0 && prev < n) x = k8[(size_t)perm[pos] * ld8 + perm[prev]];
     mbb[t] = v;   // [b][i][j] = M[unit(b,i)][unit(b,j)]
+    mx[t] = x;    // [b][i][j] = M[unit(b,i)][unit(b-1,j)]: what the previous block's flips do to this block's fields
     if (j == 0) {
         DsPos d{DS_NULL, 0xFFFFu};
         if (pos < n) {
@@ -82,6 +86,7 @@ __global__ void dense_prep_blocks_kernel(const int8_t* __restrict__ k8, int ld8,
 struct DenseParams {
     int N, np, rows_p, words, B, domain, ldw;
     const int8_t* mbb;         // [rows_p/32][32][32] of this schedule row
+    const int8_t* mx;          // [rows_p/32][32][32] cross matrices block b <- block b-1
     const DsPos* info;         // [rows_p]
     int row_base;              // first row of this schedule row inside the tensor map (r * rows_p)
     uint64_t* states;          // [B][words] current packed states (updated in place)
@@ -115,6 +120,28 @@ __device__ __forceinline__ double ds_exact_field(const double* __restrict__ row,
     return __shfl_sync(0xFFFFFFFFu, __dadd_rn(pair, hi), 0);
 }
 
+// exact_field_warp (relax.cuh) on the packed state in GLOBAL memory, read past L1 (the state is toggled by atomics)
+__device__ __forceinline__ double exact_field_warp_cg(const double* __restrict__ row, const uint32_t* bits, int N, int domain, int lane) {
+    const double lowv = domain == HN_DOMAIN_BINARY ? 0.0 : -1.0;
+    double acc = 0.0;
+    if (lane < 4) {
+        const int n4 = N & ~3;
+        for (int j = lane; j < n4; j += 4) {
+            const uint32_t b = (__ldcg(bits + (j >> 5)) >> (j & 31)) & 1u;
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(row + j), b ? 1.0 : lowv));
+        }
+        if (lane == 0)
+            for (int j = n4; j < N; j++) {
+                const uint32_t b = (__ldcg(bits + (j >> 5)) >> (j & 31)) & 1u;
+                acc = __dadd_rn(acc, __dmul_rn(__ldg(row + j), b ? 1.0 : lowv));
+            }
+    }
+    const double other = __shfl_down_sync(0xFFFFFFFFu, acc, 2);
+    const double pair = __dadd_rn(acc, other);
+    const double hi = __shfl_down_sync(0xFFFFFFFFu, pair, 1);
+    return __shfl_sync(0xFFFFFFFFu, __dadd_rn(pair, hi), 0);
+}
+
 __global__ void __launch_bounds__(DS_THREADS, 1)
 dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
     using namespace tc05;
@@ -126,7 +153,8 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
     unsigned char* ring = smem + (size_t)DS_T * p.np;                     // == KC * 16384
     int* part = reinterpret_cast<int*>(ring + DS_STAGES * DS_STAGE_BYTES); // [4][32][33] partial fields [quarter][probe][position]
     uint32_t* mbb_s = reinterpret_cast<uint32_t*>(part + 4 * 32 * 33);     // [32][8] words: in-block matrix of the current block
-    uint32_t* pos_off = mbb_s + 256;                                       // [32] state-byte offsets of the block's positions
+    uint32_t* mx_s = mbb_s + 256;                                          // [32][8] words: cross matrix (previous block's flips)
+    uint32_t* pos_off = mx_s + 256;                                        // [32] state-byte offsets of the block's positions
     uint32_t* pos_unit = pos_off + 32;                                     // [32] their units
     uint64_t* bars = reinterpret_cast<uint64_t*>(pos_unit + 32);
     uint64_t* full = bars;                  // [stages] TMA
@@ -146,14 +174,14 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
         mbar_fence_init();
         tma_prefetch_desc(&map_w);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    if (warp == 1) tmem_alloc(tmem_slot, 256);   // two accumulators: block b+1 is contracted while block b is decided
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
     int stage = 0; uint32_t phase = 0;      // ring position (TMA producer and MMA issuer each keep their own copy)
-    uint32_t s8_par = 0;                    // MMA issuer: parity of the next s8_ready completion (nblk + 1 per tile)
+    uint32_t s8_par = 0;                    // MMA issuer: parity of the next s8_ready completion (nblk per tile)
     uint32_t d_par = 0;                     // warps 4-7: parity of the next d_full completion (nblk per tile)
 
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -224,7 +252,8 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                         const uint64_t db = smem_desc_k128(smem_u32(ring + (size_t)stage * DS_STAGE_BYTES));
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            mma_i8(tmem_base, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (uint32_t)((kc | j) != 0));
+                            mma_i8(tmem_base + (uint32_t)((b & 1) * 128), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
+                                   (uint32_t)((kc | j) != 0));
                         mma_commit(&empty[stage]);
                         if (kc == KC - 1) mma_commit(d_full);
                     }
@@ -234,10 +263,11 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 if (prof) pm_issue += clock64() - m1;
             }
             if (prof) { atomicAdd(p.prof + 5, (unsigned long long)pm_wait); atomicAdd(p.prof + 6, (unsigned long long)pm_issue); }
-            mbar_wait(s8_ready, s8_par);   // the arrival that follows the last block's decisions: keeps the parity in step
-            s8_par ^= 1u;
         } else if (warp >= 4) {
             // ===== warps 4-7: partial fields out of TMEM (warp 4+q reads quarter q), then the block's 32 decisions =====
+            // Pipeline: the contraction of block b+1 runs while block b is decided.  It reads S8 WITHOUT block b's flips;
+            // their effect on block b+1's fields is added from the 32x32 cross matrix before block b+1 is decided, and
+            // the flips are written into S8 right after the contraction of block b+1 has completed.
             // Decisions: 4 threads per probe (8 probes per warp), thread (probe, slice) owns positions 8*slice .. +7 of the
             // block.  Step i: the owning thread decides and tells the probe's four threads (one width-4 shuffle); every
             // thread then corrects ITS eight fields with the in-block matrix row (8 dp4a).  Fields of positions already
@@ -251,14 +281,16 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
             const int delta = bipolar ? 2 : 1, bias = bipolar ? 1 : 0;
             const int low_byte = bipolar ? 0xFF : 0x00;
             int flips = 0, ties = 0;
-            // warp 4: the next block's in-block matrix row and position info, fetched one block ahead (lane = row)
-            uint4 mrow0 = make_uint4(0, 0, 0, 0), mrow1 = mrow0;
+            // warp 4: the next block's matrix rows and position info, fetched one block ahead (lane = row)
+            uint4 mrow0 = make_uint4(0, 0, 0, 0), mrow1 = mrow0, xrow0 = mrow0, xrow1 = mrow0;
             DsPos pinfo{DS_NULL, 0xFFFFu};
             if (q == 0) {
                 const uint4* src = reinterpret_cast<const uint4*>(p.mbb + (size_t)lane * 32);
                 mrow0 = __ldg(src); mrow1 = __ldg(src + 1);
                 pinfo = p.info[lane];
             }
+            uint32_t dsw_prev[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // the previous block's flips of my probe, one signed byte per position
+            uint32_t soff_prev[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fm_prev = 0, sb_prev = 0;   // ... and mine, not yet written into S8
             const bool prof = p.prof && blockIdx.x == 0 && tid == 128;
             long long pd[5] = {0, 0, 0, 0, 0};
             for (int b = 0; b < nblk; b++) {
@@ -267,9 +299,13 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 d_par ^= 1u;
                 tc_fence_after_sync();
                 const long long t1 = prof ? clock64() : 0;
+                // the contraction of block b is complete: the previous block's flips may enter S8 now, before block b+1's starts
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    if ((fm_prev >> e) & 1u) s8[soff_prev[e]] = (unsigned char)(((sb_prev >> e) & 1u) ? low_byte : 0x01);
                 {
                     uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q), r);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((b & 1) * 128 + 32 * q), r);
                     tmem_ld_wait();
                     tc_fence_before_sync();
                     int* dst = part + (q * 32 + lane) * 33;   // [quarter][probe][position]
@@ -279,14 +315,20 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 if (q == 0) {
                     mbb_s[lane * 8 + 0] = mrow0.x; mbb_s[lane * 8 + 1] = mrow0.y; mbb_s[lane * 8 + 2] = mrow0.z; mbb_s[lane * 8 + 3] = mrow0.w;
                     mbb_s[lane * 8 + 4] = mrow1.x; mbb_s[lane * 8 + 5] = mrow1.y; mbb_s[lane * 8 + 6] = mrow1.z; mbb_s[lane * 8 + 7] = mrow1.w;
+                    mx_s[lane * 8 + 0] = xrow0.x; mx_s[lane * 8 + 1] = xrow0.y; mx_s[lane * 8 + 2] = xrow0.z; mx_s[lane * 8 + 3] = xrow0.w;
+                    mx_s[lane * 8 + 4] = xrow1.x; mx_s[lane * 8 + 5] = xrow1.y; mx_s[lane * 8 + 6] = xrow1.z; mx_s[lane * 8 + 7] = xrow1.w;
                     pos_off[lane] = pinfo.off; pos_unit[lane] = pinfo.unit;
-                    if (b + 1 < nblk) {   // prefetch; lands while the tensor core works on the next block
+                    if (b + 1 < nblk) {   // prefetch; lands while this block is decided
                         const uint4* src = reinterpret_cast<const uint4*>(p.mbb + ((size_t)(b + 1) * 32 + lane) * 32);
+                        const uint4* srx = reinterpret_cast<const uint4*>(p.mx + ((size_t)(b + 1) * 32 + lane) * 32);
                         mrow0 = __ldg(src); mrow1 = __ldg(src + 1);
+                        xrow0 = __ldg(srx); xrow1 = __ldg(srx + 1);
                         pinfo = p.info[(b + 1) * DS_BLK + lane];
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // partials, matrix and position info are in shared memory
+                fence_proxy_async_smem();   // the flips written into S8 must be visible to the next block's MMAs
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // S8 is up to date; partials, matrices, position info are in shared memory
+                if (tid == 128 && b + 1 < nblk) mbar_arrive(s8_ready);   // the contraction of block b+1 may start
                 const long long t2 = prof ? clock64() : 0;
 
                 int u8[8];
@@ -294,12 +336,19 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     const int idx = 8 * sl + e;
-                    u8[e] = part[pl * 33 + idx] + part[(32 + pl) * 33 + idx] + part[(64 + pl) * 33 + idx] + part[(96 + pl) * 33 + idx] - bias;
+                    int acc = part[pl * 33 + idx] + part[(32 + pl) * 33 + idx] + part[(64 + pl) * 33 + idx] + part[(96 + pl) * 33 + idx] - bias;
+                    // what the previous block's flips (not seen by this block's contraction) do to this field
+                    const uint4 x0 = *reinterpret_cast<const uint4*>(mx_s + idx * 8), x1 = *reinterpret_cast<const uint4*>(mx_s + idx * 8 + 4);
+                    acc = __dp4a((int)x0.x, (int)dsw_prev[0], acc); acc = __dp4a((int)x0.y, (int)dsw_prev[1], acc);
+                    acc = __dp4a((int)x0.z, (int)dsw_prev[2], acc); acc = __dp4a((int)x0.w, (int)dsw_prev[3], acc);
+                    acc = __dp4a((int)x1.x, (int)dsw_prev[4], acc); acc = __dp4a((int)x1.y, (int)dsw_prev[5], acc);
+                    acc = __dp4a((int)x1.z, (int)dsw_prev[6], acc); acc = __dp4a((int)x1.w, (int)dsw_prev[7], acc);
+                    u8[e] = acc;
                     const uint32_t o = pos_off[idx];
                     const bool valid = o != DS_NULL;
                     soff[e] = valid ? (o & 0xFFFFFFu) + prow + ((((o >> 24) ^ (uint32_t)pl) & 7u) << 4) : 0u;
                     unit8[e] = pos_unit[idx];
-                    const int sv = (int)(signed char)s8[soff[e]];
+                    const int sv = (int)(signed char)s8[soff[e]];   // a unit is visited once per sweep: its byte is still the tile's initial one
                     sb |= (uint32_t)(valid && sv > 0) << e;
                     vm |= (uint32_t)valid << e;
                 }
@@ -309,9 +358,10 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 uint2 wv[32];
 #pragma unroll
                 for (int i = 0; i < 32; i++) wv[i] = *reinterpret_cast<const uint2*>(mbb_s + i * 8 + 2 * sl);
+                uint32_t dsw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 int start = 0, res_nb = 0;
                 bool have_res = false;
-                uint32_t fm = 0, applied = 0;   // flips of my eight positions: decided / already written out
+                uint32_t fm = 0, applied = 0;   // flips of my eight positions: decided / already sent to the packed state
                 const long long t3 = prof ? clock64() : 0;
                 for (;;) {
                     bool stalled = false;
@@ -331,41 +381,44 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                         msg = __shfl_sync(0xFFFFFFFFu, msg, so, 4);          // the owner's verdict to the probe's four threads
                         if (msg & 0x100) { stalled = true; start = i; }
                         const uint32_t d8 = (uint32_t)msg & 0xFFu;
+                        dsw[i >> 2] |= d8 << (8 * (i & 3));
                         const int s0 = (int)d8, s1 = (int)(d8 << 8), s2 = (int)(d8 << 16), s3 = (int)(d8 << 24);
                         u8[0] = __dp4a((int)wv[i].x, s0, u8[0]); u8[1] = __dp4a((int)wv[i].x, s1, u8[1]);
                         u8[2] = __dp4a((int)wv[i].x, s2, u8[2]); u8[3] = __dp4a((int)wv[i].x, s3, u8[3]);
                         u8[4] = __dp4a((int)wv[i].y, s0, u8[4]); u8[5] = __dp4a((int)wv[i].y, s1, u8[5]);
                         u8[6] = __dp4a((int)wv[i].y, s2, u8[6]); u8[7] = __dp4a((int)wv[i].y, s3, u8[7]);
                     }
-                    // write this pass's flips into S8 (next block's contraction, exact ties below) and the packed state
+                    // this pass's flips go to the packed state in global memory now (fire and forget); S8 gets them when
+                    // the next block's contraction, which must not see them, has completed
                     {
                         const uint32_t pend = fm & ~applied;
                         applied = fm;
 #pragma unroll
                         for (int e = 0; e < 8; e++)
-                            if ((pend >> e) & 1u) {
-                                s8[soff[e]] = (unsigned char)(((sb >> e) & 1u) ? low_byte : 0x01);
-                                atomicXor(gbits + (unit8[e] >> 5), 1u << (unit8[e] & 31));   // fire and forget
-                            }
+                            if ((pend >> e) & 1u) atomicXor(gbits + (unit8[e] >> 5), 1u << (unit8[e] & 31));
                         flips += __popc(pend);
                     }
                     if (!stalled) start = 32;
                     uint32_t m = __ballot_sync(0xFFFFFFFFu, stalled && sl == 0);
                     if (!m) break;
-                    __syncwarp();   // this block's flips already written into S8 are read by lanes 0-3 below
-                    while (m) {     // exact ties: the reference's float64 dot product decides (rare)
+                    __threadfence();   // the toggles above are performed before the packed state is read below
+                    __syncwarp();
+                    while (m) {     // exact ties: the reference's float64 dot product on the probe's current state decides (rare)
                         const int l0 = __ffs((int)m) - 1;
                         m &= m - 1;
                         const int pos = __shfl_sync(0xFFFFFFFFu, start, l0);
                         const int k = (int)pos_unit[pos];
-                        const double hx = ds_exact_field(p.Wrow + (size_t)k * p.ldw, s8, 8 * q + (l0 >> 2), p.N, kq, lane);
+                        const int pt = p0 + 8 * q + (l0 >> 2);
+                        const double hx = exact_field_warp_cg(p.Wrow + (size_t)k * p.ldw,
+                                                              reinterpret_cast<const uint32_t*>(p.states + (size_t)pt * p.words), p.N, p.domain, lane);
                         if ((lane & ~3) == l0) { have_res = true; res_nb = hx > 0.0 ? 1 : 0; if (sl == 0) ties++; }
                     }
                 }
                 const long long t4 = prof ? clock64() : 0;
-                fence_proxy_async_smem();   // the flips written into S8 must be visible to the next block's MMAs
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // all four warps are done with the block
-                if (tid == 128) mbar_arrive(s8_ready);
+#pragma unroll
+                for (int e = 0; e < 8; e++) { dsw_prev[e] = dsw[e]; soff_prev[e] = soff[e]; }
+                fm_prev = fm; sb_prev = sb;
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // all four warps are done with the block's shared scratch
                 if (prof) { const long long t5 = clock64(); pd[0] += t1 - t0; pd[1] += t2 - t1; pd[2] += t3 - t2; pd[3] += t4 - t3; pd[4] += t5 - t4; }
             }
             if (prof) for (int i = 0; i < 5; i++) atomicAdd(p.prof + i, (unsigned long long)pd[i]);
@@ -383,7 +436,7 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 128);
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 // Stability test after a dense sweep (HopfieldNetwork.go:214-225) on the exact fields G = M s of the current states

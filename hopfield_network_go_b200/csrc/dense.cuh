@@ -331,79 +331,109 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 if (tid == 128 && b + 1 < nblk) mbar_arrive(s8_ready);   // the contraction of block b+1 may start
                 const long long t2 = prof ? clock64() : 0;
 
+                // ---- my eight fields: partial sums of the four K-quarters + what the previous block's flips (which this
+                // block's contraction did not see) add; loads first, arithmetic after (a warp issues in order) ----
                 int u8[8];
                 uint32_t soff[8], unit8[8], sb = 0, vm = 0;
+                {
+                    int pq[8][4];
+                    uint4 xr[8][2];
+                    uint32_t po[8];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int idx = 8 * sl + e;
-                    int acc = part[pl * 33 + idx] + part[(32 + pl) * 33 + idx] + part[(64 + pl) * 33 + idx] + part[(96 + pl) * 33 + idx] - bias;
-                    // what the previous block's flips (not seen by this block's contraction) do to this field
-                    const uint4 x0 = *reinterpret_cast<const uint4*>(mx_s + idx * 8), x1 = *reinterpret_cast<const uint4*>(mx_s + idx * 8 + 4);
-                    acc = __dp4a((int)x0.x, (int)dsw_prev[0], acc); acc = __dp4a((int)x0.y, (int)dsw_prev[1], acc);
-                    acc = __dp4a((int)x0.z, (int)dsw_prev[2], acc); acc = __dp4a((int)x0.w, (int)dsw_prev[3], acc);
-                    acc = __dp4a((int)x1.x, (int)dsw_prev[4], acc); acc = __dp4a((int)x1.y, (int)dsw_prev[5], acc);
-                    acc = __dp4a((int)x1.z, (int)dsw_prev[6], acc); acc = __dp4a((int)x1.w, (int)dsw_prev[7], acc);
-                    u8[e] = acc;
-                    const uint32_t o = pos_off[idx];
-                    const bool valid = o != DS_NULL;
-                    soff[e] = valid ? (o & 0xFFFFFFu) + prow + ((((o >> 24) ^ (uint32_t)pl) & 7u) << 4) : 0u;
-                    unit8[e] = pos_unit[idx];
-                    const int sv = (int)(signed char)s8[soff[e]];   // a unit is visited once per sweep: its byte is still the tile's initial one
-                    sb |= (uint32_t)(valid && sv > 0) << e;
-                    vm |= (uint32_t)valid << e;
+                    for (int e = 0; e < 8; e++) {
+                        const int idx = 8 * sl + e;
+#pragma unroll
+                        for (int qq = 0; qq < 4; qq++) pq[e][qq] = part[(qq * 32 + pl) * 33 + idx];
+                        po[e] = pos_off[idx];
+                        unit8[e] = pos_unit[idx];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const bool valid = po[e] != DS_NULL;
+                        soff[e] = valid ? (po[e] & 0xFFFFFFu) + prow + ((((po[e] >> 24) ^ (uint32_t)pl) & 7u) << 4) : 0u;
+                        vm |= (uint32_t)valid << e;
+                    }
+                    int sv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) sv[e] = (int)(signed char)s8[soff[e]];   // a unit is visited once per sweep: still the tile's initial byte
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        xr[e][0] = *reinterpret_cast<const uint4*>(mx_s + (8 * sl + e) * 8);
+                        xr[e][1] = *reinterpret_cast<const uint4*>(mx_s + (8 * sl + e) * 8 + 4);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        sb |= (uint32_t)(((vm >> e) & 1u) && sv[e] > 0) << e;
+                        int a0 = pq[e][0] + pq[e][1] - bias, a1 = pq[e][2] + pq[e][3];
+                        a0 = __dp4a((int)xr[e][0].x, (int)dsw_prev[0], a0); a1 = __dp4a((int)xr[e][0].y, (int)dsw_prev[1], a1);
+                        a0 = __dp4a((int)xr[e][0].z, (int)dsw_prev[2], a0); a1 = __dp4a((int)xr[e][0].w, (int)dsw_prev[3], a1);
+                        a0 = __dp4a((int)xr[e][1].x, (int)dsw_prev[4], a0); a1 = __dp4a((int)xr[e][1].y, (int)dsw_prev[5], a1);
+                        a0 = __dp4a((int)xr[e][1].z, (int)dsw_prev[6], a0); a1 = __dp4a((int)xr[e][1].w, (int)dsw_prev[7], a1);
+                        u8[e] = a0 + a1;
+                    }
                 }
                 if (!active) vm = 0;
-                // the in-block matrix entries this thread needs, all 32 rows up front: nothing in the decision chain
-                // below waits for memory (a warp issues in order: one exposed load latency per step would triple it)
-                uint2 wv[32];
+                // per position of mine: xb = ~0 when the unit is low (then U >= 0 is the candidate side), the flip's signed
+                // step as a byte (0: not a position to decide), and the field value that means an exact tie (U == -2b)
+                uint32_t xb[8], dm[8];
+                int tv[8];
 #pragma unroll
-                for (int i = 0; i < 32; i++) wv[i] = *reinterpret_cast<const uint2*>(mbb_s + i * 8 + 2 * sl);
+                for (int e = 0; e < 8; e++) {
+                    const uint32_t bit = (sb >> e) & 1u;
+                    xb[e] = bit ? 0u : 0xFFFFFFFFu;
+                    dm[e] = ((vm >> e) & 1u) ? ((uint32_t)(bit ? -delta : delta) & 0xFFu) : 0u;
+                    tv[e] = -2 * (int)bit;
+                }
                 uint32_t dsw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                int start = 0, res_nb = 0;
-                bool have_res = false;
                 uint32_t fm = 0, applied = 0;   // flips of my eight positions: decided / already sent to the packed state
                 const long long t3 = prof ? clock64() : 0;
-                for (;;) {
-                    bool stalled = false;
+
+                // ---- pass 1, the common case: no memory access and no branch in the step-to-step dependency chain ----
+                uint32_t live = 0xFFFFFFFFu;    // cleared when my probe stops at an exact tie
+                int start = 32;                 // ... the position it stopped at
+                for (int so = 0; so < 4; so++) {
+                    uint2 w[8];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const int so = i >> 3, e = i & 7;
-                        const int U = u8[e], bit = (int)((sb >> e) & 1u);
-                        const bool elig = sl == so && ((vm >> e) & 1u) && !stalled && i >= start;
-                        const bool cand = bit ? (U < 0) : (U >= 0);
-                        const bool pre = have_res && i == start;            // an exact tie resolved before this pass
-                        const bool stall_now = elig && (U + 2 * bit == 0) && !pre;   // exact tie of the true field: stop here
-                        const int nb = pre ? res_nb : (bit ^ 1);
-                        const bool flip = elig && !stall_now && cand && nb != bit;
-                        int msg = (flip ? (bit ? -delta : delta) : 0) & 0xFF;
-                        if (stall_now) msg |= 0x100;
-                        fm |= (uint32_t)flip << e;
-                        msg = __shfl_sync(0xFFFFFFFFu, msg, so, 4);          // the owner's verdict to the probe's four threads
-                        if (msg & 0x100) { stalled = true; start = i; }
-                        const uint32_t d8 = (uint32_t)msg & 0xFFu;
-                        dsw[i >> 2] |= d8 << (8 * (i & 3));
+                    for (int e = 0; e < 8; e++) w[e] = *reinterpret_cast<const uint2*>(mbb_s + (8 * so + e) * 8 + 2 * sl);
+                    const uint32_t segm = sl == so ? 0xFFFFFFFFu : 0u;
+                    uint32_t d0 = 0, d1 = 0;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int U = u8[e];
+                        const uint32_t h = dm[e] & segm & live;                        // my decision to take, and its step byte
+                        uint32_t msg = ((uint32_t)(U >> 31) ^ xb[e]) & h;              // candidate <=> sign(U) == bit
+                        if (U == tv[e] && h != 0u) msg = 0x100u;                       // exact tie of the true field: stop here
+                        fm |= (uint32_t)((msg & 0xFFu) != 0u) << e;
+                        msg = __shfl_sync(0xFFFFFFFFu, msg, so, 4);                    // the owner's verdict to the probe's four threads
+                        if (msg & 0x100u) { live = 0u; start = 8 * so + e; }
+                        const uint32_t d8 = msg & 0xFFu;
+                        if (e < 4) d0 |= d8 << (8 * (e & 3)); else d1 |= d8 << (8 * (e & 3));
                         const int s0 = (int)d8, s1 = (int)(d8 << 8), s2 = (int)(d8 << 16), s3 = (int)(d8 << 24);
-                        u8[0] = __dp4a((int)wv[i].x, s0, u8[0]); u8[1] = __dp4a((int)wv[i].x, s1, u8[1]);
-                        u8[2] = __dp4a((int)wv[i].x, s2, u8[2]); u8[3] = __dp4a((int)wv[i].x, s3, u8[3]);
-                        u8[4] = __dp4a((int)wv[i].y, s0, u8[4]); u8[5] = __dp4a((int)wv[i].y, s1, u8[5]);
-                        u8[6] = __dp4a((int)wv[i].y, s2, u8[6]); u8[7] = __dp4a((int)wv[i].y, s3, u8[7]);
+                        u8[0] = __dp4a((int)w[e].x, s0, u8[0]); u8[1] = __dp4a((int)w[e].x, s1, u8[1]);
+                        u8[2] = __dp4a((int)w[e].x, s2, u8[2]); u8[3] = __dp4a((int)w[e].x, s3, u8[3]);
+                        u8[4] = __dp4a((int)w[e].y, s0, u8[4]); u8[5] = __dp4a((int)w[e].y, s1, u8[5]);
+                        u8[6] = __dp4a((int)w[e].y, s2, u8[6]); u8[7] = __dp4a((int)w[e].y, s3, u8[7]);
                     }
-                    // this pass's flips go to the packed state in global memory now (fire and forget); S8 gets them when
-                    // the next block's contraction, which must not see them, has completed
-                    {
-                        const uint32_t pend = fm & ~applied;
-                        applied = fm;
 #pragma unroll
-                        for (int e = 0; e < 8; e++)
-                            if ((pend >> e) & 1u) atomicXor(gbits + (unit8[e] >> 5), 1u << (unit8[e] & 31));
-                        flips += __popc(pend);
-                    }
-                    if (!stalled) start = 32;
-                    uint32_t m = __ballot_sync(0xFFFFFFFFu, stalled && sl == 0);
-                    if (!m) break;
+                    for (int sg = 0; sg < 4; sg++) if (sg == so) { dsw[2 * sg] = d0; dsw[2 * sg + 1] = d1; }
+                }
+                auto send_flips = [&]() {   // this pass's flips to the packed state in global memory (fire and forget); S8 gets
+                    const uint32_t pend = fm & ~applied;   // them when the next block's contraction, which must not see them, is complete
+                    applied = fm;
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        if ((pend >> e) & 1u) atomicXor(gbits + (unit8[e] >> 5), 1u << (unit8[e] & 31));
+                    flips += __popc(pend);
+                };
+                send_flips();
+                // ---- exact ties (rare): decide on the probe's current state, resume the probe from that position ----
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, start < 32 && sl == 0);
+                while (m) {
+                    int res_nb = 0;
+                    bool have_res = false;
                     __threadfence();   // the toggles above are performed before the packed state is read below
                     __syncwarp();
-                    while (m) {     // exact ties: the reference's float64 dot product on the probe's current state decides (rare)
+                    while (m) {   // the reference's float64 dot product in gonum's order
                         const int l0 = __ffs((int)m) - 1;
                         m &= m - 1;
                         const int pos = __shfl_sync(0xFFFFFFFFu, start, l0);
@@ -413,6 +443,43 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                                                               reinterpret_cast<const uint32_t*>(p.states + (size_t)pt * p.words), p.N, p.domain, lane);
                         if ((lane & ~3) == l0) { have_res = true; res_nb = hx > 0.0 ? 1 : 0; if (sl == 0) ties++; }
                     }
+                    // general pass: probes without a pending decision have start == 32 and stay idle
+                    bool stalled = false;
+                    int nstart = 32;
+                    for (int so = 0; so < 4; so++) {
+                        uint32_t d0 = 0, d1 = 0;
+#pragma unroll
+                        for (int sg = 0; sg < 4; sg++) if (sg == so) { d0 = dsw[2 * sg]; d1 = dsw[2 * sg + 1]; }
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const int i = 8 * so + e;
+                            const uint2 w = *reinterpret_cast<const uint2*>(mbb_s + i * 8 + 2 * sl);
+                            const int U = u8[e], bit = (int)((sb >> e) & 1u);
+                            const bool elig = sl == so && ((vm >> e) & 1u) && !stalled && i >= start;
+                            const bool cand = bit ? (U < 0) : (U >= 0);
+                            const bool pre = have_res && i == start;            // the tie resolved above
+                            const bool stall_now = elig && (U + 2 * bit == 0) && !pre;
+                            const int nb = pre ? res_nb : (bit ^ 1);
+                            const bool flip = elig && !stall_now && cand && nb != bit;
+                            int msg = (flip ? (bit ? -delta : delta) : 0) & 0xFF;
+                            if (stall_now) msg |= 0x100;
+                            fm |= (uint32_t)flip << e;
+                            msg = __shfl_sync(0xFFFFFFFFu, msg, so, 4);
+                            if (msg & 0x100) { stalled = true; nstart = i; }
+                            const uint32_t d8 = (uint32_t)msg & 0xFFu;
+                            if (e < 4) d0 |= d8 << (8 * (e & 3)); else d1 |= d8 << (8 * (e & 3));
+                            const int s0 = (int)d8, s1 = (int)(d8 << 8), s2 = (int)(d8 << 16), s3 = (int)(d8 << 24);
+                            u8[0] = __dp4a((int)w.x, s0, u8[0]); u8[1] = __dp4a((int)w.x, s1, u8[1]);
+                            u8[2] = __dp4a((int)w.x, s2, u8[2]); u8[3] = __dp4a((int)w.x, s3, u8[3]);
+                            u8[4] = __dp4a((int)w.y, s0, u8[4]); u8[5] = __dp4a((int)w.y, s1, u8[5]);
+                            u8[6] = __dp4a((int)w.y, s2, u8[6]); u8[7] = __dp4a((int)w.y, s3, u8[7]);
+                        }
+#pragma unroll
+                        for (int sg = 0; sg < 4; sg++) if (sg == so) { dsw[2 * sg] = d0; dsw[2 * sg + 1] = d1; }
+                    }
+                    start = nstart;
+                    send_flips();
+                    m = __ballot_sync(0xFFFFFFFFu, start < 32 && sl == 0);
                 }
                 const long long t4 = prof ? clock64() : 0;
 #pragma unroll

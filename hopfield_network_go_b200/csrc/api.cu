@@ -102,6 +102,8 @@ struct hn_handle_s {
     hn_config cfg;
     int N = 0, ldw = 0, words = 0, ldp = 0, sms = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;               // copy stream: probes in / results out under the kernels of the next range
+    std::vector<cudaEvent_t> chunk_ev;        // six events per range of a chunked batch
     double* W = nullptr;
     double* WT = nullptr;
     double* dW = nullptr;
@@ -626,13 +628,83 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
 }
 
 // The whole relaxation of B probes already on the device.
-int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d_pool, const uint16_t* d_inv,
-                 int n_pool, const int32_t* d_offsets, uint32_t flags, bool want_energies, bool want_dist) {
+// Relaxation of probes [off, off + cnt) of the batch already on the device (kernels only, stream h->st): initial fields
+// (or the dense lockstep sweeps, which supply them) and the sparse kernel.  Results land at the same indices of the
+// handle's result arrays.  ce: four events of this range (start, after the dense sweeps, after the fields, at the end).
+int relax_range(hn_handle h, const uint64_t* d_probes, int B_total, int off, int cnt, const uint16_t* d_pool, const uint16_t* d_inv,
+                int n_pool, const int32_t* d_offsets, uint32_t flags, bool want_dist, cudaEvent_t* ce, int* launches,
+                bool* profile_keyed, int* dense_sweeps) {
+    const int N = h->N, words = h->words;
+    const bool dedup = flags & HN_RELAX_DEDUP, hist = flags & HN_RELAX_HISTORY, serial = flags & HN_RELAX_SERIAL_STREAM;
+    (void)B_total;
+    Scratch* sc = h->scratch();
+    const uint64_t* probes = d_probes + (size_t)off * words;
+    HN_CUDA_TRY(cudaMemsetAsync(&sc->work_counter, 0, 4, h->st));
+    HN_CUDA_TRY(cudaEventRecord(ce[0], h->st));
+    // initial fields: S * W^T (FP64 tensor pipe); exact integer stream: G = S * K^T on the integer tensor pipe when W is
+    // symmetric (K's rows are its columns), else S * Wraw^T in float64 (half/quarter-integers: exact)
+    const bool int_fields = integer_stream(h) && h->w_symmetric;
+    const bool dense = dense_applicable(h, serial, hist, d_offsets, n_pool);
+    const uint64_t* relax_probes = probes;
+    h->last_dense_sweeps = 0;
+    if (dense) {   // the flip-dense first sweeps in lockstep on the tensor path; leaves states, fields and counters
+        HN_TRY(run_dense_sweeps(h, probes, cnt, d_pool, n_pool, launches));
+        relax_probes = h->d_state.as<uint64_t>();
+        HN_CUDA_TRY(cudaEventRecord(ce[1], h->st));
+    } else {
+        HN_CUDA_TRY(cudaEventRecord(ce[1], h->st));
+        if (int_fields)
+            HN_TRY(integer_fields(h, probes, cnt, reinterpret_cast<int32_t*>(h->H.as<double>())));
+        else
+            HN_TRY(launch_fields(h, probes, cnt, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
+        ++*launches;
+    }
+    *dense_sweeps = std::max(*dense_sweeps, h->last_dense_sweeps);
+    HN_CUDA_TRY(cudaEventRecord(ce[2], h->st));
+
+    RelaxParams p{};
+    p.N = N; p.ldw = h->ldw; p.words = words;
+    p.Wrow = h->W;
+    p.H0 = h->H.as<double>(); p.ldh = h->ldw;
+    p.H0i = int_fields ? reinterpret_cast<const int32_t*>(h->H.as<double>()) : nullptr;
+    p.probes = relax_probes; p.perm_pool = d_pool; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n_pool;
+    if (dense) { p.sweeps_done = h->d_sweeps.as<int32_t>(); p.flips_done = h->d_dflips.as<int32_t>(); p.margin_done = h->d_dmargin.as<int32_t>(); }
+    p.offsets = (serial || !d_offsets) ? nullptr : d_offsets + off;
+    p.B = cnt; p.max_iter = h->cfg.max_relax_iterations; p.max_unstable = h->cfg.max_relax_unstable_units;
+    p.domain = h->cfg.domain; p.check_stability = 1; p.serial_stream = serial ? 1 : 0;
+    p.final_states = h->finals.as<uint64_t>() + (size_t)off * words; p.num_steps = h->steps.as<int32_t>() + off;
+    p.stable = h->stable.as<uint8_t>() + off; p.flips = h->flips.as<int32_t>() + off; p.margin_hits = h->margin.as<int32_t>() + off;
+    p.distances = (want_dist && h->P > 0) ? h->dist.as<int32_t>() + (size_t)off * h->P : nullptr;
+    p.targets = h->targets.as<uint64_t>(); p.P = h->P;
+    p.hash = dedup ? h->hash.as<uint64_t>() + (size_t)off * 4 : nullptr;
+    p.zero_field = dedup ? h->zf.as<uint8_t>() + off : nullptr;
+    p.history = hist ? h->history.as<uint64_t>() + (size_t)off * (h->cfg.max_relax_iterations + 1) * words : nullptr;
+    p.work_counter = &sc->work_counter; p.status = sc->status;
+    HN_TRY(launch_relax(h, p));
+    ++*launches;
+    *profile_keyed = p.exact_arith || integer_stream(h) || p.key_scale != 0.0;   // see the epilogue of relax_kernel
+    HN_CUDA_TRY(cudaEventRecord(ce[3], h->st));
+    return HN_OK;
+}
+
+// probes per range of a chunked batch: the ranges run back to back on the compute stream while the copy stream moves
+// the next range's probes in and the previous range's results out (hn_relax_batch with host buffers)
+constexpr int RELAX_CHUNK = 32768;
+
+// The whole relaxation of B probes.  d_probes: device buffer of the batch; if host_probes != nullptr the probes are
+// still on the host and are uploaded range by range on the copy stream.  stream_out != nullptr: the per-probe results
+// are copied to its host buffers range by range on the copy stream, overlapping the next range's kernels.
+int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool, const uint16_t* d_inv,
+                 int n_pool, const int32_t* d_offsets, uint32_t flags, bool want_energies, bool want_dist,
+                 const uint64_t* host_probes = nullptr, const hn_relax_out* stream_out = nullptr) {
     const int N = h->N, words = h->words;
     HN_TRY(ensure_margin(h));
     HN_TRY(refresh_wt(h));
     const bool dedup = flags & HN_RELAX_DEDUP, hist = flags & HN_RELAX_HISTORY, serial = flags & HN_RELAX_SERIAL_STREAM;
-    HN_TRY(h->H.reserve(sizeof(double) * (size_t)B * h->ldw));
+    const bool zero_matrix = h->maxabs == 0.0 && h->cfg.max_relax_iterations >= 1;   // closed form, zero_matrix_relax_kernel
+    const int chunk = (serial || zero_matrix || B <= RELAX_CHUNK + RELAX_CHUNK / 4) ? B : RELAX_CHUNK;
+    const int n_chunks = (B + chunk - 1) / chunk;
+    HN_TRY(h->H.reserve(sizeof(double) * (size_t)chunk * h->ldw));
     HN_TRY(h->finals.reserve(sizeof(uint64_t) * (size_t)B * words));
     HN_TRY(h->steps.reserve(sizeof(int32_t) * (size_t)B));
     HN_TRY(h->stable.reserve((size_t)B));
@@ -643,88 +715,86 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     if (dedup) HN_TRY(h->hash.reserve(sizeof(uint64_t) * 4 * (size_t)B));
     if (dedup) HN_TRY(h->zf.reserve((size_t)B));
     if (hist) HN_TRY(h->history.reserve(sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
+    while ((int)h->chunk_ev.size() < 6 * n_chunks) {
+        cudaEvent_t e;
+        HN_CUDA_TRY(cudaEventCreate(&e));
+        h->chunk_ev.push_back(e);
+    }
 
-    int launches = 0;
+    int launches = 0, dense_sweeps = 0;
     Scratch* sc = h->scratch();
     HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));   // work counter, status, unique total
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 4 * (size_t)B, h->st));
-
-    HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
-    const bool zero_matrix = h->maxabs == 0.0 && h->cfg.max_relax_iterations >= 1;   // closed form, zero_matrix_relax_kernel
     if (zero_matrix && (serial ? n_pool < B : n_pool < 1)) {
         set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, serial ? B : 1);
         return HN_E_POOL;
     }
-    RelaxParams p{};
     bool profile_keyed = false;
-    if (zero_matrix) {
-        HN_CUDA_TRY(cudaEventRecord(h->ev[4], h->st));
-        HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
-        const int wpb = 8;
-        zero_matrix_relax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, h->st>>>(
-            d_probes, B, words, N, h->cfg.domain, h->cfg.max_relax_iterations, h->finals.as<uint64_t>(), h->steps.as<int32_t>(),
-            h->stable.as<uint8_t>(), h->flips.as<int32_t>(), h->margin.as<int32_t>(),
-            (want_dist && h->P > 0) ? h->dist.as<int32_t>() : nullptr, h->targets.as<uint64_t>(), h->P,
-            dedup ? h->hash.as<uint64_t>() : nullptr, dedup ? h->zf.as<uint8_t>() : nullptr, hist ? h->history.as<uint64_t>() : nullptr);
-        HN_CUDA_TRY(cudaGetLastError());
-        launches++;
-        profile_keyed = false;  // every final state is the all-low state: one group at level 1
-        HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
-    } else {
-    // initial fields: S * W^T (FP64 tensor pipe); exact integer stream: G = S * K^T on the integer tensor pipe when W is
-    // symmetric (K's rows are its columns), else S * Wraw^T in float64 (half/quarter-integers: exact)
-    const bool int_fields = integer_stream(h) && h->w_symmetric;
-    const bool dense = dense_applicable(h, serial, hist, d_offsets, n_pool);
-    const uint64_t* relax_probes = d_probes;
-    h->last_dense_sweeps = 0;
-    if (dense) {   // the flip-dense first sweeps in lockstep on the tensor path; leaves states, fields and counters
-        HN_TRY(run_dense_sweeps(h, d_probes, B, d_pool, n_pool, &launches));
-        relax_probes = h->d_state.as<uint64_t>();
-        HN_CUDA_TRY(cudaEventRecord(h->ev[4], h->st));
-    } else {
-        HN_CUDA_TRY(cudaEventRecord(h->ev[4], h->st));
-        if (int_fields)
-            HN_TRY(integer_fields(h, d_probes, B, reinterpret_cast<int32_t*>(h->H.as<double>())));
-        else
-            HN_TRY(launch_fields(h, d_probes, B, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
-        launches++;
+    HN_CUDA_TRY(cudaEventRecord(h->ev[0], h->st));   // the copy stream starts after everything queued so far
+    HN_CUDA_TRY(cudaStreamWaitEvent(h->st2, h->ev[0], 0));
+    auto d2h2 = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (dst && bytes) HN_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st2));
+        return HN_OK;
+    };
+    for (int c = 0; c < n_chunks; c++) {
+        const int off = c * chunk, cnt = std::min(chunk, B - off);
+        cudaEvent_t* ce = &h->chunk_ev[6 * (size_t)c];
+        if (host_probes) {   // this range's probes: host -> device on the copy stream
+            HN_CUDA_TRY(cudaMemcpyAsync(d_probes + (size_t)off * words, host_probes + (size_t)off * words,
+                                        sizeof(uint64_t) * (size_t)cnt * words, cudaMemcpyHostToDevice, h->st2));
+            HN_CUDA_TRY(cudaEventRecord(ce[4], h->st2));
+            HN_CUDA_TRY(cudaStreamWaitEvent(h->st, ce[4], 0));
+        }
+        if (zero_matrix) {
+            HN_CUDA_TRY(cudaEventRecord(ce[0], h->st));
+            HN_CUDA_TRY(cudaEventRecord(ce[1], h->st));
+            HN_CUDA_TRY(cudaEventRecord(ce[2], h->st));
+            const int wpb = 8;
+            zero_matrix_relax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, h->st>>>(
+                d_probes, B, words, N, h->cfg.domain, h->cfg.max_relax_iterations, h->finals.as<uint64_t>(), h->steps.as<int32_t>(),
+                h->stable.as<uint8_t>(), h->flips.as<int32_t>(), h->margin.as<int32_t>(),
+                (want_dist && h->P > 0) ? h->dist.as<int32_t>() : nullptr, h->targets.as<uint64_t>(), h->P,
+                dedup ? h->hash.as<uint64_t>() : nullptr, dedup ? h->zf.as<uint8_t>() : nullptr, hist ? h->history.as<uint64_t>() : nullptr);
+            HN_CUDA_TRY(cudaGetLastError());
+            launches++;
+            profile_keyed = false;  // every final state is the all-low state: one group at level 1
+            HN_CUDA_TRY(cudaEventRecord(ce[3], h->st));
+        } else {
+            HN_TRY(relax_range(h, d_probes, B, off, cnt, d_pool, d_inv, n_pool, d_offsets, flags, want_dist, ce, &launches,
+                               &profile_keyed, &dense_sweeps));
+        }
+        if (stream_out) {   // this range's results: device -> host on the copy stream, under the next range's kernels
+            HN_CUDA_TRY(cudaStreamWaitEvent(h->st2, ce[3], 0));
+            HN_TRY(d2h2(stream_out->final_states ? stream_out->final_states + (size_t)off * words : nullptr,
+                        h->finals.as<uint64_t>() + (size_t)off * words, sizeof(uint64_t) * (size_t)cnt * words));
+            HN_TRY(d2h2(stream_out->num_steps ? stream_out->num_steps + off : nullptr, h->steps.as<int32_t>() + off, sizeof(int32_t) * (size_t)cnt));
+            HN_TRY(d2h2(stream_out->stable ? stream_out->stable + off : nullptr, h->stable.as<uint8_t>() + off, (size_t)cnt));
+            HN_TRY(d2h2(stream_out->flips ? stream_out->flips + off : nullptr, h->flips.as<int32_t>() + off, sizeof(int32_t) * (size_t)cnt));
+            HN_TRY(d2h2(stream_out->margin_hits ? stream_out->margin_hits + off : nullptr, h->margin.as<int32_t>() + off, sizeof(int32_t) * (size_t)cnt));
+            if (stream_out->distances && want_dist && h->P > 0)
+                HN_TRY(d2h2(stream_out->distances + (size_t)off * h->P, h->dist.as<int32_t>() + (size_t)off * h->P, sizeof(int32_t) * (size_t)cnt * h->P));
+            if (stream_out->history && hist) {
+                const size_t per = (size_t)(h->cfg.max_relax_iterations + 1) * words;
+                HN_TRY(d2h2(stream_out->history + (size_t)off * per, h->history.as<uint64_t>() + (size_t)off * per, sizeof(uint64_t) * (size_t)cnt * per));
+            }
+        }
     }
-    HN_CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
-
-    p.N = N; p.ldw = h->ldw; p.words = words;
-    p.Wrow = h->W;
-    p.H0 = h->H.as<double>(); p.ldh = h->ldw;
-    p.H0i = int_fields ? reinterpret_cast<const int32_t*>(h->H.as<double>()) : nullptr;
-    p.probes = relax_probes; p.perm_pool = d_pool; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n_pool;
-    if (dense) { p.sweeps_done = h->d_sweeps.as<int32_t>(); p.flips_done = h->d_dflips.as<int32_t>(); p.margin_done = h->d_dmargin.as<int32_t>(); }
-    p.offsets = serial ? nullptr : d_offsets;
-    p.B = B; p.max_iter = h->cfg.max_relax_iterations; p.max_unstable = h->cfg.max_relax_unstable_units;
-    p.domain = h->cfg.domain; p.check_stability = 1; p.serial_stream = serial ? 1 : 0;
-    
-    p.final_states = h->finals.as<uint64_t>(); p.num_steps = h->steps.as<int32_t>();
-    p.stable = h->stable.as<uint8_t>(); p.flips = h->flips.as<int32_t>(); p.margin_hits = h->margin.as<int32_t>();
-    p.distances = (want_dist && h->P > 0) ? h->dist.as<int32_t>() : nullptr;
-    p.targets = h->targets.as<uint64_t>(); p.P = h->P;
-    p.hash = dedup ? h->hash.as<uint64_t>() : nullptr;
-    p.zero_field = dedup ? h->zf.as<uint8_t>() : nullptr;
-    p.history = hist ? h->history.as<uint64_t>() : nullptr;
-    p.work_counter = &sc->work_counter; p.status = sc->status;
-    HN_TRY(launch_relax(h, p));
-    launches++;
-    profile_keyed = p.exact_arith || integer_stream(h) || p.key_scale != 0.0;   // see the epilogue of relax_kernel
     HN_CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
-    }
 
     if (want_energies) {
-        // EnergyProfile of the final states (main.go:234): fresh fields by GEMM + epilogue
+        // EnergyProfile of the final states (main.go:234): fresh fields by GEMM + epilogue, range by range
         HN_TRY(h->energies.reserve(sizeof(double) * (size_t)B * N));
-        HN_TRY(launch_fields(h, h->finals.as<uint64_t>(), B, h->H.as<double>(), domain_values(h->cfg.domain)));
-        energy_epilogue_kernel<<<B, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, h->finals.as<uint64_t>(), words,
-                                                            h->W, h->ldw, N, h->cfg.domain, h->exact_arith ? 0.0 : h->tau_base,
-                                                            h->cfg.max_relax_unstable_units, h->energies.as<double>(),
-                                                            nullptr, nullptr, nullptr, nullptr);
-        HN_CUDA_TRY(cudaGetLastError());
-        launches += 2;
+        for (int c = 0; c < n_chunks; c++) {
+            const int off = c * chunk, cnt = std::min(chunk, B - off);
+            const uint64_t* fin = h->finals.as<uint64_t>() + (size_t)off * words;
+            HN_TRY(launch_fields(h, fin, cnt, h->H.as<double>(), domain_values(h->cfg.domain)));
+            energy_epilogue_kernel<<<cnt, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, fin, words,
+                                                                  h->W, h->ldw, N, h->cfg.domain, h->exact_arith ? 0.0 : h->tau_base,
+                                                                  h->cfg.max_relax_unstable_units, h->energies.as<double>() + (size_t)off * N,
+                                                                  nullptr, nullptr, nullptr, nullptr);
+            HN_CUDA_TRY(cudaGetLastError());
+            launches += 2;
+        }
     }
     h->result_unique = 0;
     if (dedup) {
@@ -738,6 +808,7 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     Scratch host_sc;
     HN_CUDA_TRY(cudaMemcpyAsync(&host_sc, sc, sizeof(Scratch), cudaMemcpyDeviceToHost, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st2));
     h->tot_flips = (int64_t)host_sc.totals[0]; h->tot_sweeps = (int64_t)host_sc.totals[1]; h->tot_margin = (int64_t)host_sc.totals[2];
     if (host_sc.status[0]) {
         set_error("permutation pool exhausted: %d rows supplied, at least %d needed", n_pool, host_sc.status[1]);
@@ -745,32 +816,42 @@ int relax_device(hn_handle h, const uint64_t* d_probes, int B, const uint16_t* d
     }
     h->result_unique = dedup ? host_sc.unique_total : 0;
     h->result_profile_keyed = profile_keyed;
-    float f = 0, r = 0, q = 0, d = 0;
-    cudaEventElapsedTime(&d, h->ev[0], h->ev[4]);
-    cudaEventElapsedTime(&f, h->ev[4], h->ev[1]);
-    cudaEventElapsedTime(&r, h->ev[1], h->ev[2]);
+    double tf = 0, tr = 0, td = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        cudaEvent_t* ce = &h->chunk_ev[6 * (size_t)c];
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&d, ce[0], ce[1]);
+        cudaEventElapsedTime(&a, ce[1], ce[2]);
+        cudaEventElapsedTime(&b, ce[2], ce[3]);
+        td += d; tf += a; tr += b;
+    }
+    float q = 0;
     cudaEventElapsedTime(&q, h->ev[2], h->ev[3]);
-    h->timing.fields_ms = f; h->timing.relax_ms = r; h->timing.post_ms = q; h->timing.launches = launches;
-    h->timing.dense_ms = d; h->timing.dense_sweeps = h->last_dense_sweeps;
+    h->timing.fields_ms = tf; h->timing.relax_ms = tr; h->timing.post_ms = q; h->timing.launches = launches;
+    h->timing.dense_ms = td; h->timing.dense_sweeps = dense_sweeps;
     h->result_B = B; h->result_P = want_dist ? h->P : 0; h->result_flags = flags | (want_energies ? 0x100u : 0u);
     return HN_OK;
 }
 
-int download_results(hn_handle h, hn_relax_out* out) {
+// streamed: the per-probe arrays (final states, steps, flags, counters, distances, history) were already copied range by
+// range by relax_device; only what exists after the whole batch is left
+int download_results(hn_handle h, hn_relax_out* out, bool streamed = false) {
     const int B = h->result_B, N = h->N, words = h->words;
     if (B <= 0) { set_error("no relaxation results on the device"); return HN_E_STATE; }
     auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
         if (dst && bytes) HN_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st));
         return HN_OK;
     };
-    HN_TRY(d2h(out->final_states, h->finals.p, sizeof(uint64_t) * (size_t)B * words));
-    HN_TRY(d2h(out->num_steps, h->steps.p, sizeof(int32_t) * (size_t)B));
-    HN_TRY(d2h(out->stable, h->stable.p, (size_t)B));
-    HN_TRY(d2h(out->flips, h->flips.p, sizeof(int32_t) * (size_t)B));
-    HN_TRY(d2h(out->margin_hits, h->margin.p, sizeof(int32_t) * (size_t)B));
+    if (!streamed) {
+        HN_TRY(d2h(out->final_states, h->finals.p, sizeof(uint64_t) * (size_t)B * words));
+        HN_TRY(d2h(out->num_steps, h->steps.p, sizeof(int32_t) * (size_t)B));
+        HN_TRY(d2h(out->stable, h->stable.p, (size_t)B));
+        HN_TRY(d2h(out->flips, h->flips.p, sizeof(int32_t) * (size_t)B));
+        HN_TRY(d2h(out->margin_hits, h->margin.p, sizeof(int32_t) * (size_t)B));
+    }
     if (out->distances) {
         if (h->result_P != h->P) { set_error("distances were not computed"); return HN_E_STATE; }
-        HN_TRY(d2h(out->distances, h->dist.p, sizeof(int32_t) * (size_t)B * h->P));
+        if (!streamed) HN_TRY(d2h(out->distances, h->dist.p, sizeof(int32_t) * (size_t)B * h->P));
     }
     if (out->energies) {
         if (!(h->result_flags & 0x100u)) { set_error("energies were not computed"); return HN_E_STATE; }
@@ -794,7 +875,7 @@ int download_results(hn_handle h, hn_relax_out* out) {
     }
     if (out->history) {
         if (!(h->result_flags & HN_RELAX_HISTORY)) { set_error("history was not captured"); return HN_E_STATE; }
-        HN_TRY(d2h(out->history, h->history.p, sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
+        if (!streamed) HN_TRY(d2h(out->history, h->history.p, sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
     }
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     out->total_flips = h->tot_flips; out->total_sweeps = h->tot_sweeps; out->total_margin_hits = h->tot_margin;   // summed on the device
@@ -1176,6 +1257,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     do {
         if (cudaSetDevice(cfg->device) != cudaSuccess) { rc = HN_E_CUDA; break; }
         if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { rc = HN_E_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess) { rc = HN_E_CUDA; break; }
         const size_t wb = sizeof(double) * (size_t)h->N * h->ldw;
         if (cudaMalloc(&h->W, wb) != cudaSuccess || cudaMalloc(&h->dW, wb) != cudaSuccess) { rc = HN_E_OOM; break; }
         if (cudaMemsetAsync(h->W, 0, wb, h->st) != cudaSuccess) { rc = HN_E_CUDA; break; }  // matrix.Zero(), :248-250
@@ -1221,6 +1303,8 @@ int hn_destroy(hn_handle h) {
     if (h->dW) cudaFree(h->dW);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->lev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
+    if (h->st2) { cudaStreamSynchronize(h->st2); cudaStreamDestroy(h->st2); }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return HN_OK;
@@ -1578,7 +1662,7 @@ int hn_relax_batch(hn_handle h, const uint64_t* probes_packed, int32_t n_probes,
     }
     HN_TRY(set_device(h));
     HN_TRY(validate_pool_host(h, perm_pool, n_pool));
-    HN_TRY(upload_states(h, h->probes, probes_packed, n_probes));
+    HN_TRY(h->probes.reserve(sizeof(uint64_t) * (size_t)n_probes * h->words));   // uploaded range by range inside relax_device
     HN_TRY(upload_pool(h, perm_pool, n_pool, h->pool, &h->d_pool, &h->d_inv));
     h->pool_version++;
     h->resident_B = n_probes; h->resident_pool = n_pool;
@@ -1591,8 +1675,8 @@ int hn_relax_batch(hn_handle h, const uint64_t* probes_packed, int32_t n_probes,
         d_off = h->offsets.as<int32_t>();
     }
     HN_TRY(relax_device(h, h->probes.as<uint64_t>(), n_probes, h->d_pool, h->d_inv, n_pool, d_off,
-                        flags, out->energies != nullptr, out->distances != nullptr));
-    return download_results(h, out);
+                        flags, out->energies != nullptr, out->distances != nullptr, probes_packed, out));
+    return download_results(h, out, true);
 }
 
 int hn_update_states(hn_handle h, uint64_t* states_packed, int32_t n, const uint16_t* perms) {

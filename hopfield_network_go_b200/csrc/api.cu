@@ -688,8 +688,11 @@ int relax_range(hn_handle h, const uint64_t* d_probes, int B_total, int off, int
 }
 
 // probes per range of a chunked batch: the ranges run back to back on the compute stream while the copy stream moves
-// the next range's probes in and the previous range's results out (hn_relax_batch with host buffers)
-constexpr int RELAX_CHUNK = 32768;
+// the next range's probes in and the previous range's results out (hn_relax_batch with host buffers), and the fields /
+// dense-sweep working set is that of one range.  Measured at config 3 (2^17 probes): ranges of 32768 cost 6 ms of kernel
+// tails per step and hide 7 ms of PCIe copies, i.e. nothing is gained at that size; so a range is a whole config-3 batch
+// and only larger batches are cut.
+constexpr int RELAX_CHUNK = 1 << 17;
 
 // The whole relaxation of B probes.  d_probes: device buffer of the batch; if host_probes != nullptr the probes are
 // still on the host and are uploaded range by range on the copy stream.  stream_out != nullptr: the per-probe results

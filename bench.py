@@ -290,6 +290,8 @@ def main():
     for _ in range(args.steps):
         dev_ms.append(net.relax_resident(dedup=True))
         t = net.last_timing()
+        if os.environ.get("HN_MERGE_TRACE") and rank == 0:
+            print(f"[resident trace] device {dev_ms[-1]:.2f}: dense {t.dense_ms:.2f} fields {t.fields_ms:.2f} relax {t.relax_ms:.2f} post {t.post_ms:.2f}", flush=True)
         for k in ("fields_ms", "relax_ms", "post_ms", "dense_ms"):
             stage.setdefault(k, []).append(getattr(t, k, 0.0))
         launches += t.launches
@@ -309,6 +311,10 @@ def main():
         barrier()
         t1 = time.perf_counter()
         res = net.relax_batch(probes_np, pool, dedup=True, reuse_pinned_buffers=True)   # page-locked result buffers of the network
+        if os.environ.get("HN_MERGE_TRACE") and rank == 0:
+            tt = net.last_timing()
+            print(f"[e2e trace] relax_batch {1e3 * (time.perf_counter() - t1):.2f} ms (device {res.device_ms:.2f}: dense {tt.dense_ms:.2f} "
+                  f"fields {tt.fields_ms:.2f} relax {tt.relax_ms:.2f} post {tt.post_ms:.2f})", flush=True)
         if world > 1:   # per-GPU unique tables merged on rank 0's GPU (first-seen order, hits)
             merged = multigpu.gather_unique_tables_device(net, rank * b)
             if rank == 0:

@@ -689,10 +689,11 @@ int relax_range(hn_handle h, const uint64_t* d_probes, int B_total, int off, int
 
 // probes per range of a chunked batch: the ranges run back to back on the compute stream while the copy stream moves
 // the next range's probes in and the previous range's results out (hn_relax_batch with host buffers), and the fields /
-// dense-sweep working set is that of one range.  Measured at config 3 (2^17 probes): ranges of 32768 cost 6 ms of kernel
-// tails per step and hide 7 ms of PCIe copies, i.e. nothing is gained at that size; so a range is a whole config-3 batch
-// and only larger batches are cut.
-constexpr int RELAX_CHUNK = 1 << 17;
+// dense-sweep working set is that of one range.  Measured at config 3 (2^17 probes per GPU): every extra range costs
+// ~2 ms of kernel tails and host round trips; the copies it hides take 7 ms per step on one GPU but 27 ms when eight
+// GPUs share the host's PCIe fabric (12.8 GB/s per GPU).  So: two ranges per config-3 batch when the results are
+// streamed to the host, one range (up to 2^17 probes) when they stay on the device.
+constexpr int RELAX_CHUNK_STREAMED = 1 << 16, RELAX_CHUNK_RESIDENT = 1 << 17;
 
 // The whole relaxation of B probes.  d_probes: device buffer of the batch; if host_probes != nullptr the probes are
 // still on the host and are uploaded range by range on the copy stream.  stream_out != nullptr: the per-probe results
@@ -705,7 +706,8 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
     HN_TRY(refresh_wt(h));
     const bool dedup = flags & HN_RELAX_DEDUP, hist = flags & HN_RELAX_HISTORY, serial = flags & HN_RELAX_SERIAL_STREAM;
     const bool zero_matrix = h->maxabs == 0.0 && h->cfg.max_relax_iterations >= 1;   // closed form, zero_matrix_relax_kernel
-    const int chunk = (serial || zero_matrix || B <= RELAX_CHUNK + RELAX_CHUNK / 4) ? B : RELAX_CHUNK;
+    const int range = (host_probes || stream_out) ? RELAX_CHUNK_STREAMED : RELAX_CHUNK_RESIDENT;
+    const int chunk = (serial || zero_matrix || B <= range + range / 4) ? B : range;
     const int n_chunks = (B + chunk - 1) / chunk;
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)chunk * h->ldw));
     HN_TRY(h->finals.reserve(sizeof(uint64_t) * (size_t)B * words));

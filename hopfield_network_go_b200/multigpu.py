@@ -167,11 +167,20 @@ def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[
     merged only after the float-profile comparison).  All ranks call; rank 0 returns {"first", "hits", "rank_of",
     "local_id"} (numpy), the others None."""
     import ctypes as C
+    import os
+    import time
     import torch
     import torch.distributed as dist
     from . import capi
     lib = capi.load()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    trace = os.environ.get("HN_MERGE_TRACE") and rank == 0
+    marks = []
+    def mark(name):
+        if trace:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+    mark("start")
     dev = torch.device("cuda", torch.cuda.current_device())
     nu, pk = C.c_int32(), C.c_int32()
     capi.check(lib.hn_export_unique_device(net._h, 0, None, None, None, None, None, C.byref(nu), C.byref(pk)))
@@ -180,6 +189,7 @@ def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[
     heads = [torch.zeros_like(head) for _ in range(world)]
     dist.all_gather(heads, head, group=group)
     heads = torch.stack(heads).cpu().numpy()
+    mark("heads")
     counts = heads[:, 0].astype(np.int64)
     umax = max(1, int(counts.max()))
     # one int64 payload per rank: [first | hits | zero-field | 4 key words | packed state]
@@ -194,8 +204,10 @@ def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[
                                            states.data_ptr(), zf.data_ptr(), C.byref(nu), C.byref(pk)))
     pay[:, 0], pay[:, 1], pay[:, 2] = first, hits.to(torch.int64), zf.to(torch.int64)
     pay[:, 3:7], pay[:, 7:] = keys, states
+    mark("export")
     bufs = [torch.empty_like(pay) for _ in range(world)] if rank == 0 else None
     dist.gather(pay, bufs, dst=0, group=group)
+    mark("gather")
     if rank != 0:
         return None
     allp = torch.cat([bufs[r][:int(counts[r])] for r in range(world)]).contiguous()
@@ -206,11 +218,15 @@ def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[
     K = allp[:, 3:7].contiguous()
     S = allp[:, 7:].contiguous()
     torch.cuda.synchronize()
+    mark("concat")
     f_out, h_out, r_out = np.empty(max(n, 1), np.int64), np.empty(max(n, 1), np.int64), np.empty(max(n, 1), np.int64)
     ng = C.c_int64()
     capi.check(lib.hn_merge_unique_device(net._h, n, F.data_ptr(), H.data_ptr(), K.data_ptr(), S.data_ptr(), Z.data_ptr(),
                                           int(heads[0, 1]), capi.ptr(f_out), capi.ptr(h_out), capi.ptr(r_out), C.byref(ng)))
     g = ng.value
+    mark("merge")
+    if trace:
+        print("[merge trace] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f} ms" for a, b in zip(marks, marks[1:])), flush=True)
     starts = np.concatenate(([0], np.cumsum(counts)))
     rep = r_out[:g]
     rank_of = np.searchsorted(starts[1:], rep, side="right").astype(np.int32)

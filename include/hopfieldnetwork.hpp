@@ -34,6 +34,10 @@ inline void check(int rc) {
 struct LearnStateData {  // datacollector/LearnStateData.go:14-19
     int Epoch; int TargetStateIndex; std::vector<double> EnergyProfile; bool Stable;
 };
+struct HopfieldNetworkSummary {  // HopfieldNetwork.go:124-134 (consumed by main.go:262-279)
+    std::vector<double> Matrix; int Dimension; bool ForceSymmetric, ForceZeroDiagonal; int Epochs;
+    int MaximumRelaxationUnstableUnits, MaximumRelaxationIterations; double LearningNoiseScale; int UnitsUpdatedPerStep;
+};
 struct RelaxationResult {  // HopfieldNetwork.go:268-273 (last history entry only, plus NumSteps)
     bool Stable; int NumSteps; std::vector<double> DistancesToTargets; State FinalState; std::vector<double> EnergyProfile;
 };
@@ -51,9 +55,20 @@ public:
         return w;
     }
     void SetMatrix(const std::vector<double>& w) { check(hn_set_weights(handle_, w.data())); }
+    HopfieldNetworkSummary GetNetworkSummary() const {  // HopfieldNetwork.go:137-149
+        return HopfieldNetworkSummary{GetMatrix(), cfg_.dimension, cfg_.force_symmetric != 0, cfg_.force_zero_diagonal != 0, epochs_,
+                                      cfg_.max_relax_unstable_units, cfg_.max_relax_iterations, noise_scale_, units_updated_};
+    }
 
     std::vector<double> AllUnitEnergies(const State& s) { return profiles({s}, true).energies[0]; }   // :198-200
-    double UnitEnergy(const State& s, int i) { return AllUnitEnergies(s)[(size_t)i]; }                  // :185-187
+    // :185-187 — the reference's scalar loop (Binary: -1 per term, BinaryDomainManager.go:43-52), not AllUnitEnergies(s)[i]
+    double UnitEnergy(const State& s, int i) {
+        std::vector<uint64_t> packed((size_t)hn_words(cfg_.dimension));
+        check(hn_pack_states_f64(cfg_.dimension, 1, s.data(), packed.data()));
+        double e = 0.0;
+        check(hn_unit_energy(handle_, packed.data(), 1, i, &e));
+        return e;
+    }
     double StateEnergy(const State& s) { return profiles({s}, false).total[0]; }                       // :171-173
     bool StateIsStable(const State& s) { return profiles({s}, false).stable[0] != 0; }                 // :214-225
     bool AllStatesAreStable(const std::vector<State>& v) {                                              // :236-243
@@ -152,7 +167,7 @@ private:
     hn_config cfg_{};
     hn_handle handle_ = nullptr;
     hn_rng rng_ = nullptr;
-    int epochs_ = 0, rule_ = 0, method_ = 0, noise_ = 0;
+    int epochs_ = 0, rule_ = 0, method_ = 0, noise_ = 0, units_updated_ = 1;
     double noise_scale_ = 0.0;
 };
 
@@ -186,7 +201,7 @@ public:
             throw std::invalid_argument(pre + "unitsUpdatedPerStep must be a positive integer that is smaller than the network dimension!");
         std::unique_ptr<HopfieldNetwork> net(new HopfieldNetwork());
         net->cfg_ = cfg_; net->epochs_ = epochs_; net->rule_ = rule_; net->method_ = method_; net->noise_ = noise_;
-        net->noise_scale_ = noise_scale_;
+        net->noise_scale_ = noise_scale_; net->units_updated_ = units_;
         check(hn_rng_create(seed_, &net->rng_));
         check(hn_create(&cfg_, &net->handle_));
         if (rand_init_) {  // :235-246 distuv.Normal{0, 0.01, randSrc}

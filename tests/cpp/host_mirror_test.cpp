@@ -50,6 +50,10 @@ int main(int argc, char** argv) {
         if (r.FinalState != x) return fail("final state");
         for (double e : r.EnergyProfile) if (!(e < 0.0)) return fail("energy profile");
     }
+    // UnitEnergy is the reference's scalar loop: for a bipolar network it agrees with AllUnitEnergies to rounding
+    if (std::fabs(net->UnitEnergy(x, 5) - net->AllUnitEnergies(x)[5]) > 1e-12) return fail("UnitEnergy");
+    auto summary = net->GetNetworkSummary();
+    if (summary.Dimension != n || summary.Epochs != 1 || !summary.ForceSymmetric || summary.Matrix.size() != (size_t)n * n) return fail("summary");
     std::printf("OK gpu\n");
     return 0;
 }

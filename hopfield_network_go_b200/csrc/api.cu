@@ -148,6 +148,7 @@ struct hn_handle_s {
     double dense_min_flips = 200.0;   // sweep densely again while the last sweep flipped more than this per unfinished probe (the next one
                                       // flips ~0.75x as many; a dense sweep costs what ~160 flips per probe cost the sparse kernel)
     int last_dense_sweeps = 0;
+    uint64_t image_tried_version = 0;   // ensure_learning_image: the W version the image was last (tried to be) built for
     bool fused_flags_valid = false;   // Scratch::maxabs_bits / not_quarters describe the current W (update_constraints_i32_kernel)
     DevBuf opA8, opB8;                // int8 operands of the learning contractions (tcgen05 path)
     cudaEvent_t ev[6] = {};
@@ -262,7 +263,8 @@ int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H,
 // of the parity of P; Delta: half / quarter integers); int_ok only if every entry fits int16 and the exactness bound of
 // the field holds.  (An int8 image with dp4a was tried for |K| <= 127: half the column bytes, no faster — the kernel is
 // bound by its dependent chain and issue slots, not by the L2->SM bytes; profiles/r01_relax_i16_final_ncu_summary.txt.)
-int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W = fl(c * Wraw)
+int build_integer_structure(hn_handle h, bool symmetric, double c, const double* raw = nullptr) {   // c: W = fl(c * raw); raw defaults to h->Wraw
+    if (!raw) raw = h->Wraw;
     const int64_t total = (int64_t)h->N * h->ldw;
     if (!h->K16) HN_CUDA_TRY(cudaMalloc(&h->K16, sizeof(int16_t) * (size_t)total));
     HN_TRY(h->small.reserve(sizeof(Scratch)));
@@ -270,14 +272,14 @@ int build_integer_structure(hn_handle h, bool symmetric, double c) {   // c: W =
     unsigned long long* mx = &h->scratch()->maxabs_raw_bits;
     HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(mx, 0, 8, h->st));
-    const double* src = h->Wraw;
+    const double* src = raw;
     if (!symmetric) {  // column k of Wraw must be contiguous: transpose into dW (free outside learning epochs)
         HN_CUDA_TRY(cudaMemsetAsync(h->dW, 0, sizeof(double) * (size_t)total, h->st));
         dim3 g((h->N + SYM_T - 1) / SYM_T, (h->N + SYM_T - 1) / SYM_T), b(SYM_T, 8);
-        transpose_kernel<<<g, b, 0, h->st>>>(h->Wraw, h->dW, h->N, h->ldw);
+        transpose_kernel<<<g, b, 0, h->st>>>(raw, h->dW, h->N, h->ldw);
         src = h->dW;
     }
-    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(h->Wraw, h->N, h->ldw, mx, nullptr);
+    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(raw, h->N, h->ldw, mx, nullptr);
     HN_CUDA_TRY(cudaGetLastError());
     int32_t f = 1; double m = 0;
     for (double scale : {0.5, 1.0, 2.0, 4.0}) {
@@ -337,6 +339,19 @@ int detect_integer_structure(hn_handle h) {
     return HN_OK;
 }
 
+bool wants_integer_stream(hn_handle h);
+bool integer_stream(hn_handle h);
+// Un-normalised weights inside a learning run (quarter-integers, exact arithmetic): the integer image is rebuilt from W
+// itself (W = 1 * W), so that the sweeps of the next Delta epoch run on the integer stream and the fields of the sweep
+// and of the per-epoch diagnostics come from the integer tensor path instead of three FP64 GEMMs.  Symmetric W only.
+int ensure_learning_image(hn_handle h) {
+    if (h->int_ok || !h->use_tc05 || !wants_integer_stream(h) || !h->w_symmetric) return HN_OK;
+    HN_TRY(ensure_margin(h));
+    if (!h->exact_arith || h->maxabs == 0.0 || h->image_tried_version == h->w_version) return HN_OK;
+    h->image_tried_version = h->w_version;
+    return build_integer_structure(h, true, 1.0, h->W);
+}
+
 // float32 shadow of the column matrix (W if symmetric else W^T), rebuilt after any weight change
 int ensure_w32(hn_handle h) {
     if (h->w32_valid) return HN_OK;
@@ -356,9 +371,11 @@ int select_columns(hn_handle h, RelaxParams& p) {
     p.tau_flip = h->tau_flip;
     p.exact_arith = 0;
     p.key_scale = h->int_ok ? h->key_scale : 0.0;
-    if (h->exact_arith && h->cfg.column_stream != HN_COLUMNS_F32 && !integer_stream(h)) {
-        p.exact_arith = 1;           // no margin: "inside" means the field is an exact zero, decided as h <= 0 -> low
-        p.tau_base = p.tau_flip = 0.0;
+    if (h->exact_arith && h->cfg.column_stream != HN_COLUMNS_F32) {
+        // no margin: "inside" means the field is an exact zero, decided as h <= 0 -> low without re-evaluation (on the
+        // integer stream too: the sweeps of a learning epoch meet thousands of exact zeros)
+        p.exact_arith = 1;
+        if (!integer_stream(h)) p.tau_base = p.tau_flip = 0.0;
     }
     if (h->cfg.column_stream == HN_COLUMNS_F32) {
         HN_TRY(ensure_w32(h));
@@ -1051,8 +1068,11 @@ int sweep_once(hn_handle h, int n, const uint16_t* perms) {
     HN_CUDA_TRY(cudaMemcpyAsync(h->offsets.p, off.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->st));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));  // `off` must outlive the copy
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_TRY(ensure_learning_image(h));
+    const bool int_fields = integer_stream(h) && h->w_symmetric;
     HN_CUDA_TRY(cudaEventRecord(h->lev[0], h->st));
-    HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain)));
+    if (int_fields) HN_TRY(integer_fields(h, h->bitsB.as<uint64_t>(), n, reinterpret_cast<int32_t*>(h->H.as<double>())));
+    else HN_TRY(launch_fields(h, h->bitsB.as<uint64_t>(), n, h->H.as<double>(), domain_values(h->cfg.domain), integer_stream(h) ? h->Wraw : nullptr));
     HN_CUDA_TRY(cudaEventRecord(h->lev[1], h->st));
     HN_TRY(h->small.reserve(sizeof(Scratch)));
     Scratch* sc = h->scratch();
@@ -1061,6 +1081,7 @@ int sweep_once(hn_handle h, int n, const uint16_t* perms) {
     p.N = N; p.ldw = h->ldw; p.words = words;
     p.Wrow = h->W;
     p.H0 = h->H.as<double>(); p.ldh = h->ldw;
+    p.H0i = int_fields ? reinterpret_cast<const int32_t*>(h->H.as<double>()) : nullptr;
     p.probes = h->bitsB.as<uint64_t>(); p.perm_pool = d_perm; p.inv_pool = d_inv; p.ldp = h->ldp; p.n_pool = n;
     p.offsets = h->offsets.as<int32_t>(); p.B = n; p.max_iter = 1; p.max_unstable = 0; p.domain = h->cfg.domain;
     p.check_stability = 0; p.serial_stream = 0;
@@ -1159,13 +1180,24 @@ int energy_profiles_impl(hn_handle h, const uint64_t* d_states, int n, double* e
     const int N = h->N;
     HN_TRY(ensure_margin(h));
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)n * h->ldw));
+    HN_TRY(ensure_learning_image(h));
+    // exact arithmetic (quarter-integer weights) with the integer image at hand: fields from the integer tensor path, the
+    // float64 energies follow exactly (h = g / scale, every product and sum exact)
+    const bool int_path = h->exact_arith && integer_stream(h) && h->w_symmetric;
     HN_CUDA_TRY(cudaEventRecord(h->lev[7], h->st));
-    HN_TRY(launch_fields(h, d_states, n, h->H.as<double>(), domain_values(h->cfg.domain)));
+    if (int_path) HN_TRY(integer_fields(h, d_states, n, reinterpret_cast<int32_t*>(h->H.as<double>())));
+    else HN_TRY(launch_fields(h, d_states, n, h->H.as<double>(), domain_values(h->cfg.domain)));
     HN_CUDA_TRY(cudaEventRecord(h->lev[0], h->st));
     if (energies_out) HN_TRY(h->energies.reserve(sizeof(double) * (size_t)n * N));
     HN_TRY(h->eunst.reserve(sizeof(int32_t) * (size_t)n));
     HN_TRY(h->estab.reserve((size_t)n));
     HN_TRY(h->esum.reserve(sizeof(double) * (size_t)n));
+    if (int_path)
+        energy_epilogue_i32_kernel<<<n, RED_THREADS, 0, h->st>>>(reinterpret_cast<const int32_t*>(h->H.as<double>()), h->ldw, d_states, h->words, N,
+                                                                h->cfg.domain, 1.0 / h->int_scale, h->cfg.max_relax_unstable_units,
+                                                                energies_out ? h->energies.as<double>() : nullptr,
+                                                                h->eunst.as<int32_t>(), h->estab.as<uint8_t>(), h->esum.as<double>());
+    else
     energy_epilogue_kernel<<<n, RED_THREADS, 0, h->st>>>(h->H.as<double>(), h->ldw, d_states, h->words, h->W, h->ldw, N,
                                                         h->cfg.domain, h->exact_arith ? 0.0 : h->tau_base, h->cfg.max_relax_unstable_units,
                                                         energies_out ? h->energies.as<double>() : nullptr,

@@ -382,6 +382,43 @@ energy_epilogue_kernel(const double* __restrict__ H, int ldh, const uint64_t* __
     }
 }
 
+// The same from the EXACT integer fields G = M s of the integer tensor path (exact-arithmetic weights, i.e. inside a
+// learning run): (M s)_u = 2 g_u + diag * s_u with g = K s and K = scale * W, so the float64 field is h = g / scale
+// exactly and e = -0.5 * (h * v) is the reference's value bit for bit; a zero field is an exact zero (energy not > 0).
+__global__ void __launch_bounds__(RED_THREADS)
+energy_epilogue_i32_kernel(const int32_t* __restrict__ G, int ldg, const uint64_t* __restrict__ states, int words, int n, int domain,
+                           double inv_scale, int max_unstable, double* __restrict__ energies, int32_t* __restrict__ unstable,
+                           uint8_t* __restrict__ stable, double* __restrict__ state_energy) {
+    __shared__ double sm[RED_THREADS / 32];
+    __shared__ int s_cnt;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(states + (size_t)s * words);
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    double esum = 0.0;
+    int cnt = 0;
+    for (int i = tid; i < n; i += RED_THREADS) {
+        const int b = (int)((bits[i >> 5] >> (i & 31)) & 1u);
+        // diag * s_u: bipolar -1 * (+-1); binary -2 * (0 / 1)
+        const int self = domain == HN_DOMAIN_BINARY ? -2 * b : (b ? -1 : 1);
+        const int g = (G[(size_t)s * ldg + i] - self) / 2;   // exact: the difference is even
+        const double h = (double)g * inv_scale;
+        const double v = b ? 1.0 : -1.0;
+        const double e = -0.5 * (h * v);
+        if (energies) energies[(size_t)s * n + i] = e;
+        esum += e;
+        if (e > 0.0) cnt++;
+    }
+    atomicAdd(&s_cnt, cnt);
+    const double r = block_reduce_sum_det(esum, sm);
+    __syncthreads();
+    if (tid == 0) {
+        if (unstable) unstable[s] = s_cnt;
+        if (stable) stable[s] = (uint8_t)(s_cnt <= max_unstable);
+        if (state_energy) state_energy[s] = r;
+    }
+}
+
 // ---- UnitEnergy: the reference's scalar loop (API surface, not used by its main) ----
 // BipolarDomainManager.go:29-37:  energy += -0.5 * W_ij * s_i * s_j            (left to right, sequential over j)
 // BinaryDomainManager.go:43-52:   energy += -0.5 * W_ij * s_i * (2 s_j - 1) - 1 (sic: one -1 per term)

@@ -634,7 +634,7 @@ relax_kernel(RelaxParams p) {
                 k3 ^= k3 >> 14; k3 *= 0x85EBCA6Bu; k3 ^= k3 >> 16;
                 h2 = ((uint64_t)k1 << 32) | k0;
                 h3 = ((uint64_t)k3 << 32) | k2;
-                if (!p.exact_arith && tid == 0) { h2 ^= s_tz[0]; h3 ^= s_tz[1]; }   // units whose re-evaluated float field is +0
+                if ((INTF || !p.exact_arith) && tid == 0) { h2 ^= s_tz[0]; h3 ^= s_tz[1]; }   // units whose re-evaluated float field is +0
             }
             {
                 const bool inv = (p.domain == HN_DOMAIN_BIPOLAR) && (s_bits[0] & 1u) && !s_zero_field;

@@ -28,14 +28,16 @@ def test_hebbian_epoch_bitwise(built, n, p, domain):
     net.close()
 
 
+@pytest.mark.parametrize("stream", [0, 3])   # float64 column stream / AUTO: inside a learning run AUTO rebuilds the integer image of
+                                             # the un-normalised weights every epoch (integer-path sweeps, fields and diagnostics)
 @pytest.mark.parametrize("n,p,domain,sym", [(128, 12, 0, True), (200, 20, 0, False), (256, 30, 1, True), (1024, 100, 0, True)])
-def test_delta_epochs_bitwise(built, n, p, domain, sym):
+def test_delta_epochs_bitwise(built, n, p, domain, sym, stream):
     """Several Delta epochs with MaximalInversion noise; explicit noised copies + permutations (the
     RNG-derived inputs) are shared by oracle and GPU.  W, relaxed copies: bit-exact."""
     rng = orc.Rng(31)
     t = rng.generate_states(domain, n, p)
     onet = orc.Net(n, domain=domain, force_symmetric=sym)
-    net = gpu_net(n, domain, SetForceSymmetric=sym)
+    net = gpu_net(n, domain, SetForceSymmetric=sym, SetColumnStream=stream)
     for epoch in range(4):
         noised = t.copy()
         for s in range(p):

@@ -92,7 +92,7 @@ struct Scratch {
     unsigned long long maxabs_bits;    // ensure_margin: max |W_ij|
     unsigned long long maxabs_raw_bits;  // build_integer_structure: max |Wraw_ij|
     int32_t dense_unfinished;          // dense sweeps: probes not yet stable after the last scan
-    int32_t dense_pad;
+    int32_t frac_flags;                // fused update: 1 not even integers, 2 not integers, 4 not halves somewhere in W
     unsigned long long dense_flips;    // dense sweeps: flips of the last sweep
     int32_t pair_count[2];             // dedup level 2: [0] merges of different states recorded, [1] refuted by the float profiles
     unsigned long long totals[3];      // relax: sum of flips, sweeps, margin hits over the batch (sum_counters_kernel)
@@ -148,6 +148,7 @@ struct hn_handle_s {
     double dense_min_flips = 200.0;   // sweep densely again while the last sweep flipped more than this per unfinished probe (the next one
                                       // flips ~0.75x as many; a dense sweep costs what ~160 flips per probe cost the sparse kernel)
     int last_dense_sweeps = 0;
+    int frac_flags = 7; uint64_t frac_version = 0;   // which fractions occur in W (fused update kernel), and for which W
     uint64_t image_tried_version = 0;   // ensure_learning_image: the W version the image was last (tried to be) built for
     bool fused_flags_valid = false;   // Scratch::maxabs_bits / not_quarters describe the current W (update_constraints_i32_kernel)
     DevBuf opA8, opB8;                // int8 operands of the learning contractions (tcgen05 path)
@@ -193,10 +194,12 @@ int ensure_margin(hn_handle h) {
     Scratch* sc = h->scratch();
     if (h->fused_flags_valid) {   // the fused update kernel already scanned the new W (max |W|, quarter test)
         h->fused_flags_valid = false;
-        double mx = 0; int32_t nq = 1;
+        double mx = 0; int32_t nq = 1, ff = 7;
         HN_CUDA_TRY(cudaMemcpyAsync(&mx, &sc->maxabs_bits, 8, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaMemcpyAsync(&nq, &sc->not_quarters, 4, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaMemcpyAsync(&ff, &sc->frac_flags, 4, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        h->frac_flags = ff; h->frac_version = h->w_version;
         if (!nq && 4.0 * (double)h->N * mx < 2251799813685248.0) {
             // exact arithmetic (see below): no margin is ever consulted; keep a valid upper bound in tau anyway
             const double u = 1.1102230246251565e-16, r = (double)h->N * mx;
@@ -263,7 +266,8 @@ int launch_fields(hn_handle h, const uint64_t* d_states, int count, double* d_H,
 // of the parity of P; Delta: half / quarter integers); int_ok only if every entry fits int16 and the exactness bound of
 // the field holds.  (An int8 image with dp4a was tried for |K| <= 127: half the column bytes, no faster — the kernel is
 // bound by its dependent chain and issue slots, not by the L2->SM bytes; profiles/r01_relax_i16_final_ncu_summary.txt.)
-int build_integer_structure(hn_handle h, bool symmetric, double c, const double* raw = nullptr) {   // c: W = fl(c * raw); raw defaults to h->Wraw
+int build_integer_structure(hn_handle h, bool symmetric, double c, const double* raw = nullptr, int first_scale = 0,
+                            double known_max = -1.0) {   // c: W = fl(c * raw); raw defaults to h->Wraw
     if (!raw) raw = h->Wraw;
     const int64_t total = (int64_t)h->N * h->ldw;
     if (!h->K16) HN_CUDA_TRY(cudaMalloc(&h->K16, sizeof(int16_t) * (size_t)total));
@@ -279,10 +283,16 @@ int build_integer_structure(hn_handle h, bool symmetric, double c, const double*
         transpose_kernel<<<g, b, 0, h->st>>>(raw, h->dW, h->N, h->ldw);
         src = h->dW;
     }
-    maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(raw, h->N, h->ldw, mx, nullptr);
-    HN_CUDA_TRY(cudaGetLastError());
+    if (known_max < 0.0) {
+        maxabs_kernel<<<h->sms * 4, 256, 0, h->st>>>(raw, h->N, h->ldw, mx, nullptr);
+        HN_CUDA_TRY(cudaGetLastError());
+    } else {
+        HN_CUDA_TRY(cudaMemcpyAsync(mx, &known_max, 8, cudaMemcpyHostToDevice, h->st));
+    }
     int32_t f = 1; double m = 0;
-    for (double scale : {0.5, 1.0, 2.0, 4.0}) {
+    const double scales[4] = {0.5, 1.0, 2.0, 4.0};
+    for (int si = first_scale; si < 4; si++) {
+        const double scale = scales[si];
         HN_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, h->st));
         to_i16_kernel<<<grid_for(total, 256, h->sms), 256, 0, h->st>>>(src, h->K16, total, h->ldw, scale,
                                                                        h->cfg.domain == HN_DOMAIN_BINARY ? -2 : -1, flag);
@@ -349,7 +359,9 @@ int ensure_learning_image(hn_handle h) {
     HN_TRY(ensure_margin(h));
     if (!h->exact_arith || h->maxabs == 0.0 || h->image_tried_version == h->w_version) return HN_OK;
     h->image_tried_version = h->w_version;
-    return build_integer_structure(h, true, 1.0, h->W);
+    int first = 0;   // the fused update kernel already saw which fractions occur: go straight to the scale that fits
+    if (h->frac_version == h->w_version) first = (h->frac_flags & 4) ? 3 : (h->frac_flags & 2) ? 2 : (h->frac_flags & 1) ? 1 : 0;
+    return build_integer_structure(h, true, 1.0, h->W, first, h->maxabs);
 }
 
 // float32 shadow of the column matrix (W if symmetric else W^T), rebuilt after any weight change
@@ -456,12 +468,23 @@ int upload_pool(hn_handle h, const uint16_t* pool, int rows, DevBuf& buf, uint16
                                   sizeof(uint16_t) * h->N, rows, cudaMemcpyHostToDevice, h->st));
     dim3 g(rows, std::max(1, std::min(64, (h->N + 255) / 256)));
     invert_perm_kernel<<<g, 256, 0, h->st>>>(*d_perm, *d_inv, h->N, h->ldp, rows);
+    // validated on the device (the host loop over rows x N entries costs more than a learning epoch at N = 16384)
+    HN_TRY(h->small.reserve(sizeof(Scratch)));
+    int32_t* bad = &h->scratch()->asym_flag;   // free here: detect_symmetry uses it only inside its own call
+    HN_CUDA_TRY(cudaMemsetAsync(bad, 0, 4, h->st));
+    check_perm_kernel<<<g, 256, 0, h->st>>>(*d_perm, *d_inv, h->N, h->ldp, rows, bad);
     HN_CUDA_TRY(cudaGetLastError());
+    int32_t b = 0;
+    HN_CUDA_TRY(cudaMemcpyAsync(&b, bad, 4, cudaMemcpyDeviceToHost, h->st));
+    HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (b) { set_error("perm_pool row %d is not a permutation of 0..%d", b - 1, h->N - 1); return HN_E_INVALID; }
     return HN_OK;
 }
 
 int validate_pool_host(hn_handle h, const uint16_t* pool, int rows) {
-    // every row must be a permutation of 0..N-1 (a bad row would corrupt device memory)
+    // every row must be a permutation of 0..N-1 (a bad row would corrupt device memory); small pools are checked here,
+    // before any device work, every pool again on the device when it is uploaded (upload_pool)
+    if ((int64_t)rows * h->N > (1 << 20)) return HN_OK;
     std::vector<uint8_t> seen((size_t)h->N);
     for (int r = 0; r < rows; r++) {
         std::fill(seen.begin(), seen.end(), 0);
@@ -604,7 +627,8 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
     const int tiles = (B + DS_T - 1) / DS_T;
     h->last_dense_sweeps = 0;
     for (int r = 0; r < rows; r++) {
-        HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_unfinished, 0, 16, h->st));   // unfinished, pad, flips
+        HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_unfinished, 0, 4, h->st));
+        HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_flips, 0, 8, h->st));
         DenseParams dp{};
         dp.N = N; dp.np = np; dp.rows_p = rp; dp.words = words; dp.B = B; dp.domain = h->cfg.domain; dp.ldw = h->ldw;
         dp.mbb = h->d_mbb.as<int8_t>() + (size_t)r * rp * DS_BLK;
@@ -961,9 +985,11 @@ int apply_update_and_constraints_int(hn_handle h, double s) {
     Scratch* sc = h->scratch();
     HN_CUDA_TRY(cudaMemsetAsync(&sc->maxabs_bits, 0, 8, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(&sc->not_quarters, 0, 4, h->st));
+    HN_CUDA_TRY(cudaMemsetAsync(&sc->frac_flags, 0, 4, h->st));
     dim3 g((h->N + 31) / 32, (h->N + 31) / 32), b(32, 8);
     update_constraints_i32_kernel<<<g, b, 0, h->st>>>(h->W, reinterpret_cast<const int32_t*>(h->dW), h->N, h->ldw, h->cfg.learning_rate, s,
-                                                     h->cfg.force_zero_diagonal, h->cfg.force_symmetric, &sc->maxabs_bits, &sc->not_quarters);
+                                                     h->cfg.force_zero_diagonal, h->cfg.force_symmetric, &sc->maxabs_bits, &sc->not_quarters,
+                                                     &sc->frac_flags);
     HN_CUDA_TRY(cudaGetLastError());
     h->w_symmetric = h->cfg.force_symmetric != 0;
     weights_changed(h);

@@ -45,13 +45,24 @@ __global__ void expand_units_i8_kernel(const uint64_t* __restrict__ bitsA, const
     }
 }
 
+// which fractions occur: off <- v is not a multiple of 1/4; fr |= 1 (not an even integer) | 2 (not an integer) | 4 (not a
+// multiple of 1/2).  One conversion each way instead of four rint (FP64 pipe): q = 4v as an integer when it is one.
+__device__ __forceinline__ void frac_scan(double v, bool& off, int& fr) {
+    const double v4 = 4.0 * v;
+    if (fabs(v4) < 4503599627370496.0) {
+        const long long q = __double2ll_rn(v4);
+        if ((double)q != v4) { off = true; fr |= 7; }
+        else fr |= ((q & 7) ? 1 : 0) | ((q & 3) ? 2 : 0) | ((q & 1) ? 4 : 0);
+    } else { off = true; fr |= 7; }   // beyond 2^50: no exact-arithmetic claim
+}
+
 // ---- W <- W + lr*(s*dWi), then enforceConstraints, in ONE pass over tile pairs (LearningRule.go:72-74 / :111-113) ----
 // dWi: the exact integer contraction (all-reduced over the ranks), s = 1 (Hebbian) or 0.5 (Delta): s*dWi is the
 // reference's updatedMatrix entry exactly, fl(lr * .) its Scale, fl(W + .) its Add; zero diagonal, then 0.5*(W + W^T)
 // from the updated values.  Also the max |W| and the "every entry a multiple of 1/4" flag ensure_margin needs.
 __global__ void update_constraints_i32_kernel(double* __restrict__ w, const int32_t* __restrict__ dwi, int n, int ld, double lr,
                                               double s, int zero_diag, int symmetric, unsigned long long* maxabs_bits,
-                                              int32_t* not_quarters) {
+                                              int32_t* not_quarters, int32_t* frac_flags) {
     __shared__ double ta[32][33], tb[32][33];
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj < bi) return;
@@ -71,13 +82,14 @@ __global__ void update_constraints_i32_kernel(double* __restrict__ w, const int3
     __syncthreads();
     double m = 0.0;
     bool off = false;
+    int fr = 0;   // 1: some entry is not an even integer, 2: not an integer, 4: not a multiple of 1/2
     for (int r = ty; r < 32; r += blockDim.y) {
         const int i = bi * 32 + r, j = bj * 32 + tx;
         if (i < n && j < n) {
             const double a = ta[r][tx];
             const double v = symmetric ? __dmul_rn(0.5, __dadd_rn(a, tb[tx][r])) : a;
             w[(size_t)i * ld + j] = v;
-            m = fmax(m, fabs(v)); off |= rint(4.0 * v) != 4.0 * v;
+            m = fmax(m, fabs(v)); frac_scan(v, off, fr);
         }
         if (bi != bj) {
             const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
@@ -85,10 +97,11 @@ __global__ void update_constraints_i32_kernel(double* __restrict__ w, const int3
                 const double b = tb[r][tx];
                 const double v = symmetric ? __dmul_rn(0.5, __dadd_rn(b, ta[tx][r])) : b;
                 w[(size_t)i2 * ld + j2] = v;
-                m = fmax(m, fabs(v)); off |= rint(4.0 * v) != 4.0 * v;
+                m = fmax(m, fabs(v)); frac_scan(v, off, fr);
             }
         }
     }
+    if (fr) atomicOr(frac_flags, fr);
     if (off) *not_quarters = 1;
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
     if (tx == 0) atomicMax(maxabs_bits, (unsigned long long)__double_as_longlong(m));
@@ -302,8 +315,21 @@ __global__ void invert_perm_kernel(const uint16_t* __restrict__ perm, uint16_t* 
                                    int ldp, int rows) {
     const int r = blockIdx.x;
     if (r >= rows) return;
-    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x)
-        inv[(size_t)r * ldp + perm[(size_t)r * ldp + i]] = (uint16_t)i;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+        const int u = perm[(size_t)r * ldp + i];
+        if (u < n) inv[(size_t)r * ldp + u] = (uint16_t)i;   // entries >= n are reported by check_perm_kernel
+    }
+}
+// every row must be a permutation of 0..n-1 (a bad row would send the relaxation kernel out of bounds): after the
+// inversion, perm[inv[u]] == u for every unit u exactly when the row is one.  bad <- 1 + index of an offending row.
+__global__ void check_perm_kernel(const uint16_t* __restrict__ perm, const uint16_t* __restrict__ inv, int n, int ldp, int rows,
+                                  int32_t* bad) {
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    for (int u = blockIdx.y * blockDim.x + threadIdx.x; u < n; u += gridDim.y * blockDim.x) {
+        const int pos = inv[(size_t)r * ldp + u];
+        if (perm[(size_t)r * ldp + u] >= n || pos >= n || perm[(size_t)r * ldp + pos] != u) atomicMax(bad, r + 1);
+    }
 }
 
 // ---- bit-matrix transpose: X[P][words] (state-major) -> XT[N][pwords] (unit-major)

@@ -292,8 +292,9 @@ def main():
         t = net.last_timing()
         if os.environ.get("HN_MERGE_TRACE") and rank == 0:
             print(f"[resident trace] device {dev_ms[-1]:.2f}: dense {t.dense_ms:.2f} fields {t.fields_ms:.2f} relax {t.relax_ms:.2f} post {t.post_ms:.2f}", flush=True)
-        for k in ("fields_ms", "relax_ms", "post_ms", "dense_ms"):
+        for k in ("fields_ms", "relax_ms", "post_ms", "dense_ms", "dense_kernel_ms", "dense_gemm_ms", "dense_scan_ms"):
             stage.setdefault(k, []).append(getattr(t, k, 0.0))
+        dense_sweeps, dense_flips = t.dense_sweeps, t.dense_flips
         launches += t.launches
     barrier()
     wall = time.perf_counter() - t0
@@ -302,7 +303,11 @@ def main():
     out = capi.HnRelaxOut()
     capi.check(capi.load().hn_download_results(net._h, C.byref(out)))
     flips, sweeps = out.total_flips, out.total_sweeps
-    alg_bytes = 8 * n * flips + 8 * n * sweeps + b * (n // 4 + 4 * p + 16)
+    # the share of the sparse kernel (the dominant one): what the dense lockstep sweeps did not do.  Every probe of this
+    # workload is still unstable after the dense sweeps, so each of them counts dense_sweeps sweeps there.
+    sp_flips, sp_sweeps = flips - dense_flips, sweeps - b * dense_sweeps
+    alg_bytes = 8 * n * sp_flips + 8 * n * sp_sweeps + b * (n // 4 + 4 * p + 16)
+    alg_bytes_all = 8 * n * flips + 8 * n * sweeps + b * (n // 4 + 4 * p + 16)
     step_ms = float(np.sum(dev_ms))
     # e2e: host buffers through hn_relax_batch (+ the cross-GPU merge of the unique tables), every step timed
     e2e_t = []
@@ -342,7 +347,7 @@ def main():
             alt_ms[name] = alt.relax_resident(dedup=True)
             alt_relax_ms[name] = alt.last_timing().relax_ms
             alt.close()
-    relax_total = float(np.sum(stage["relax_ms"])) + float(np.sum(stage.get("dense_ms", [0.0])))
+    relax_total = float(np.sum(stage["relax_ms"]))
     tmax = torch.tensor([step_ms, relax_total, float(np.mean(e2e_t)), alt_ms["f64"], alt_ms["f32"], alt_ms["i16"],
                          alt_relax_ms["f64"]], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -362,7 +367,7 @@ def main():
         achieved = alg_bytes * args.steps / (relax_ms_max * 1e-3) / 1e9
         col_bytes = {"f64": 8, "f32": 4, "i16": 2}[stream]
         field_bytes = 4 if stream == "i16" else 8
-        streamed = col_bytes * n * flips + field_bytes * n * sweeps     # what the sparse stream moves L2->SM per launch
+        streamed = col_bytes * n * sp_flips + field_bytes * n * sp_sweeps     # what the sparse kernel moves L2->SM per launch
         kernel = {"f64": "relax_kernel<32,double,128,4>", "f32": "relax_kernel<32,float,128,4>", "i16": "relax_kernel<32,short,128,9>"}[stream]
         # measured L2->SM read bandwidth with this kernel's access shape (tools/peaks_microbench.cu -> profiles/r02_peaks.json)
         def l2_peak(mib):
@@ -384,14 +389,17 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                              "traffic": None, "kernel": kernel,
-                             "note": "per GPU; SURVEY 8(d)'s line: ALGORITHMIC bytes of the reference algorithm (one float64 column "
-                                     "per flip + one pass over the fields per sweep) over the relaxation time, against the measured "
-                                     "HBM copy peak.  HBM does not bind this path (traffic << algorithmic bytes: the weight image is "
-                                     "L2 resident and narrower than float64), so the fraction exceeds 1; roofline_l2 and issue_frac "
-                                     "are the fractions of the resources that do bind",
+                             "note": "per GPU, the dominant kernel (sparse relaxation, after the dense lockstep sweeps).  SURVEY 8(d)'s "
+                                     "line: ALGORITHMIC bytes of the reference algorithm for the flips and sweeps this kernel performs (one "
+                                     "float64 column per flip + one pass over the fields per sweep) over its time, against the measured HBM "
+                                     "copy peak.  HBM does not bind this path (traffic << algorithmic bytes: the weight image is L2 "
+                                     "resident and narrower than float64), so the fraction exceeds 1; roofline_l2 and issue_frac are the "
+                                     "fractions of the resources that do bind, roofline_dense describes the tensor-core phase",
                              "peak_source": "measured" if peaks else "fallback",
-                             "algorithmic_bytes_per_launch": int(alg_bytes),
-                             "flips_per_probe": flips / b, "sweeps_per_probe": sweeps / b},
+                             "algorithmic_bytes_per_launch": int(alg_bytes), "algorithmic_bytes_whole_relaxation": int(alg_bytes_all),
+                             "whole_relaxation_gbs": alg_bytes_all * args.steps / ((relax_ms_max + float(np.sum(stage["dense_ms"]))) * 1e-3) / 1e9,
+                             "flips_per_probe": flips / b, "sweeps_per_probe": sweeps / b,
+                             "flips_per_probe_in_this_kernel": sp_flips / b, "sweeps_per_probe_in_this_kernel": sp_sweeps / b},
                 "roofline_l2": {"bound": "l2_to_sm", "achieved": streamed * args.steps / (relax_ms_max * 1e-3) / 1e9, "peak": l2pk,
                                 "unit": "GB/s", "streamed_bytes_per_launch": int(streamed),
                                 "peak_source": "profiles/r02_peaks.json: tools/peaks_microbench.cu, independent pseudo-random rows "
@@ -401,10 +409,15 @@ def main():
                                         "its weight tiles by TMA and is not counted here"},
                 "issue_frac": issue.get("issue_slots_busy_frac"),
                 "issue_frac_source": issue.get("source"),
+                "roofline_dense": dense_roofline(n, b, dense_sweeps, dense_flips, stage, own, load_json("profiles", "r02_relax_issue.json")),
                 "clocks": sampler.summary(), "wall_s": wall,
                 "stage_ms_per_step": {"fields_gemm": float(np.mean(stage["fields_ms"])), "relax": float(np.mean(stage["relax_ms"])),
-                                      "dense_sweeps": float(np.mean(stage.get("dense_ms", [0.0]))),
+                                      "dense_sweeps": float(np.mean(stage["dense_ms"])),
+                                      "dense_sweep_kernel": float(np.mean(stage["dense_kernel_ms"])),
+                                      "dense_fields_gemm": float(np.mean(stage["dense_gemm_ms"])),
+                                      "dense_stability_scan": float(np.mean(stage["dense_scan_ms"])),
                                       "dedup": float(np.mean(stage["post_ms"]))},
+                "dense_sweeps_per_step": int(dense_sweeps),
                 "margin_hits_per_probe": out.total_margin_hits / b,
                 "unique_attractors": int(n_unique_global if n_unique_global is not None else out.n_unique),
                 "unique_table": {"different_state_merges_verified": verified, "refuted": refuted}}
@@ -453,6 +466,33 @@ def main():
     net.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def dense_roofline(n, b, sweeps, dense_flips, stage, own, ncu):
+    """The tensor-core phase: `sweeps` lockstep sweeps per step, each an N x N x B int8 contraction computed block by block
+    (32 positions x 32 probes, K cut in four quarters to fill the 128-row MMA: one quarter of the issued MACs are fields),
+    plus the exact fields contraction (N x N x B) after every sweep."""
+    if not sweeps:
+        return None
+    km, gm = float(np.mean(stage["dense_kernel_ms"])), float(np.mean(stage["dense_gemm_ms"]))
+    useful = 2.0 * n * n * b * sweeps
+    pk = {e["n"]: e["tops"] for e in own.get("tcgen05_i8", [])}
+    tiles = (b + 31) // 32
+    np_, rp = (n + 511) // 512 * 512, (n + 31) // 32 * 32
+    stream = float(tiles) * rp * np_ * sweeps
+    tma = max([e["gbs"] for e in own.get("tma_stream", [])], default=None)
+    d = ncu.get("dense_sweep", {})
+    return {"bound": "tensor", "unit": "TOP/s", "kernel": "dense_sweep_kernel",
+            "achieved_useful": useful / (km * 1e-3) / 1e12, "achieved_issued": 4 * useful / (km * 1e-3) / 1e12,
+            "peak": pk.get(128) or pk.get(256), "peak_source": "profiles/r02_peaks.json: tcgen05.mma.kind::i8 M=128 N=128 K=32 issue rate on resident tiles",
+            "frac_issued": (4 * useful / (km * 1e-3) / 1e12) / (pk.get(128) or pk.get(256)) if (pk.get(128) or pk.get(256)) else None,
+            "tensor_pipe_active_frac": d.get("tensor_pipe_active_frac"), "tensor_pipe_source": d.get("source"),
+            "weight_stream": {"bytes_per_step": stream, "gbs": stream / (km * 1e-3) / 1e9, "tma_stream_peak_gbs": tma,
+                              "note": "every tile of 32 probes streams the whole byte image (N x N) through TMA once per sweep; L2 resident"},
+            "flips_per_probe": dense_flips / b, "sweeps": int(sweeps),
+            "fields_gemm": {"kernel": "igemm_tc05_kernel<true>", "top_s": useful / (gm * 1e-3) / 1e12 if gm > 0 else None, "peak": pk.get(256),
+                            "frac": (useful / (gm * 1e-3) / 1e12) / pk[256] if gm > 0 and 256 in pk else None,
+                            "note": "131072 x 4096 x 4096 per sweep, int32 output written to HBM (2 GiB): bound by the output store"}}
 
 
 def measure_delta_epoch(hn, local, n, p, epochs, noise_scale=0.1, dist=None, rank=0, world=1, cpu=False):
@@ -511,8 +551,11 @@ def measure_delta_epoch(hn, local, n, p, epochs, noise_scale=0.1, dist=None, ran
     sweep_bytes = 8.0 * n * st["sweep_flips"] + p * (8.0 * n + n / 4)       # one float64 column per flip + one pass over the fields
     res = {"ms": ms, "targets_per_gpu": p, "n_gpus": world, "device_stage_ms": {k2: v for k2, v in st.items() if k2 != "sweep_flips"},
            "sweep_flips_per_target": st["sweep_flips"] / p,
-           "roofline": {"fp64_tensor": {"bound": "tensor", "unit": "TFLOP/s", "peak": fp64_peak,
+           "roofline": {"fp64_tensor": {"bound": "tensor", "unit": "TFLOP/s (equivalent: 2 N^2 P per contraction)", "peak": fp64_peak,
                                         "peak_source": "profiles/r02_peaks.json: mma.sync.m8n8k4.f64 issue rate (tcgen05 has no f64 kind)",
+                                        "note": "the reference's contractions are float64; with exact-arithmetic weights (every Delta / Hebbian "
+                                                "epoch from a zero matrix) the library computes all three as exact int8 tensor-core "
+                                                "contractions (tcgen05), so the equivalent rate exceeds the FP64 pipe's peak",
                                         "sweep_fields_gemm": tf(st["sweep_fields_ms"]), "dw_gemm": tf(st["dw_gemm_ms"]),
                                         "energies_gemm": tf(st["energy_gemm_ms"]), "flop_per_gemm": gemm_flop},
                         "sweep": {"bound": "hbm", "unit": "GB/s", "peak": hbm,

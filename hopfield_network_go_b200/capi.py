@@ -54,7 +54,9 @@ class HnLearnTiming(C.Structure):
 
 class HnRelaxTiming(C.Structure):
     _fields_ = [("fields_ms", C.c_double), ("relax_ms", C.c_double), ("post_ms", C.c_double),
-                ("launches", C.c_int32), ("dense_sweeps", C.c_int32), ("dense_ms", C.c_double)]
+                ("launches", C.c_int32), ("dense_sweeps", C.c_int32), ("dense_ms", C.c_double),
+                ("dense_kernel_ms", C.c_double), ("dense_gemm_ms", C.c_double), ("dense_scan_ms", C.c_double),
+                ("dense_flips", C.c_int64)]
 
 
 _lib = None

@@ -104,6 +104,9 @@ struct hn_handle_s {
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr;               // copy stream: probes in / results out under the kernels of the next range
     std::vector<cudaEvent_t> chunk_ev;        // six events per range of a chunked batch
+    std::vector<cudaEvent_t> dense_ev;        // four events per dense sweep (start, sweep kernel, fields contraction, scan)
+    double acc_dense_kernel_ms = 0, acc_dense_gemm_ms = 0, acc_dense_scan_ms = 0;   // sums over the ranges of the current batch
+    int64_t acc_dense_flips = 0;
     double* W = nullptr;
     double* WT = nullptr;
     double* dW = nullptr;
@@ -626,7 +629,14 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
     HN_CUDA_TRY(cudaFuncSetAttribute(dense_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (B + DS_T - 1) / DS_T;
     h->last_dense_sweeps = 0;
+    while ((int)h->dense_ev.size() < 4 * rows) {
+        cudaEvent_t e;
+        HN_CUDA_TRY(cudaEventCreate(&e));
+        h->dense_ev.push_back(e);
+    }
     for (int r = 0; r < rows; r++) {
+        cudaEvent_t* de = &h->dense_ev[4 * (size_t)r];
+        HN_CUDA_TRY(cudaEventRecord(de[0], h->st));
         HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_unfinished, 0, 4, h->st));
         HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_flips, 0, 8, h->st));
         DenseParams dp{};
@@ -642,18 +652,27 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         dp.prof = prof ? h->partial.as<unsigned long long>() : nullptr;
         dense_sweep_kernel<<<std::min(tiles, h->sms), DS_THREADS, smem, h->st>>>(h->dense_map, dp);
         HN_CUDA_TRY(cudaGetLastError());
+        HN_CUDA_TRY(cudaEventRecord(de[1], h->st));
         HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, reinterpret_cast<int32_t*>(h->H.as<double>())));
+        HN_CUDA_TRY(cudaEventRecord(de[2], h->st));
         dense_scan_kernel<<<(B * 32 + 255) / 256, 256, 0, h->st>>>(reinterpret_cast<const int32_t*>(h->H.as<double>()), h->ldw,
                                                                    h->d_state.as<uint64_t>(), words, N, B, h->cfg.domain, h->W, h->ldw,
                                                                    h->cfg.max_relax_unstable_units, h->d_finished.as<uint8_t>(),
                                                                    h->d_dmargin.as<int32_t>(), &sc->dense_unfinished);
         HN_CUDA_TRY(cudaGetLastError());
+        HN_CUDA_TRY(cudaEventRecord(de[3], h->st));
         if (launches) *launches += 3;
         h->last_dense_sweeps = r + 1;
         int32_t unf = 0; unsigned long long fl = 0;
         HN_CUDA_TRY(cudaMemcpyAsync(&unf, &sc->dense_unfinished, 4, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaMemcpyAsync(&fl, &sc->dense_flips, 8, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        {
+            float a = 0, b2 = 0, c2 = 0;
+            cudaEventElapsedTime(&a, de[0], de[1]); cudaEventElapsedTime(&b2, de[1], de[2]); cudaEventElapsedTime(&c2, de[2], de[3]);
+            h->acc_dense_kernel_ms += a; h->acc_dense_gemm_ms += b2; h->acc_dense_scan_ms += c2;
+            h->acc_dense_flips += (int64_t)fl;
+        }
         if (prof) {   // clock cycles of CTA 0 by phase, per block of 32 positions (diagnostic)
             unsigned long long pc[8];
             HN_CUDA_TRY(cudaMemcpy(pc, h->partial.p, 64, cudaMemcpyDeviceToHost));
@@ -768,6 +787,7 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
     }
 
     int launches = 0, dense_sweeps = 0;
+    h->acc_dense_kernel_ms = h->acc_dense_gemm_ms = h->acc_dense_scan_ms = 0; h->acc_dense_flips = 0;
     Scratch* sc = h->scratch();
     HN_CUDA_TRY(cudaMemsetAsync(sc, 0, offsetof(Scratch, asym_flag), h->st));   // work counter, status, unique total
     if (dedup) HN_CUDA_TRY(cudaMemsetAsync(h->hash.p, 0, sizeof(uint64_t) * 4 * (size_t)B, h->st));
@@ -875,6 +895,8 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
     cudaEventElapsedTime(&q, h->ev[2], h->ev[3]);
     h->timing.fields_ms = tf; h->timing.relax_ms = tr; h->timing.post_ms = q; h->timing.launches = launches;
     h->timing.dense_ms = td; h->timing.dense_sweeps = dense_sweeps;
+    h->timing.dense_kernel_ms = h->acc_dense_kernel_ms; h->timing.dense_gemm_ms = h->acc_dense_gemm_ms;
+    h->timing.dense_scan_ms = h->acc_dense_scan_ms; h->timing.dense_flips = h->acc_dense_flips;
     h->result_B = B; h->result_P = want_dist ? h->P : 0; h->result_flags = flags | (want_energies ? 0x100u : 0u);
     return HN_OK;
 }
@@ -1367,6 +1389,7 @@ int hn_destroy(hn_handle h) {
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->lev) if (e) cudaEventDestroy(e);
     for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->dense_ev) if (e) cudaEventDestroy(e);
     if (h->st2) { cudaStreamSynchronize(h->st2); cudaStreamDestroy(h->st2); }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;

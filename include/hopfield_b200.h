@@ -342,6 +342,10 @@ typedef struct hn_relax_timing {
     int32_t launches;   /* kernels launched     */
     int32_t dense_sweeps; /* sweeps taken by the dense lockstep kernel (tcgen05 path) before the hand-over */
     double dense_ms;    /* those sweeps, with the fields contraction and stability scan after each of them */
+    double dense_kernel_ms;  /* ... of which the lockstep sweep kernel itself (tcgen05 block contractions + decisions) */
+    double dense_gemm_ms;    /* ... the exact fields contraction after every sweep (igemm_tc05)                        */
+    double dense_scan_ms;    /* ... the stability scan after every sweep                                               */
+    int64_t dense_flips;     /* units flipped by the dense sweeps (the rest of total_flips belongs to the sparse kernel) */
 } hn_relax_timing;
 int hn_last_relax_timing(hn_handle h, hn_relax_timing* t);
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_struct_layouts_match_header(built):
     assert C.sizeof(capi.HnConfig) == 40
-    assert C.sizeof(capi.HnRelaxTiming) == 40 and C.sizeof(capi.HnLearnTiming) == 72
+    assert C.sizeof(capi.HnRelaxTiming) == 72 and C.sizeof(capi.HnLearnTiming) == 72
     assert capi.HnRelaxOut.unique_cap.offset == 80 and capi.HnRelaxOut.state_hash.offset == 96
     assert C.sizeof(capi.HnRelaxOut) == 136
     cfg = capi.HnConfig()

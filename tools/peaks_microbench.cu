@@ -228,6 +228,7 @@ int main() {
             out += buf;
         };
         run(tc_i8_kernel<256>, 256, false);
+        run(tc_i8_kernel<128>, 128, false);
         run(tc_i8_kernel<64>, 64, false);
         run(tc_i8_kernel<32>, 32, false);
         run(tc_i8_kernel<16>, 16, true);

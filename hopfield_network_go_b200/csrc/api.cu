@@ -91,6 +91,7 @@ struct Scratch {
     unsigned long long rowabs_bits;    // ensure_margin: max_i sum_k |W_ik| (double bits)
     unsigned long long maxabs_bits;    // ensure_margin: max |W_ij|
     unsigned long long maxabs_raw_bits;  // build_integer_structure: max |Wraw_ij|
+    int32_t dense_ambiguous;           // dense sweeps: probes whose stability hangs on exactly-zero fields (float64 re-evaluation)
     int32_t dense_unfinished;          // dense sweeps: probes not yet stable after the last scan
     int32_t frac_flags;                // fused update: 1 not even integers, 2 not integers, 4 not halves somewhere in W
     unsigned long long dense_flips;    // dense sweeps: flips of the last sweep
@@ -142,7 +143,7 @@ struct hn_handle_s {
     bool result_profile_keyed = false;
     bool sweep_timed = false;
     // dense lockstep sweeps (dense.cuh)
-    DevBuf d_mperm, d_mbb, d_mx, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished;
+    DevBuf d_mperm, d_mbb, d_mx, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished, d_scan;   // d_scan: unstable[B], zero[B], only[B]
     CUtensorMap dense_map;
     int dense_rows = 0;
     uint64_t w_version = 1, pool_version = 1, dense_w_version = 0, dense_pool_version = 0;
@@ -502,10 +503,11 @@ int validate_pool_host(hn_handle h, const uint16_t* pool, int rows) {
 
 // G = S * M^T, exact int32 (the integer stream's initial fields; W symmetric): tcgen05 / TMEM / TMA kernel on the byte
 // image, the mma.sync kernel where the image needs two byte planes
-int integer_fields(hn_handle h, const uint64_t* d_states, int count, int32_t* d_G) {
+int integer_fields(hn_handle h, const uint64_t* d_states, int count, int32_t* d_G, int32_t* scan_unstable = nullptr,
+                   int32_t* scan_zero = nullptr) {
     const bool bipolar = h->cfg.domain == HN_DOMAIN_BIPOLAR;
     if (h->use_tc05 && h->k8_valid)
-        return launch_igemm_tc05(d_states, h->words, count, h->K8, h->ldw, h->N, bipolar, d_G, h->ldw, h->sms, h->st);
+        return launch_igemm_tc05(d_states, h->words, count, h->K8, h->ldw, h->N, bipolar, d_G, h->ldw, h->sms, h->st, scan_unstable, scan_zero);
     return launch_igemm_fields(d_states, h->words, count, h->K16, h->ldw, h->N, bipolar, d_G, h->ldw, h->int_maxabs <= 127.0, h->st);
 }
 
@@ -634,10 +636,18 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         HN_CUDA_TRY(cudaEventCreate(&e));
         h->dense_ev.push_back(e);
     }
+    HN_TRY(h->d_scan.reserve((size_t)B * 9));
+    int32_t* d_unst = h->d_scan.as<int32_t>();
+    int32_t* d_zero = d_unst + B;
+    uint8_t* d_only = reinterpret_cast<uint8_t*>(d_zero + B);
+    int32_t* G = reinterpret_cast<int32_t*>(h->H.as<double>());
+    const bool fused = h->use_tc05 && h->k8_valid;   // stability scan inside the contraction's epilogue
+    int32_t unf_prev = B;
+    bool fields_stored = false;
     for (int r = 0; r < rows; r++) {
         cudaEvent_t* de = &h->dense_ev[4 * (size_t)r];
         HN_CUDA_TRY(cudaEventRecord(de[0], h->st));
-        HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_unfinished, 0, 4, h->st));
+        HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_ambiguous, 0, 8, h->st));    // ambiguous, unfinished
         HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_flips, 0, 8, h->st));
         DenseParams dp{};
         dp.N = N; dp.np = np; dp.rows_p = rp; dp.words = words; dp.B = B; dp.domain = h->cfg.domain; dp.ldw = h->ldw;
@@ -653,19 +663,43 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         dense_sweep_kernel<<<std::min(tiles, h->sms), DS_THREADS, smem, h->st>>>(h->dense_map, dp);
         HN_CUDA_TRY(cudaGetLastError());
         HN_CUDA_TRY(cudaEventRecord(de[1], h->st));
-        HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, reinterpret_cast<int32_t*>(h->H.as<double>())));
-        HN_CUDA_TRY(cudaEventRecord(de[2], h->st));
-        dense_scan_kernel<<<(B * 32 + 255) / 256, 256, 0, h->st>>>(reinterpret_cast<const int32_t*>(h->H.as<double>()), h->ldw,
-                                                                   h->d_state.as<uint64_t>(), words, N, B, h->cfg.domain, h->W, h->ldw,
-                                                                   h->cfg.max_relax_unstable_units, h->d_finished.as<uint8_t>(),
-                                                                   h->d_dmargin.as<int32_t>(), &sc->dense_unfinished);
-        HN_CUDA_TRY(cudaGetLastError());
+        // This sweep's flips decide whether another dense sweep is worth it.  The fields go to HBM (2 GiB at config 3)
+        // only after the last one, where the sparse kernel starts from them, or when some probe's stability hangs on
+        // exactly-zero fields.
+        unsigned long long fl = 0;
+        HN_CUDA_TRY(cudaMemcpyAsync(&fl, &sc->dense_flips, 8, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        const bool last = r == rows - 1 || (double)fl < h->dense_min_flips * (double)unf_prev;
+        int32_t cnt[2] = {0, 0};   // ambiguous, unfinished
+        if (fused) {
+            HN_CUDA_TRY(cudaMemsetAsync(d_unst, 0, sizeof(int32_t) * 2 * (size_t)B, h->st));
+            HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, last ? G : nullptr, d_unst, d_zero));
+            HN_CUDA_TRY(cudaEventRecord(de[2], h->st));
+            dense_classify_kernel<<<(B + 255) / 256, 256, 0, h->st>>>(d_unst, d_zero, B, h->cfg.max_relax_unstable_units,
+                                                                      h->d_finished.as<uint8_t>(), h->d_dmargin.as<int32_t>(), d_only,
+                                                                      &sc->dense_unfinished, &sc->dense_ambiguous);
+            HN_CUDA_TRY(cudaGetLastError());
+            HN_CUDA_TRY(cudaMemcpyAsync(cnt, &sc->dense_ambiguous, 8, cudaMemcpyDeviceToHost, h->st));
+            HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+            fields_stored = last;
+        } else {
+            HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, G));
+            HN_CUDA_TRY(cudaEventRecord(de[2], h->st));
+            fields_stored = true;
+        }
+        if (!fused || cnt[0] > 0) {   // float64 re-evaluation of the exactly-zero fields (of every probe on the mma.sync path)
+            if (!fields_stored) { HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, G)); fields_stored = true; }
+            dense_scan_kernel<<<(B * 32 + 255) / 256, 256, 0, h->st>>>(G, h->ldw, h->d_state.as<uint64_t>(), words, N, B, h->cfg.domain, h->W,
+                                                                       h->ldw, h->cfg.max_relax_unstable_units, h->d_finished.as<uint8_t>(),
+                                                                       h->d_dmargin.as<int32_t>(), &sc->dense_unfinished,
+                                                                       fused ? d_only : nullptr);
+            HN_CUDA_TRY(cudaGetLastError());
+        }
         HN_CUDA_TRY(cudaEventRecord(de[3], h->st));
         if (launches) *launches += 3;
         h->last_dense_sweeps = r + 1;
-        int32_t unf = 0; unsigned long long fl = 0;
+        int32_t unf = 0;
         HN_CUDA_TRY(cudaMemcpyAsync(&unf, &sc->dense_unfinished, 4, cudaMemcpyDeviceToHost, h->st));
-        HN_CUDA_TRY(cudaMemcpyAsync(&fl, &sc->dense_flips, 8, cudaMemcpyDeviceToHost, h->st));
         HN_CUDA_TRY(cudaStreamSynchronize(h->st));
         {
             float a = 0, b2 = 0, c2 = 0;
@@ -682,8 +716,11 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
                             "end barrier %.0f | MMA warp: wait decisions %.0f, issue+stream %.0f\n", r + 1, (double)fl / std::max(1, B),
                     pc[0] / nb, pc[1] / nb, pc[2] / nb, pc[3] / nb, pc[4] / nb, pc[5] / nb, pc[6] / nb);
         }
-        if (unf == 0 || (double)fl < h->dense_min_flips * (double)unf) break;   // the sparse kernel is cheaper from here on
+        unf_prev = std::max(unf, 1);
+        if (last || unf == 0) break;   // the sparse kernel is cheaper from here on
     }
+    // every probe froze before the last planned sweep: the hand-over to the sparse kernel still reads the fields
+    if (!fields_stored) HN_TRY(integer_fields(h, h->d_state.as<uint64_t>(), B, G));
     return HN_OK;
 }
 
@@ -1375,7 +1412,7 @@ int hn_destroy(hn_handle h) {
     DevBuf* bufs[] = {&h->targets, &h->probes, &h->pool, &h->offsets, &h->H, &h->finals, &h->steps, &h->stable,
                       &h->flips, &h->margin, &h->dist, &h->hash, &h->energies, &h->history, &h->rep, &h->first, &h->hits,
                       &h->flag, &h->rank, &h->table, &h->rep1, &h->rep2, &h->pairs, &h->opA8, &h->opB8, &h->d_mperm, &h->d_mbb, &h->d_mx, &h->d_info,
-                      &h->d_state, &h->d_sweeps, &h->d_dflips, &h->d_dmargin, &h->d_finished, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
+                      &h->d_state, &h->d_sweeps, &h->d_dflips, &h->d_dmargin, &h->d_finished, &h->d_scan, &h->attractor, &h->ufirst, &h->uhits, &h->small, &h->partial,
                       &h->bitsA, &h->bitsB, &h->bitsC, &h->bitsAT, &h->bitsCT, &h->perms, &h->eunst, &h->estab, &h->esum,
                       &h->emargin};
     for (DevBuf* b : bufs) b->release();

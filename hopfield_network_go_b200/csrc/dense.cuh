@@ -509,12 +509,28 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
 // Stability test after a dense sweep (HopfieldNetwork.go:214-225) on the exact fields G = M s of the current states
 // (integer fields GEMM): one warp per probe.  U = G - bias, g2 = U + 2b = 2g; unit unstable iff v*g < 0; g == 0 is an
 // exact tie, decided on the float64 row in the reference's order and counted.  Stable probes are frozen.
+// After the fused scan of the fields contraction (igemm_tc05.cuh): per probe, unstable = #{v*g < 0}, zero = #{g == 0}.
+// More strictly unstable units than the tolerance -> the probe goes on (its zero fields are the test's exact ties: counted).
+// Otherwise, with no zero field the probe is stable and frozen; with zero fields the float64 re-evaluation of those units
+// decides (dense_scan_kernel on the stored fields, only for such probes: only[p] = 1).
+__global__ void dense_classify_kernel(const int32_t* __restrict__ unstable, const int32_t* __restrict__ zero, int B, int max_unstable,
+                                      uint8_t* __restrict__ finished, int32_t* __restrict__ margin_done, uint8_t* __restrict__ only,
+                                      int32_t* __restrict__ unfinished_total, int32_t* __restrict__ ambiguous_total) {
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= B) return;
+    only[pi] = 0;
+    if (finished[pi]) return;
+    if (unstable[pi] > max_unstable) { margin_done[pi] += zero[pi]; atomicAdd(unfinished_total, 1); }
+    else if (zero[pi] == 0) finished[pi] = 1;
+    else { only[pi] = 1; atomicAdd(ambiguous_total, 1); }
+}
+
 __global__ void __launch_bounds__(256)
 dense_scan_kernel(const int32_t* __restrict__ G, int ldg, const uint64_t* __restrict__ states, int words, int N, int B, int domain,
                   const double* __restrict__ W, int ldw, int max_unstable, uint8_t* __restrict__ finished,
-                  int32_t* __restrict__ margin_done, int32_t* __restrict__ unfinished_total) {
+                  int32_t* __restrict__ margin_done, int32_t* __restrict__ unfinished_total, const uint8_t* __restrict__ only) {
     const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (pi >= B || finished[pi]) return;
+    if (pi >= B || finished[pi] || (only && !only[pi])) return;
     const uint32_t* bits = reinterpret_cast<const uint32_t*>(states + (size_t)pi * words);
     const int bias = domain == HN_DOMAIN_BIPOLAR ? 1 : 0;
     int cnt = 0, ties = 0;

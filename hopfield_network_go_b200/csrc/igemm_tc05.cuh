@@ -34,7 +34,7 @@ template <bool A_BITS>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const uint64_t* __restrict__ states, int words, int B, int N, int Kdim,
-                  int bipolar, int32_t* __restrict__ G, int ldg) {
+                  int bipolar, int32_t* __restrict__ G, int ldg, int32_t* __restrict__ scan_unstable, int32_t* __restrict__ scan_zero) {
     using namespace tc05;
     extern __shared__ unsigned char tg_smem_raw[];
     const uint32_t raw = smem_u32(tg_smem_raw);
@@ -165,7 +165,27 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * TG_BN + c * 32), r);
                 tmem_ld_wait();
                 const int col = n0 + c * 32;
-                if (row < B) {
+                if constexpr (A_BITS) {
+                    // stability scan fused into the fields contraction (the test that follows a dense lockstep sweep,
+                    // HopfieldNetwork.go:214-225): per probe, the units with v*g < 0 and the units with an exactly zero field.
+                    // The tile holds (M s)_u = 2 g_u + diag s_u; with the unit's bit b:  2 g = value - bias + 2b.
+                    if (scan_unstable && row < B && col < N) {
+                        const uint32_t bw = reinterpret_cast<const uint32_t*>(states + (size_t)row * words)[col >> 5];
+                        const int bias = bipolar ? 1 : 0;
+                        int cu = 0, cz = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const int b = (int)((bw >> i) & 1u);
+                            const int g2 = (int)r[i] - bias + 2 * b;
+                            const bool in = col + i < N;
+                            cu += (in && (b ? g2 < 0 : g2 > 0)) ? 1 : 0;
+                            cz += (in && g2 == 0) ? 1 : 0;
+                        }
+                        if (cu) atomicAdd(scan_unstable + row, cu);
+                        if (cz) atomicAdd(scan_zero + row, cz);
+                    }
+                }
+                if (row < B && G) {
                     int32_t* out = G + (size_t)row * ldg + col;
 #pragma unroll
                     for (int v = 0; v < 8; v++)
@@ -184,15 +204,19 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // M8: row-major int8 [N][ld8] (ld8 multiple of 16), row k = column k of the integer image (symmetric weights)
+// scan_unstable / scan_zero (optional, [B], zeroed by the caller): per-probe counts of units with v*g < 0 / g == 0;
+// G may be nullptr then (fields not stored)
 static inline int launch_igemm_tc05(const uint64_t* states, int words, int B, const int8_t* M8, int ld8, int N, bool bipolar,
-                                    int32_t* G, int ldg, int sms, cudaStream_t st) {
+                                    int32_t* G, int ldg, int sms, cudaStream_t st, int32_t* scan_unstable = nullptr,
+                                    int32_t* scan_zero = nullptr) {
     if (B <= 0) return HN_OK;
     CUtensorMap map;
     const int rc = tc05::make_map_bytes_2d(&map, M8, (uint64_t)ld8, (uint64_t)N, (uint64_t)ld8, TG_BN);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
     HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     const int tiles = ((B + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-    igemm_tc05_kernel<true><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, map, states, words, B, N, N, bipolar ? 1 : 0, G, ldg);
+    igemm_tc05_kernel<true><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, map, states, words, B, N, N, bipolar ? 1 : 0, G, ldg,
+                                                                               scan_unstable, scan_zero);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }
@@ -209,7 +233,7 @@ static inline int launch_igemm_tc05_mats(const int8_t* A8, int M, const int8_t* 
     if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
     HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     const int tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-    igemm_tc05_kernel<false><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(ma, mb, nullptr, 0, M, N, K, 0, C, ldc);
+    igemm_tc05_kernel<false><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(ma, mb, nullptr, 0, M, N, K, 0, C, ldc, nullptr, nullptr);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }

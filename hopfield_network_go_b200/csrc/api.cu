@@ -145,6 +145,13 @@ struct hn_handle_s {
     // dense lockstep sweeps (dense.cuh)
     DevBuf d_mperm, d_mbb, d_mx, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished, d_scan;   // d_scan: unstable[B], zero[B], only[B]
     CUtensorMap dense_map;
+    // zero-copy results (hn_relax_batch with page-locked host buffers): device-visible addresses of the caller's arrays
+    bool zero_copy = true;             // HN_ZERO_COPY=0 turns it off
+    uint64_t* zc_finals = nullptr;
+    int32_t* zc_dist = nullptr;
+    std::vector<uint16_t> pool_host;       // the schedule last uploaded into `pool` (an identical one is not uploaded again)
+    int pool_host_rows = 0;
+    const uint64_t* zc_probes = nullptr;   // this range's probes in the caller's page-locked memory (read by the first dense sweep)
     int dense_rows = 0;
     uint64_t w_version = 1, pool_version = 1, dense_w_version = 0, dense_pool_version = 0;
     bool use_dense = true;
@@ -485,6 +492,24 @@ int upload_pool(hn_handle h, const uint16_t* pool, int rows, DevBuf& buf, uint16
     return HN_OK;
 }
 
+// The schedule of a relaxation call: validated and uploaded (with its inverse) unless it is the one already resident —
+// callers relax batch after batch on the same pool of unit orders, and everything derived from it (the dense sweeps'
+// row-permuted images, keyed by pool_version) then stays valid too.
+int validate_pool_host(hn_handle h, const uint16_t* pool, int rows);
+int stage_pool(hn_handle h, const uint16_t* pool, int rows) {
+    const size_t count = (size_t)rows * h->N;
+    if (h->d_pool && h->pool_host_rows == rows && h->pool_host.size() == count &&
+        std::memcmp(h->pool_host.data(), pool, sizeof(uint16_t) * count) == 0)
+        return HN_OK;
+    h->pool_host_rows = 0;
+    HN_TRY(validate_pool_host(h, pool, rows));
+    HN_TRY(upload_pool(h, pool, rows, h->pool, &h->d_pool, &h->d_inv));
+    h->pool_version++;
+    h->pool_host.assign(pool, pool + count);
+    h->pool_host_rows = rows;
+    return HN_OK;
+}
+
 int validate_pool_host(hn_handle h, const uint16_t* pool, int rows) {
     // every row must be a permutation of 0..N-1 (a bad row would corrupt device memory); small pools are checked here,
     // before any device work, every pool again on the device when it is uploaded (upload_pool)
@@ -619,7 +644,8 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
     HN_TRY(h->d_dflips.reserve(sizeof(int32_t) * (size_t)B));
     HN_TRY(h->d_dmargin.reserve(sizeof(int32_t) * (size_t)B));
     HN_TRY(h->d_finished.reserve((size_t)B));
-    HN_CUDA_TRY(cudaMemcpyAsync(h->d_state.p, d_probes, sizeof(uint64_t) * (size_t)B * words, cudaMemcpyDeviceToDevice, h->st));
+    if (!h->zc_probes)
+        HN_CUDA_TRY(cudaMemcpyAsync(h->d_state.p, d_probes, sizeof(uint64_t) * (size_t)B * words, cudaMemcpyDeviceToDevice, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(h->d_sweeps.p, 0, sizeof(int32_t) * (size_t)B, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(h->d_dflips.p, 0, sizeof(int32_t) * (size_t)B, h->st));
     HN_CUDA_TRY(cudaMemsetAsync(h->d_dmargin.p, 0, sizeof(int32_t) * (size_t)B, h->st));
@@ -656,6 +682,7 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         dp.info = h->d_info.as<DsPos>() + (size_t)r * rp;
         dp.row_base = r * rp;
         dp.states = h->d_state.as<uint64_t>();
+        if (r == 0 && h->zc_probes) { dp.states_src = h->zc_probes; dp.states_copy = const_cast<uint64_t*>(d_probes); }
         dp.finished = h->d_finished.as<uint8_t>();
         dp.sweeps_done = h->d_sweeps.as<int32_t>(); dp.flips_done = h->d_dflips.as<int32_t>(); dp.margin_done = h->d_dmargin.as<int32_t>();
         dp.Wrow = h->W; dp.sweep_index = r; dp.flips_total = &sc->dense_flips;
@@ -771,7 +798,8 @@ int relax_range(hn_handle h, const uint64_t* d_probes, int B_total, int off, int
     p.domain = h->cfg.domain; p.check_stability = 1; p.serial_stream = serial ? 1 : 0;
     p.final_states = h->finals.as<uint64_t>() + (size_t)off * words; p.num_steps = h->steps.as<int32_t>() + off;
     p.stable = h->stable.as<uint8_t>() + off; p.flips = h->flips.as<int32_t>() + off; p.margin_hits = h->margin.as<int32_t>() + off;
-    p.distances = (want_dist && h->P > 0) ? h->dist.as<int32_t>() + (size_t)off * h->P : nullptr;
+    p.distances = (want_dist && h->P > 0) ? (h->zc_dist ? h->zc_dist : h->dist.as<int32_t>()) + (size_t)off * h->P : nullptr;
+    p.final_states_host = h->zc_finals ? h->zc_finals + (size_t)off * words : nullptr;
     p.targets = h->targets.as<uint64_t>(); p.P = h->P;
     p.hash = dedup ? h->hash.as<uint64_t>() + (size_t)off * 4 : nullptr;
     p.zero_field = dedup ? h->zf.as<uint8_t>() + off : nullptr;
@@ -792,6 +820,18 @@ int relax_range(hn_handle h, const uint64_t* d_probes, int B_total, int off, int
 // streamed to the host, one range (up to 2^17 probes) when they stay on the device.
 constexpr int RELAX_CHUNK_STREAMED = 1 << 16, RELAX_CHUNK_RESIDENT = 1 << 17;
 
+// Device-visible address of a caller's host array if all of it is page-locked (cudaHostAlloc / cudaHostRegister: mapped
+// into the unified address space), else nullptr.
+static void* mapped_host(const void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return nullptr;
+    cudaPointerAttributes a{}, b{};
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    if (cudaPointerGetAttributes(&b, static_cast<const char*>(ptr) + bytes - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (b.type != cudaMemoryTypeHost) return nullptr;
+    return a.devicePointer;
+}
+
 // The whole relaxation of B probes.  d_probes: device buffer of the batch; if host_probes != nullptr the probes are
 // still on the host and are uploaded range by range on the copy stream.  stream_out != nullptr: the per-probe results
 // are copied to its host buffers range by range on the copy stream, overlapping the next range's kernels.
@@ -803,7 +843,22 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
     HN_TRY(refresh_wt(h));
     const bool dedup = flags & HN_RELAX_DEDUP, hist = flags & HN_RELAX_HISTORY, serial = flags & HN_RELAX_SERIAL_STREAM;
     const bool zero_matrix = h->maxabs == 0.0 && h->cfg.max_relax_iterations >= 1;   // closed form, zero_matrix_relax_kernel
-    const int range = (host_probes || stream_out) ? RELAX_CHUNK_STREAMED : RELAX_CHUNK_RESIDENT;
+    // Zero-copy results: when the caller's final-state and distance arrays are page-locked, the relaxation kernel writes
+    // every probe's rows straight into them as the probe finishes (relax.cuh, epilogue), so the two large device -> host
+    // transfers (282 MB per 2^17 probes at config 3) ride under the kernel itself instead of following it, and the
+    // batch needs no splitting into ranges.
+    h->zc_finals = nullptr; h->zc_dist = nullptr;
+    bool zc = false;
+    if (stream_out && h->zero_copy && !hist && !serial && !zero_matrix) {
+        const bool dist_out = want_dist && h->P > 0 && stream_out->distances;
+        uint64_t* zf = static_cast<uint64_t*>(mapped_host(stream_out->final_states, sizeof(uint64_t) * (size_t)B * words));
+        int32_t* zd = dist_out ? static_cast<int32_t*>(mapped_host(stream_out->distances, sizeof(int32_t) * (size_t)B * h->P)) : nullptr;
+        zc = (stream_out->final_states || dist_out) && (zf || !stream_out->final_states) && (zd || !dist_out);
+        if (zc) { h->zc_finals = zf; h->zc_dist = zd; }
+    }
+    const uint64_t* zc_probes = (host_probes && h->zero_copy)
+        ? static_cast<const uint64_t*>(mapped_host(host_probes, sizeof(uint64_t) * (size_t)B * words)) : nullptr;
+    const int range = ((host_probes || stream_out) && !zc) ? RELAX_CHUNK_STREAMED : RELAX_CHUNK_RESIDENT;
     const int chunk = (serial || zero_matrix || B <= range + range / 4) ? B : range;
     const int n_chunks = (B + chunk - 1) / chunk;
     HN_TRY(h->H.reserve(sizeof(double) * (size_t)chunk * h->ldw));
@@ -813,7 +868,7 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
     HN_TRY(h->flips.reserve(sizeof(int32_t) * (size_t)B));
     HN_TRY(h->margin.reserve(sizeof(int32_t) * (size_t)B));
     HN_TRY(h->small.reserve(sizeof(Scratch)));
-    if (want_dist && h->P > 0) HN_TRY(h->dist.reserve(sizeof(int32_t) * (size_t)B * h->P));
+    if (want_dist && h->P > 0 && !h->zc_dist) HN_TRY(h->dist.reserve(sizeof(int32_t) * (size_t)B * h->P));
     if (dedup) HN_TRY(h->hash.reserve(sizeof(uint64_t) * 4 * (size_t)B));
     if (dedup) HN_TRY(h->zf.reserve((size_t)B));
     if (hist) HN_TRY(h->history.reserve(sizeof(uint64_t) * (size_t)B * (h->cfg.max_relax_iterations + 1) * words));
@@ -842,7 +897,12 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
     for (int c = 0; c < n_chunks; c++) {
         const int off = c * chunk, cnt = std::min(chunk, B - off);
         cudaEvent_t* ce = &h->chunk_ev[6 * (size_t)c];
-        if (host_probes) {   // this range's probes: host -> device on the copy stream
+        // a range that starts with dense lockstep sweeps reads page-locked probes where they lie (dense.cuh, tile load of
+        // the first sweep) instead of waiting for their transfer
+        h->zc_probes = nullptr;
+        if (host_probes && zc_probes && !zero_matrix && dense_applicable(h, serial, hist, d_offsets, n_pool))
+            h->zc_probes = zc_probes + (size_t)off * words;
+        if (host_probes && !h->zc_probes) {   // this range's probes: host -> device on the copy stream
             HN_CUDA_TRY(cudaMemcpyAsync(d_probes + (size_t)off * words, host_probes + (size_t)off * words,
                                         sizeof(uint64_t) * (size_t)cnt * words, cudaMemcpyHostToDevice, h->st2));
             HN_CUDA_TRY(cudaEventRecord(ce[4], h->st2));
@@ -868,13 +928,14 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
         }
         if (stream_out) {   // this range's results: device -> host on the copy stream, under the next range's kernels
             HN_CUDA_TRY(cudaStreamWaitEvent(h->st2, ce[3], 0));
-            HN_TRY(d2h2(stream_out->final_states ? stream_out->final_states + (size_t)off * words : nullptr,
-                        h->finals.as<uint64_t>() + (size_t)off * words, sizeof(uint64_t) * (size_t)cnt * words));
+            if (!h->zc_finals)
+                HN_TRY(d2h2(stream_out->final_states ? stream_out->final_states + (size_t)off * words : nullptr,
+                            h->finals.as<uint64_t>() + (size_t)off * words, sizeof(uint64_t) * (size_t)cnt * words));
             HN_TRY(d2h2(stream_out->num_steps ? stream_out->num_steps + off : nullptr, h->steps.as<int32_t>() + off, sizeof(int32_t) * (size_t)cnt));
             HN_TRY(d2h2(stream_out->stable ? stream_out->stable + off : nullptr, h->stable.as<uint8_t>() + off, (size_t)cnt));
             HN_TRY(d2h2(stream_out->flips ? stream_out->flips + off : nullptr, h->flips.as<int32_t>() + off, sizeof(int32_t) * (size_t)cnt));
             HN_TRY(d2h2(stream_out->margin_hits ? stream_out->margin_hits + off : nullptr, h->margin.as<int32_t>() + off, sizeof(int32_t) * (size_t)cnt));
-            if (stream_out->distances && want_dist && h->P > 0)
+            if (stream_out->distances && want_dist && h->P > 0 && !h->zc_dist)
                 HN_TRY(d2h2(stream_out->distances + (size_t)off * h->P, h->dist.as<int32_t>() + (size_t)off * h->P, sizeof(int32_t) * (size_t)cnt * h->P));
             if (stream_out->history && hist) {
                 const size_t per = (size_t)(h->cfg.max_relax_iterations + 1) * words;
@@ -934,7 +995,9 @@ int relax_device(hn_handle h, uint64_t* d_probes, int B, const uint16_t* d_pool,
     h->timing.dense_ms = td; h->timing.dense_sweeps = dense_sweeps;
     h->timing.dense_kernel_ms = h->acc_dense_kernel_ms; h->timing.dense_gemm_ms = h->acc_dense_gemm_ms;
     h->timing.dense_scan_ms = h->acc_dense_scan_ms; h->timing.dense_flips = h->acc_dense_flips;
-    h->result_B = B; h->result_P = want_dist ? h->P : 0; h->result_flags = flags | (want_energies ? 0x100u : 0u);
+    // (distances written straight to the caller's memory are not on the device: a later download finds none)
+    h->result_B = B; h->result_P = (want_dist && !h->zc_dist) ? h->P : 0; h->result_flags = flags | (want_energies ? 0x100u : 0u);
+    h->zc_finals = nullptr; h->zc_dist = nullptr; h->zc_probes = nullptr;
     return HN_OK;
 }
 
@@ -954,9 +1017,9 @@ int download_results(hn_handle h, hn_relax_out* out, bool streamed = false) {
         HN_TRY(d2h(out->flips, h->flips.p, sizeof(int32_t) * (size_t)B));
         HN_TRY(d2h(out->margin_hits, h->margin.p, sizeof(int32_t) * (size_t)B));
     }
-    if (out->distances) {
+    if (out->distances && !streamed) {
         if (h->result_P != h->P) { set_error("distances were not computed"); return HN_E_STATE; }
-        if (!streamed) HN_TRY(d2h(out->distances, h->dist.p, sizeof(int32_t) * (size_t)B * h->P));
+        HN_TRY(d2h(out->distances, h->dist.p, sizeof(int32_t) * (size_t)B * h->P));
     }
     if (out->energies) {
         if (!(h->result_flags & 0x100u)) { set_error("energies were not computed"); return HN_E_STATE; }
@@ -1400,6 +1463,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     if (const char* e = getenv("HN_DENSE_ROWS")) h->dense_max_rows = std::max(1, std::atoi(e));
     if (const char* e = getenv("HN_DENSE_MIN_N")) h->dense_min_n = std::max(32, std::atoi(e));
     if (const char* e = getenv("HN_DENSE_MIN_FLIPS")) h->dense_min_flips = std::atof(e);
+    if (const char* e = getenv("HN_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
     *out = h;
     return HN_OK;
 }
@@ -1784,10 +1848,8 @@ int hn_relax_batch(hn_handle h, const uint64_t* probes_packed, int32_t n_probes,
         return HN_OK;
     }
     HN_TRY(set_device(h));
-    HN_TRY(validate_pool_host(h, perm_pool, n_pool));
     HN_TRY(h->probes.reserve(sizeof(uint64_t) * (size_t)n_probes * h->words));   // uploaded range by range inside relax_device
-    HN_TRY(upload_pool(h, perm_pool, n_pool, h->pool, &h->d_pool, &h->d_inv));
-    h->pool_version++;
+    HN_TRY(stage_pool(h, perm_pool, n_pool));
     h->resident_B = n_probes; h->resident_pool = n_pool;
     const int32_t* d_off = nullptr;
     if (offsets && !(flags & HN_RELAX_SERIAL_STREAM)) {
@@ -1819,9 +1881,7 @@ int hn_upload_perm_pool(hn_handle h, const uint16_t* perm_pool, int32_t n_pool) 
     if (!check_handle(h, "hn_upload_perm_pool")) return HN_E_INVALID;
     if (n_pool <= 0 || !perm_pool) { set_error("hn_upload_perm_pool: bad argument"); return HN_E_INVALID; }
     HN_TRY(set_device(h));
-    HN_TRY(validate_pool_host(h, perm_pool, n_pool));
-    HN_TRY(upload_pool(h, perm_pool, n_pool, h->pool, &h->d_pool, &h->d_inv));
-    h->pool_version++;
+    HN_TRY(stage_pool(h, perm_pool, n_pool));
     HN_CUDA_TRY(cudaStreamSynchronize(h->st));
     h->resident_pool = n_pool;
     return HN_OK;

@@ -90,6 +90,8 @@ struct DenseParams {
     const DsPos* info;         // [rows_p]
     int row_base;              // first row of this schedule row inside the tensor map (r * rows_p)
     uint64_t* states;          // [B][words] current packed states (updated in place)
+    const uint64_t* states_src;  // first sweep of a batch whose probes are still in mapped page-locked host memory: every tile
+    uint64_t* states_copy;       // reads its probes from there and leaves them in `states` and in the resident probe buffer
     const uint8_t* finished;   // [B]
     int32_t* sweeps_done;      // [B]
     int32_t* flips_done;       // [B]
@@ -193,8 +195,15 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 const int pp = t / nw, w = t % nw;
                 uint32_t bits = 0;
                 const int unit0 = 32 * w;
-                if (p0 + pp < p.B && w < words32 && unit0 < p.N)
-                    bits = reinterpret_cast<const uint32_t*>(p.states + (size_t)(p0 + pp) * p.words)[w];
+                if (p0 + pp < p.B && w < words32) {
+                    const size_t at = (size_t)(p0 + pp) * p.words * 2 + w;
+                    if (p.states_src) {
+                        bits = reinterpret_cast<const uint32_t*>(p.states_src)[at];
+                        reinterpret_cast<uint32_t*>(p.states)[at] = bits;
+                        reinterpret_cast<uint32_t*>(p.states_copy)[at] = bits;
+                    } else bits = reinterpret_cast<const uint32_t*>(p.states)[at];
+                    if (unit0 >= p.N) bits = 0;
+                }
                 uint32_t v[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) v[e] = tg_expand4((bits >> (4 * e)) & 0xFu, bipolar);

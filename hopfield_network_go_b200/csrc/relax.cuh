@@ -59,11 +59,12 @@ struct RelaxParams {
     int exact_arith;     // float64 stream on quarter-integer weights: every field is exact, tau = 0, a zero field is a zero
     // outputs (device)
     uint64_t* final_states;  // [B][words]
+    uint64_t* final_states_host;  // [B][words] or nullptr: second copy, written straight into mapped page-locked host memory
     int32_t* num_steps;      // [B]
     uint8_t* stable;         // [B]
     int32_t* flips;          // [B]
     int32_t* margin_hits;    // [B]
-    int32_t* distances;      // [B][P] or nullptr
+    int32_t* distances;      // [B][P] or nullptr (device memory, or mapped page-locked host memory: rows are written coalesced)
     const uint64_t* targets; // [P][words]
     int P;
     uint64_t* hash;          // [B][4] unique-table keys (zeroed by the host): [0..1] canonical-state hash, [2..3] exact-profile key; or nullptr
@@ -108,6 +109,7 @@ __device__ __forceinline__ double exact_field_warp(const double* __restrict__ ro
 
 constexpr uint32_t RELAX_NONE = 0xFFFFFFFFu;
 constexpr int RELAX_TAU_STEP = 256;
+constexpr int RELAX_DIST_STAGE = 512;   // distances staged in shared memory per probe before one coalesced row write
 
 // Dynamic shared memory layout (see relax_smem_bytes):
 //   s_bits  [nbw, padded to 4]   uint32  packed state (exact path, outputs)
@@ -180,6 +182,7 @@ relax_kernel(RelaxParams p) {
     __shared__ unsigned long long s_tz[2];       // hash marks of those units, by the sign of v (unique-table key, epilogue)
     __shared__ int s_flag;
     __shared__ long long s_rowbase;
+    __shared__ int s_dist[RELAX_DIST_STAGE];
 
     int tid = threadIdx.x;
     asm volatile("" : "+r"(tid));   // keep the thread index in a register (the compiler would re-read SR_TID every flip)
@@ -561,6 +564,10 @@ relax_kernel(RelaxParams p) {
         if (p.final_states) {
             uint32_t* fw = reinterpret_cast<uint32_t*>(p.final_states + (size_t)pi * p.words);
             for (int w = tid; w < p.words * 2; w += RELAX_THREADS) fw[w] = w < nbw ? s_bits[w] : 0u;
+            if (p.final_states_host) {
+                uint32_t* fh = reinterpret_cast<uint32_t*>(p.final_states_host + (size_t)pi * p.words);
+                for (int w = tid; w < p.words * 2; w += RELAX_THREADS) fh[w] = w < nbw ? s_bits[w] : 0u;
+            }
         }
         if (tid == 0) {
             const int steps = is_stable ? sweeps + 1 : p.max_iter + 1;  // len(StateHistory), main.go:231
@@ -573,16 +580,26 @@ relax_kernel(RelaxParams p) {
         }
         // Manhattan distance with inversion to every target (DistanceMeasure.go:28-42):
         // bipolar 2*min(dH, N-dH), binary min(dH, N-dH); exact integers.
+        // The row of a probe is staged in shared memory and written with consecutive threads on consecutive words, so
+        // that it also goes out in full segments when the destination is mapped host memory (no device copy, no
+        // device -> host transfer after the kernel).
         if (p.distances) {
-            for (int t = warp; t < p.P; t += RELAX_WARPS) {
-                const uint32_t* tw = reinterpret_cast<const uint32_t*>(p.targets + (size_t)t * p.words);
-                int dh = 0;
-                for (int w = lane; w < nbw; w += 32) dh += __popc(s_bits[w] ^ tw[w]);
-                dh = __reduce_add_sync(0xFFFFFFFFu, dh);
-                if (lane == 0) {
-                    const int m = min(dh, N - dh);
-                    p.distances[(size_t)pi * p.P + t] = p.domain == HN_DOMAIN_BINARY ? m : 2 * m;
+            int32_t* drow = p.distances + (size_t)pi * p.P;
+            for (int t0 = 0; t0 < p.P; t0 += RELAX_DIST_STAGE) {
+                const int tn = min(RELAX_DIST_STAGE, p.P - t0);
+                for (int t = warp; t < tn; t += RELAX_WARPS) {
+                    const uint32_t* tw = reinterpret_cast<const uint32_t*>(p.targets + (size_t)(t0 + t) * p.words);
+                    int dh = 0;
+                    for (int w = lane; w < nbw; w += 32) dh += __popc(s_bits[w] ^ tw[w]);
+                    dh = __reduce_add_sync(0xFFFFFFFFu, dh);
+                    if (lane == 0) {
+                        const int m = min(dh, N - dh);
+                        s_dist[t] = p.domain == HN_DOMAIN_BINARY ? m : 2 * m;
+                    }
                 }
+                __syncthreads();
+                for (int i = tid; i < tn; i += RELAX_THREADS) drow[t0 + i] = s_dist[i];
+                if (t0 + RELAX_DIST_STAGE < p.P) __syncthreads();
             }
         }
         // Unique-table keys (UniqueRelaxedStateHandler.go:44 keys on the printed energy profile), four words per probe:

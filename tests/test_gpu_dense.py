@@ -112,3 +112,32 @@ def test_dense_sweeps_with_exact_ties(built):
     _, first, hits = orc.unique_table(ores["energies"])
     assert np.array_equal(res.UniqueFirst, first) and np.array_equal(res.UniqueHits, hits)
     net.close()
+
+
+@pytest.mark.parametrize("n,p,b,domain,dense", [(4096, 400, 200, 0, 1), (1000, 1030, 150, 0, 0), (257, 30, 77, 1, 0)])
+def test_zero_copy_results_match_copied_results(built, n, p, b, domain, dense):
+    """Page-locked result buffers: the relaxation kernel writes final states and distance rows straight into the caller's
+    memory (relax.cuh epilogue, staged per probe).  Same arrays as the copy path and as the oracle, including a target
+    count above one staging pass (1030 > 512)."""
+    onet, k2, pool, probes, targets = make_problem(n, p, b, 21, domain=domain)
+    ores = onet.relax_batch(probes.copy(), pool, threads=8, want_energies=False, fast_k2=k2)
+    with _env(HN_DENSE_MIN_N=256 if dense else 1 << 20):
+        net = gpu_net(n, domain, SetColumnStream=AUTO)
+    net.SetMatrix(onet.w)
+    net.SetLearnedStates(orc.pack(targets))
+    copied = net.relax_batch(probes, pool, dedup=True)
+    packed = orc.pack(probes)
+    pinned_probes = net._result_buffer("probes_in", packed.shape, np.uint64, True)   # page-locked: read in place by the first dense sweep
+    pinned_probes[...] = packed
+    mapped = net.relax_batch(pinned_probes, pool, dedup=True, reuse_pinned_buffers=True)
+    assert np.array_equal(net.download_probes(b), packed)   # ... and left in the resident probe buffer as well
+    assert (net.last_timing().dense_sweeps >= 1) == bool(dense)
+    assert_relax_equal(mapped, ores, n)
+    _full_compare(mapped, copied)
+    with _env(HN_ZERO_COPY=0):
+        off = gpu_net(n, domain, SetColumnStream=AUTO)
+    off.SetMatrix(onet.w)
+    off.SetLearnedStates(orc.pack(targets))
+    _full_compare(off.relax_batch(probes, pool, dedup=True, reuse_pinned_buffers=True), copied)
+    net.close()
+    off.close()

@@ -316,14 +316,16 @@ def main():
         barrier()
         t1 = time.perf_counter()
         res = net.relax_batch(probes_np, pool, dedup=True, reuse_pinned_buffers=True)   # page-locked result buffers of the network
-        if os.environ.get("HN_MERGE_TRACE") and rank == 0:
+        if os.environ.get("HN_MERGE_TRACE"):
             tt = net.last_timing()
-            print(f"[e2e trace] relax_batch {1e3 * (time.perf_counter() - t1):.2f} ms (device {res.device_ms:.2f}: dense {tt.dense_ms:.2f} "
+            print(f"[e2e trace] rank {rank} relax_batch {1e3 * (time.perf_counter() - t1):.2f} ms (device {res.device_ms:.2f}: dense {tt.dense_ms:.2f} "
                   f"fields {tt.fields_ms:.2f} relax {tt.relax_ms:.2f} post {tt.post_ms:.2f})", flush=True)
         if world > 1:   # per-GPU unique tables merged on rank 0's GPU (first-seen order, hits)
             merged = multigpu.gather_unique_tables_device(net, rank * b)
             if rank == 0:
                 n_unique_global = len(merged["first"])
+        if os.environ.get("HN_MERGE_TRACE"):
+            print(f"[e2e trace] rank {rank} before the closing barrier {1e3 * (time.perf_counter() - t1):.2f} ms", flush=True)
         barrier()
         if it > 0:
             e2e_t.append(time.perf_counter() - t1)

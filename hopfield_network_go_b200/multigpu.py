@@ -159,6 +159,16 @@ def gather_unique_tables(local: dict, group=None) -> Optional[dict]:
     return merge_unique_tables(tables)
 
 
+def _merge_outputs(net, n):
+    """Host arrays hn_merge_unique_device writes into: kept on the network and reused while large enough (fresh arrays
+    of a million rows are page-faulted in on every call).  The returned table's arrays are views of them."""
+    cap, bufs = getattr(net, "_merge_out", (0, None))
+    if cap < n:
+        cap, bufs = n, tuple(np.zeros(n, np.int64) for _ in range(3))
+        net._merge_out = (cap, bufs)
+    return bufs
+
+
 def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[dict]:
     """Cross-GPU merge of unique tables WITHOUT the host in the data path (nccl backend): every rank exports its table
     — global first index, hits, key words, packed final states, zero-field marks — into device tensors
@@ -219,7 +229,7 @@ def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[
     S = allp[:, 7:].contiguous()
     torch.cuda.synchronize()
     mark("concat")
-    f_out, h_out, r_out = np.empty(max(n, 1), np.int64), np.empty(max(n, 1), np.int64), np.empty(max(n, 1), np.int64)
+    f_out, h_out, r_out = _merge_outputs(net, max(n, 1))
     ng = C.c_int64()
     capi.check(lib.hn_merge_unique_device(net._h, n, F.data_ptr(), H.data_ptr(), K.data_ptr(), S.data_ptr(), Z.data_ptr(),
                                           int(heads[0, 1]), capi.ptr(f_out), capi.ptr(h_out), capi.ptr(r_out), C.byref(ng)))
@@ -227,8 +237,23 @@ def gather_unique_tables_device(net, index_offset: int, group=None) -> Optional[
     mark("merge")
     if trace:
         print("[merge trace] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f} ms" for a, b in zip(marks, marks[1:])), flush=True)
-    starts = np.concatenate(([0], np.cumsum(counts)))
-    rep = r_out[:g]
-    rank_of = np.searchsorted(starts[1:], rep, side="right").astype(np.int32)
-    return {"first": f_out[:g].astype(np.int64), "hits": h_out[:g].astype(np.int64), "rank_of": rank_of,
-            "local_id": (rep - starts[rank_of]).astype(np.int32)}
+    return MergedUniqueTable(f_out[:g], h_out[:g], r_out[:g], np.concatenate(([0], np.cumsum(counts))))
+
+
+class MergedUniqueTable(dict):
+    """Result of gather_unique_tables_device: "first" (global index of the first probe of every attractor, in first-seen
+    order) and "hits" as written by hn_merge_unique_device.  "rank_of" / "local_id" — which rank's table holds the
+    attractor's representative state, and at which row — are derived on first use: with one attractor per probe
+    (config 3: a million rows at 8 GPUs) deriving them costs more host time than the merge itself."""
+
+    def __init__(self, first, hits, rep, starts):
+        super().__init__(first=first, hits=hits)
+        self._rep, self._starts = rep, starts
+
+    def __missing__(self, key):
+        if key not in ("rank_of", "local_id"):
+            raise KeyError(key)
+        rank_of = np.searchsorted(self._starts[1:], self._rep, side="right").astype(np.int32)
+        self["rank_of"] = rank_of
+        self["local_id"] = (self._rep - self._starts[rank_of]).astype(np.int32)
+        return self[key]

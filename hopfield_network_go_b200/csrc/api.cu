@@ -455,7 +455,7 @@ int launch_relax_int(hn_handle h, const RelaxParams& p) {
     if (n <= 512) return launch_relax_t<16, int16_t, 32, 32>(h, p, 0);
     if (n <= 1024) return launch_relax_t<32, int16_t, 32, 32>(h, p, 0);
     if (n <= 2048) return launch_relax_t<32, int16_t, 64, 18>(h, p, 0);
-    if (n <= 4096) return launch_relax_t<32, int16_t, 128, 9>(h, p, 0);
+    if (n <= 4096) return launch_relax_t<32, int16_t, 128, 9>(h, p, 0);   // 64 units x 64 threads measured slower: 185-198 ms vs 170 ms at config 3 (6-10 CTAs/SM)
     if (n <= 8192) return launch_relax_t<32, int16_t, 256, 4>(h, p, 0);
     if (n <= 16384) return launch_relax_t<32, int16_t, 512, 2>(h, p, 0);
     set_error("relaxation kernel supports dimension <= 16384 (got %d)", n);

@@ -146,6 +146,7 @@ struct hn_handle_s {
     DevBuf d_mperm, d_mbb, d_mx, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished, d_scan;   // d_scan: unstable[B], zero[B], only[B]
     CUtensorMap dense_map;
     // zero-copy results (hn_relax_batch with page-locked host buffers): device-visible addresses of the caller's arrays
+    int dense_box_rows = 32;           // rows per TMA box of the dense sweeps weight stream (HN_TMA_BOX_DENSE; 8-row boxes measured 2.3x slower)
     bool zero_copy = true;             // HN_ZERO_COPY=0 turns it off
     uint64_t* zc_finals = nullptr;
     int32_t* zc_dist = nullptr;
@@ -628,7 +629,7 @@ int prepare_dense(hn_handle h, const uint16_t* d_pool, int rows) {
                                                                              h->d_info.as<DsPos>() + (size_t)r * rp);
     }
     HN_CUDA_TRY(cudaGetLastError());
-    const int rc = tc05::make_map_bytes_2d(&h->dense_map, h->d_mperm.p, (uint64_t)np, (uint64_t)rows * rp, (uint64_t)np, DS_BLK);
+    const int rc = tc05::make_map_bytes_2d(&h->dense_map, h->d_mperm.p, (uint64_t)np, (uint64_t)rows * rp, (uint64_t)np, h->dense_box_rows);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled (dense sweeps) failed (%d)", rc); return HN_E_CUDA; }
     h->dense_rows = rows; h->dense_w_version = h->w_version; h->dense_pool_version = h->pool_version;
     return HN_OK;
@@ -677,6 +678,7 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_flips, 0, 8, h->st));
         DenseParams dp{};
         dp.N = N; dp.np = np; dp.rows_p = rp; dp.words = words; dp.B = B; dp.domain = h->cfg.domain; dp.ldw = h->ldw;
+        dp.box_rows = h->dense_box_rows;
         dp.mbb = h->d_mbb.as<int8_t>() + (size_t)r * rp * DS_BLK;
         dp.mx = h->d_mx.as<int8_t>() + (size_t)r * rp * DS_BLK;
         dp.info = h->d_info.as<DsPos>() + (size_t)r * rp;
@@ -1464,6 +1466,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     if (const char* e = getenv("HN_DENSE_MIN_N")) h->dense_min_n = std::max(32, std::atoi(e));
     if (const char* e = getenv("HN_DENSE_MIN_FLIPS")) h->dense_min_flips = std::atof(e);
     if (const char* e = getenv("HN_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
+    if (const char* e = getenv("HN_TMA_BOX_DENSE")) { const int x = std::atoi(e); if (x == 8 || x == 16 || x == 32) h->dense_box_rows = x; }
     *out = h;
     return HN_OK;
 }

@@ -85,6 +85,7 @@ __global__ void dense_prep_blocks_kernel(const int8_t* __restrict__ k8, int ld8,
 
 struct DenseParams {
     int N, np, rows_p, words, B, domain, ldw;
+    int box_rows;              // rows per TMA box of the tensor map (a quarter's 32 rows arrive as 32 / box_rows boxes)
     const int8_t* mbb;         // [rows_p/32][32][32] of this schedule row
     const int8_t* mx;          // [rows_p/32][32][32] cross matrices block b <- block b-1
     const DsPos* info;         // [rows_p]
@@ -237,7 +238,8 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                         unsigned char* dst = ring + (size_t)stage * DS_STAGE_BYTES;
 #pragma unroll
                         for (int q = 0; q < 4; q++)
-                            tma_load_2d(dst + q * 4096, &map_w, q * kq + kc * 128, p.row_base + b * DS_BLK, &full[stage]);
+                            for (int r = 0; r < DS_BLK; r += p.box_rows)
+                                tma_load_2d(dst + q * 4096 + r * 128, &map_w, q * kq + kc * 128, p.row_base + b * DS_BLK + r, &full[stage]);
                         if (++stage == DS_STAGES) { stage = 0; phase ^= 1u; }
                     }
             }

@@ -20,6 +20,17 @@ namespace hn {
 constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 128, TG_STAGES = 4;
 constexpr int TG_A_BYTES = TG_BM * TG_BK, TG_B_BYTES = TG_BN * TG_BK;
 constexpr int TG_THREADS = 320;
+// rows per TMA box: an operand tile is fetched as several boxes of this many 128-byte rows (same shared-memory layout:
+// the 128-byte swizzle repeats every 8 rows); HN_TMA_BOX picks it at run time (measured at config 3: 128 and 32 rows alike, 8 rows 1.8x slower).
+constexpr int TG_BOX_DEFAULT = 128;
+static inline int tg_box_rows() {
+    static const int v = [] {
+        const char* e = getenv("HN_TMA_BOX");
+        const int x = e ? atoi(e) : TG_BOX_DEFAULT;
+        return (x == 8 || x == 16 || x == 32 || x == 64 || x == 128 || x == 256) ? x : TG_BOX_DEFAULT;
+    }();
+    return v;
+}
 constexpr size_t TG_SMEM = (size_t)TG_STAGES * (TG_A_BYTES + TG_B_BYTES) + 256 + 1024;   // + barriers + alignment slack
 
 // 4 state bits -> 4 int8 in one word: bipolar +1 / -1 (0x01 / 0xFF), binary 1 / 0
@@ -34,7 +45,8 @@ template <bool A_BITS>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const uint64_t* __restrict__ states, int words, int B, int N, int Kdim,
-                  int bipolar, int32_t* __restrict__ G, int ldg, int32_t* __restrict__ scan_unstable, int32_t* __restrict__ scan_zero) {
+                  int bipolar, int32_t* __restrict__ G, int ldg, int32_t* __restrict__ scan_unstable, int32_t* __restrict__ scan_zero,
+                  int box_rows) {
     using namespace tc05;
     extern __shared__ unsigned char tg_smem_raw[];
     const uint32_t raw = smem_u32(tg_smem_raw);
@@ -74,8 +86,11 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full[stage], A_BITS ? TG_B_BYTES : TG_A_BYTES + TG_B_BYTES);
-                    tma_load_2d(sB + (size_t)stage * TG_B_BYTES, &map_b, kb * TG_BK, n0, &full[stage]);
-                    if constexpr (!A_BITS) tma_load_2d(sA + (size_t)stage * TG_A_BYTES, &map_a, kb * TG_BK, m0, &full[stage]);
+                    for (int r = 0; r < TG_BN; r += box_rows)
+                        tma_load_2d(sB + (size_t)stage * TG_B_BYTES + (size_t)r * TG_BK, &map_b, kb * TG_BK, n0 + r, &full[stage]);
+                    if constexpr (!A_BITS)
+                        for (int r = 0; r < TG_BM; r += box_rows)
+                            tma_load_2d(sA + (size_t)stage * TG_A_BYTES + (size_t)r * TG_BK, &map_a, kb * TG_BK, m0 + r, &full[stage]);
                     if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -111,19 +126,36 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== A producers: bits -> int8, 128-byte swizzled K-major tile =====
         const int a = tid - 64;   // 0..127
         int stage = 0; uint32_t phase = 0;
+        // the state words of K step kb + 1 are requested before the ring slot of step kb is waited for: their L2 latency
+        // (longer than the MMAs of a step) must not sit between two steps
+        auto fetch = [&](int m0, int kb, uint32_t (&out)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q = a + 128 * j;
+                const int probe = m0 + (q >> 2), unit0 = kb * TG_BK + (q & 3) * 32;
+                out[j] = 0;
+                if (probe < B && unit0 < N)
+                    out[j] = (uint32_t)(__ldg(states + (size_t)probe * words + (unit0 >> 6)) >> (unit0 & 63));
+            }
+        };
+        uint32_t nxt[4] = {0, 0, 0, 0};
+        if ((int)blockIdx.x < tiles) fetch(((int)blockIdx.x / n_tiles) * TG_BM, 0, nxt);
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TG_BM;
             for (int kb = 0; kb < kblocks; kb++) {
+                uint32_t cur[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+                if (kb + 1 < kblocks) fetch(m0, kb + 1, nxt);
+                else if (tile + (int)gridDim.x < tiles) fetch(((tile + (int)gridDim.x) / n_tiles) * TG_BM, 0, nxt);
                 mbar_wait(&empty[stage], phase ^ 1u);
                 unsigned char* dst = sA + (size_t)stage * TG_A_BYTES;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int q = a + 128 * j;
                     const int row = q >> 2, quarter = q & 3;
-                    const int probe = m0 + row, unit0 = kb * TG_BK + quarter * 32;
-                    uint32_t bits = 0;
-                    if (probe < B && unit0 < N)
-                        bits = (uint32_t)(__ldg(states + (size_t)probe * words + (unit0 >> 6)) >> (unit0 & 63));
+                    const int unit0 = kb * TG_BK + quarter * 32;
+                    const uint32_t bits = cur[j];
                     uint32_t w[8];
 #pragma unroll
                     for (int e = 0; e < 8; e++) w[e] = tg_expand4((bits >> (4 * e)) & 0xFu, bipolar != 0);
@@ -211,12 +243,13 @@ static inline int launch_igemm_tc05(const uint64_t* states, int words, int B, co
                                     int32_t* scan_zero = nullptr) {
     if (B <= 0) return HN_OK;
     CUtensorMap map;
-    const int rc = tc05::make_map_bytes_2d(&map, M8, (uint64_t)ld8, (uint64_t)N, (uint64_t)ld8, TG_BN);
+    const int box = tg_box_rows();
+    const int rc = tc05::make_map_bytes_2d(&map, M8, (uint64_t)ld8, (uint64_t)N, (uint64_t)ld8, box);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
     HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     const int tiles = ((B + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
     igemm_tc05_kernel<true><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, map, states, words, B, N, N, bipolar ? 1 : 0, G, ldg,
-                                                                               scan_unstable, scan_zero);
+                                                                               scan_unstable, scan_zero, box);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }
@@ -228,12 +261,13 @@ static inline int launch_igemm_tc05_mats(const int8_t* A8, int M, const int8_t* 
                                          int sms, cudaStream_t st) {
     if (M <= 0 || N <= 0) return HN_OK;
     CUtensorMap ma, mb;
-    int rc = tc05::make_map_bytes_2d(&ma, A8, (uint64_t)pitch, (uint64_t)M, (uint64_t)pitch, TG_BM);
-    if (rc == 0) rc = tc05::make_map_bytes_2d(&mb, B8, (uint64_t)pitch, (uint64_t)N, (uint64_t)pitch, TG_BN);
+    const int box = std::min(tg_box_rows(), TG_BM);   // one box size for both operands: it must divide the smaller tile
+    int rc = tc05::make_map_bytes_2d(&ma, A8, (uint64_t)pitch, (uint64_t)M, (uint64_t)pitch, box);
+    if (rc == 0) rc = tc05::make_map_bytes_2d(&mb, B8, (uint64_t)pitch, (uint64_t)N, (uint64_t)pitch, box);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
     HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     const int tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-    igemm_tc05_kernel<false><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(ma, mb, nullptr, 0, M, N, K, 0, C, ldc, nullptr, nullptr);
+    igemm_tc05_kernel<false><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(ma, mb, nullptr, 0, M, N, K, 0, C, ldc, nullptr, nullptr, box);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }

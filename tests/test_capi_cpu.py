@@ -112,3 +112,22 @@ def test_rng_advance_equals_drawing(built):
     for _ in range(5000):
         o.uint64()
     assert o.uint64() == g.Uint64()
+
+
+def test_hot_kernels_do_not_spill(built):
+    """The relaxation kernels are compiled against a register cap per occupancy target (__launch_bounds__ in relax.cuh:
+    56 registers at 9 CTAs/SM for the shipped integer kernel).  A change that makes one of them spill compiles and passes
+    every parity test but costs tens of percent (measured: 170 -> 252 ms per config-3 step for 148 bytes of spill
+    stores), so the built library is checked: no stack frame in any relaxation / dense-sweep / contraction kernel."""
+    import re
+    import shutil
+    import subprocess
+    from hopfield_network_go_b200 import build
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([tool, "-res-usage", build.LIB_PATH], capture_output=True, text=True).stdout
+    seen = 0
+    for name, stack in re.findall(r"Function (\S+):\s*\n\s*REG:\d+ STACK:(\d+)", out):
+        if any(k in name for k in ("relax_kernel", "dense_sweep_kernel", "igemm_tc05_kernel")):
+            seen += 1
+            assert int(stack) == 0, f"{name} spills ({stack} bytes of stack)"
+    assert seen >= 20, "resource usage of the hot kernels not found in the library"

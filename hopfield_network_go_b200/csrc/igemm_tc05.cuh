@@ -7,8 +7,9 @@
 // One persistent CTA per SM, 128 probes x 256 units per tile, K streamed in 128-byte steps through a 4-stage ring:
 //   warp 0      TMA producer: the M8 tile (256 rows x 128 B, 128-byte swizzle) of every K step;
 //   warp 1      allocates TMEM (2 accumulators of 256 columns) and issues tcgen05.mma.kind::i8 (M=128, N=256, K=32);
-//   warps 2-5   expand the probes' bits into the int8 A tile in the same swizzled layout (generic proxy + proxy fence);
-//   warps 6-9   epilogue: tcgen05.ld of the finished accumulator (one TMEM sub-partition per warp) -> global int32,
+//   warps 2-9   expand the probes' bits into the int8 A tile in the same swizzled layout (generic proxy + proxy fence);
+//               eight warps because this expansion, not the tensor pipe or the weight stream, bounds a K step otherwise;
+//   warps 10-13 epilogue: tcgen05.ld of the finished accumulator (one TMEM sub-partition per warp) -> global int32,
 //               overlapped with the next tile's MMAs through the second accumulator.
 // Everything is exact integer arithmetic: the result is bit-identical to igemm_fields_kernel and to the float64 GEMM.
 #pragma once
@@ -19,7 +20,9 @@ namespace hn {
 
 constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 128, TG_STAGES = 4;
 constexpr int TG_A_BYTES = TG_BM * TG_BK, TG_B_BYTES = TG_BN * TG_BK;
-constexpr int TG_THREADS = 320;
+constexpr int TG_THREADS = 448;   // warp 0 TMA, warp 1 MMA, warps 2-9 A producers, warps 10-13 epilogue
+constexpr int TG_PRODUCER_WARPS = 8;
+constexpr int TG_GROUPS_DEFAULT = 4;   // HN_IGEMM_GROUPS picks 1 / 2 / 4 at run time (measured per config-3 step: 8.98 / 7.74 / 7.10 ms)
 // rows per TMA box: an operand tile is fetched as several boxes of this many 128-byte rows (same shared-memory layout:
 // the 128-byte swizzle repeats every 8 rows); HN_TMA_BOX picks it at run time (measured at config 3: 128 and 32 rows alike, 8 rows 1.8x slower).
 constexpr int TG_BOX_DEFAULT = 128;
@@ -34,14 +37,16 @@ static inline int tg_box_rows() {
 constexpr size_t TG_SMEM = (size_t)TG_STAGES * (TG_A_BYTES + TG_B_BYTES) + 256 + 1024;   // + barriers + alignment slack
 
 // 4 state bits -> 4 int8 in one word: bipolar +1 / -1 (0x01 / 0xFF), binary 1 / 0
+// (nib < 16: the four shifted copies nib << 0 / 7 / 14 / 21 do not overlap, bit 8j of their sum is bit j of nib; and
+// 0xFF - 0xFE * bit never borrows across bytes: one multiply-add instead of a multiply and an xor)
 __device__ __forceinline__ uint32_t tg_expand4(uint32_t nib, bool bipolar) {
-    const uint32_t spread = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-    return bipolar ? (0xFFFFFFFFu ^ (spread * 0xFEu)) : spread;
+    const uint32_t spread = (nib * 0x00204081u) & 0x01010101u;
+    return bipolar ? 0xFFFFFFFFu - spread * 0xFEu : spread;
 }
 
 // A_BITS: the A operand (rows = probes) is expanded from packed state bits by warps 2-5 (the fields contraction);
 // otherwise both operands are int8 matrices fetched by TMA (the learning contractions dW = X^T X, D^T T) and K = Kdim.
-template <bool A_BITS>
+template <bool A_BITS, int GROUPS>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const uint64_t* __restrict__ states, int words, int B, int N, int Kdim,
@@ -54,7 +59,7 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     unsigned char* sA = smem;
     unsigned char* sB = smem + TG_STAGES * TG_A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * (TG_A_BYTES + TG_B_BYTES));
-    uint64_t* full = bars;                    // [stages] 1 TMA arrive(+tx) + 4 producer warps
+    uint64_t* full = bars;                    // [stages] 1 TMA arrive(+tx) + 8 producer warps
     uint64_t* empty = bars + TG_STAGES;       // [stages] tcgen05.commit
     uint64_t* acc_full = bars + 2 * TG_STAGES;       // [2] tcgen05.commit after the last K step of a tile
     uint64_t* acc_empty = bars + 2 * TG_STAGES + 2;  // [2] 4 epilogue warps
@@ -66,7 +71,7 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int kblocks = (Kdim + TG_BK - 1) / TG_BK;
 
     if (tid == 0) {
-        for (int s = 0; s < TG_STAGES; s++) { mbar_init(&full[s], A_BITS ? 5 : 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TG_STAGES; s++) { mbar_init(&full[s], A_BITS ? 1 + TG_PRODUCER_WARPS / GROUPS : 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         mbar_fence_init();
         tma_prefetch_desc(&map_b);
@@ -121,63 +126,72 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + TG_PRODUCER_WARPS) {
         if constexpr (A_BITS) {
         // ===== A producers: bits -> int8, 128-byte swizzled K-major tile =====
-        const int a = tid - 64;   // 0..127
-        int stage = 0; uint32_t phase = 0;
-        // the state words of K step kb + 1 are requested before the ring slot of step kb is waited for: their L2 latency
-        // (longer than the MMAs of a step) must not sit between two steps
-        auto fetch = [&](int m0, int kb, uint32_t (&out)[4]) {
+        // The eight warps form GROUPS groups; group g fills the ring slots of the K steps i = g (mod GROUPS), i counted
+        // across tiles (slot i mod 4).  What a warp spends per slot is mostly latency (slot wait, proxy fence, barrier
+        // arrival), so slots are filled side by side rather than by all eight warps one slot after the other.
+        static_assert(TG_STAGES == 4, "slot = step & 3");
+        constexpr int PT = 32 * TG_PRODUCER_WARPS / GROUPS, PI = TG_BM * 4 / PT;   // threads per group, (row, quarter) items per thread
+        const int g = (tid - 64) / PT, a = (tid - 64) % PT;
+        auto fetch = [&](int m0, int kb, uint32_t (&out)[PI]) {   // requested one of this group's steps ahead of the slot wait
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int q = a + 128 * j;
+            for (int j = 0; j < PI; j++) {
+                const int q = a + PT * j;
                 const int probe = m0 + (q >> 2), unit0 = kb * TG_BK + (q & 3) * 32;
                 out[j] = 0;
                 if (probe < B && unit0 < N)
                     out[j] = (uint32_t)(__ldg(states + (size_t)probe * words + (unit0 >> 6)) >> (unit0 & 63));
             }
         };
-        uint32_t nxt[4] = {0, 0, 0, 0};
-        if ((int)blockIdx.x < tiles) fetch(((int)blockIdx.x / n_tiles) * TG_BM, 0, nxt);
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * TG_BM;
-            for (int kb = 0; kb < kblocks; kb++) {
-                uint32_t cur[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) cur[j] = nxt[j];
-                if (kb + 1 < kblocks) fetch(m0, kb + 1, nxt);
-                else if (tile + (int)gridDim.x < tiles) fetch(((tile + (int)gridDim.x) / n_tiles) * TG_BM, 0, nxt);
-                mbar_wait(&empty[stage], phase ^ 1u);
-                unsigned char* dst = sA + (size_t)stage * TG_A_BYTES;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int q = a + 128 * j;
-                    const int row = q >> 2, quarter = q & 3;
-                    const int unit0 = kb * TG_BK + quarter * 32;
-                    const uint32_t bits = cur[j];
-                    uint32_t w[8];
-#pragma unroll
-                    for (int e = 0; e < 8; e++) w[e] = tg_expand4((bits >> (4 * e)) & 0xFu, bipolar != 0);
-                    if (unit0 + 32 > N) {   // ragged tail: units >= N contribute nothing
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            uint32_t mask = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; b++) if (unit0 + 4 * e + b < N) mask |= 0xFFu << (8 * b);
-                            w[e] &= mask;
-                        }
-                    }
-                    const uint32_t rbase = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-                    const uint32_t c0 = (uint32_t)quarter * 2u, sw = (uint32_t)(row & 7);
-                    *reinterpret_cast<uint4*>(dst + rbase + (((c0) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                    *reinterpret_cast<uint4*>(dst + rbase + (((c0 + 1u) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
-                if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
+        int tile = blockIdx.x, kb = 0;
+        uint32_t step = 0;
+        auto advance = [&](int n) {
+            for (int t = 0; t < n; t++) {
+                if (++kb == kblocks) { kb = 0; tile += gridDim.x; }
+                step++;
             }
+        };
+        advance(g);
+        uint32_t nxt[PI] = {};
+        if (tile < tiles) fetch((tile / n_tiles) * TG_BM, kb, nxt);
+        while (tile < tiles) {
+            const int ckb = kb;
+            const uint32_t stage = step & 3u, phase = (step >> 2) & 1u;
+            uint32_t cur[PI];
+#pragma unroll
+            for (int j = 0; j < PI; j++) cur[j] = nxt[j];
+            advance(GROUPS);
+            if (tile < tiles) fetch((tile / n_tiles) * TG_BM, kb, nxt);
+            mbar_wait(&empty[stage], phase ^ 1u);
+            unsigned char* dst = sA + (size_t)stage * TG_A_BYTES;
+#pragma unroll
+            for (int j = 0; j < PI; j++) {
+                const int q = a + PT * j;
+                const int row = q >> 2, quarter = q & 3;
+                const int unit0 = ckb * TG_BK + quarter * 32;
+                const uint32_t bits = cur[j];
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) w[e] = tg_expand4((bits >> (4 * e)) & 0xFu, bipolar != 0);
+                if (unit0 + 32 > N) {   // ragged tail: units >= N contribute nothing
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++) if (unit0 + 4 * e + bb < N) mask |= 0xFFu << (8 * bb);
+                        w[e] &= mask;
+                    }
+                }
+                const uint32_t rbase = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+                const uint32_t c0 = (uint32_t)quarter * 2u, sw = (uint32_t)(row & 7);
+                *reinterpret_cast<uint4*>(dst + rbase + (((c0) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(dst + rbase + (((c0 + 1u) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
         }
         }
     } else {
@@ -246,10 +260,16 @@ static inline int launch_igemm_tc05(const uint64_t* states, int words, int B, co
     const int box = tg_box_rows();
     const int rc = tc05::make_map_bytes_2d(&map, M8, (uint64_t)ld8, (uint64_t)N, (uint64_t)ld8, box);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
-    HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     const int tiles = ((B + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-    igemm_tc05_kernel<true><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, map, states, words, B, N, N, bipolar ? 1 : 0, G, ldg,
-                                                                               scan_unstable, scan_zero, box);
+    static const int groups = [] { const char* e = getenv("HN_IGEMM_GROUPS"); const int x = e ? atoi(e) : TG_GROUPS_DEFAULT; return (x == 1 || x == 2 || x == 4) ? x : TG_GROUPS_DEFAULT; }();
+    auto go = [&](auto kern) -> int {
+        HN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+        kern<<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(map, map, states, words, B, N, N, bipolar ? 1 : 0, G, ldg, scan_unstable, scan_zero, box);
+        return HN_OK;
+    };
+    if (groups == 1) HN_TRY(go(igemm_tc05_kernel<true, 1>));
+    else if (groups == 2) HN_TRY(go(igemm_tc05_kernel<true, 2>));
+    else HN_TRY(go(igemm_tc05_kernel<true, 4>));
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }
@@ -265,9 +285,9 @@ static inline int launch_igemm_tc05_mats(const int8_t* A8, int M, const int8_t* 
     int rc = tc05::make_map_bytes_2d(&ma, A8, (uint64_t)pitch, (uint64_t)M, (uint64_t)pitch, box);
     if (rc == 0) rc = tc05::make_map_bytes_2d(&mb, B8, (uint64_t)pitch, (uint64_t)N, (uint64_t)pitch, box);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled failed (%d)", rc); return HN_E_CUDA; }
-    HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+    HN_CUDA_TRY(cudaFuncSetAttribute(igemm_tc05_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     const int tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-    igemm_tc05_kernel<false><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(ma, mb, nullptr, 0, M, N, K, 0, C, ldc, nullptr, nullptr, box);
+    igemm_tc05_kernel<false, 1><<<std::min(tiles, sms), TG_THREADS, TG_SMEM, st>>>(ma, mb, nullptr, 0, M, N, K, 0, C, ldc, nullptr, nullptr, box);
     HN_CUDA_TRY(cudaGetLastError());
     return HN_OK;
 }

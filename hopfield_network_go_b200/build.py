@@ -14,7 +14,7 @@ HEADERS = ["common.cuh", "gemm_f64.cuh", "igemm_s8.cuh", "igemm_tc05.cuh", "tc05
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-shared",
-    "-Xcompiler", "-fPIC", "-diag-suppress", "177",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-diag-suppress", "177",
 ]
 
 

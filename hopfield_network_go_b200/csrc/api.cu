@@ -147,6 +147,7 @@ struct hn_handle_s {
     CUtensorMap dense_map;
     // zero-copy results (hn_relax_batch with page-locked host buffers): device-visible addresses of the caller's arrays
     int dense_box_rows = 32;           // rows per TMA box of the dense sweeps weight stream (HN_TMA_BOX_DENSE; 8-row boxes measured 2.3x slower)
+    bool exact_norm = true;            // Frobenius norm of quarter-integer weights by the reference's Dlassq recurrence (HN_EXACT_NORM=0: parallel sum)
     bool zero_copy = true;             // HN_ZERO_COPY=0 turns it off
     uint64_t* zc_finals = nullptr;
     int32_t* zc_dist = nullptr;
@@ -1466,6 +1467,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     if (const char* e = getenv("HN_DENSE_MIN_N")) h->dense_min_n = std::max(32, std::atoi(e));
     if (const char* e = getenv("HN_DENSE_MIN_FLIPS")) h->dense_min_flips = std::atof(e);
     if (const char* e = getenv("HN_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
+    if (const char* e = getenv("HN_EXACT_NORM")) h->exact_norm = std::atoi(e) != 0;
     if (const char* e = getenv("HN_TMA_BOX_DENSE")) { const int x = std::atoi(e); if (x == 8 || x == 16 || x == 32) h->dense_box_rows = x; }
     *out = h;
     return HN_OK;
@@ -1643,6 +1645,35 @@ int hn_enforce_constraints(hn_handle h) {
     return HN_OK;
 }
 
+// ||W||_F exactly as the reference computes it — mat.Norm(W, 2) = Dlange('F'): gonum's Dlassq recurrence (scaled sum of
+// squares) over the rows in order, then scale*sqrt(ssq) (HopfieldNetwork.go:260; oracle: orc_frobenius) — for a matrix
+// of quarter-integers given as k = 4w.  The recurrence is sequential by nature (every addition rounds), so it runs on
+// the host, once per LearnStates; the term a unit adds depends only on |k| and the current scale, hence the table.
+// The resulting W = fl((1/norm) * Wraw) is then bit-identical to the reference's, which the exact re-evaluation of tied
+// fields and the +0/-0 marks of the unique table depend on.
+static double exact_frobenius_quarters(const int16_t* k, size_t count) {
+    double scale = 0.0, ssq = 1.0;
+    std::vector<double> term(32768);
+    std::vector<uint8_t> have(32768, 0);
+    for (size_t i = 0; i < count; i++) {
+        const int a = k[i] < 0 ? -(int)k[i] : (int)k[i];
+        if (a == 0) continue;
+        const double absxi = 0.25 * (double)a;
+        if (scale < absxi) {
+            const double ratio = scale / absxi;
+            double t = ssq * ratio;
+            t = t * ratio;
+            ssq = 1.0 + t;
+            scale = absxi;
+            std::fill(have.begin(), have.end(), 0);
+        } else {
+            if (!have[a]) { const double ratio = absxi / scale; term[a] = ratio * ratio; have[a] = 1; }
+            ssq += term[a];
+        }
+    }
+    return scale * std::sqrt(ssq);
+}
+
 int hn_normalize_frobenius(hn_handle h, double* norm_out) {
     if (!check_handle(h, "hn_normalize_frobenius")) return HN_E_INVALID;
     HN_TRY(set_device(h));
@@ -1657,6 +1688,29 @@ int hn_normalize_frobenius(hn_handle h, double* norm_out) {
     }
     sumsq_partial_kernel<<<np, RED_THREADS, 0, h->st>>>(h->W, h->N, h->ldw, part);
     sumsq_final_kernel<<<1, RED_THREADS, 0, h->st>>>(part, np, part + np);
+    if (h->exact_norm) {   // quarter-integer weights (every Hebbian / Delta matrix learned from zero): the reference's own recurrence
+        const size_t count = (size_t)h->N * h->N;
+        HN_TRY(h->opA8.reserve(sizeof(int16_t) * count));
+        HN_TRY(h->small.reserve(sizeof(Scratch)));
+        int32_t* bad = &h->scratch()->int_flag;
+        HN_CUDA_TRY(cudaMemsetAsync(bad, 0, 4, h->st));
+        quarters_i16_kernel<<<grid_for((int64_t)count, 256, h->sms), 256, 0, h->st>>>(h->W, h->N, h->ldw, h->opA8.as<int16_t>(), bad);
+        HN_CUDA_TRY(cudaGetLastError());
+        int32_t b = 1;
+        HN_CUDA_TRY(cudaMemcpyAsync(&b, bad, 4, cudaMemcpyDeviceToHost, h->st));
+        HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+        if (!b) {
+            std::vector<int16_t> k(count);
+            HN_CUDA_TRY(cudaMemcpyAsync(k.data(), h->opA8.p, sizeof(int16_t) * count, cudaMemcpyDeviceToHost, h->st));
+            HN_CUDA_TRY(cudaStreamSynchronize(h->st));
+            const double nrm = exact_frobenius_quarters(k.data(), count);
+            if (nrm > 0.0 && std::isfinite(nrm)) {
+                const double both[2] = {nrm, 1.0 / nrm};
+                HN_CUDA_TRY(cudaMemcpyAsync(part + np, both, sizeof(both), cudaMemcpyHostToDevice, h->st));
+                HN_CUDA_TRY(cudaStreamSynchronize(h->st));   // `both` is a stack array
+            }
+        }
+    }
     scale_kernel<<<grid_for((int64_t)h->N * h->ldw, 256, h->sms), 256, 0, h->st>>>(h->W, h->N, h->ldw, part + np);
     HN_CUDA_TRY(cudaGetLastError());
     double nrm[2] = {0, 0};

@@ -218,6 +218,18 @@ __global__ void scale_kernel(double* __restrict__ w, int n, int ld, const double
         w[i] = __dmul_rn(s, w[i]);
 }
 
+// Dense [n][n] int16 image of 4*W for the host's exact Frobenius norm (api.cu: exact_frobenius_quarters); bad <- 1 if some
+// entry is not a multiple of 0.25 or 4|w| leaves int16.
+__global__ void quarters_i16_kernel(const double* __restrict__ w, int n, int ld, int16_t* __restrict__ out, int32_t* bad) {
+    const int64_t total = (int64_t)n * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = 4.0 * w[(i / n) * ld + (i % n)];
+        const double r = rint(x);
+        if (r != x || fabs(r) > 32767.0) *bad = 1;
+        out[i] = (int16_t)r;
+    }
+}
+
 // max_i sum_k |W_ik|  (the R of the decision margin); one CTA per row, atomicMax on the bits
 __global__ void rowabs_max_kernel(const double* __restrict__ w, int n, int ld, unsigned long long* out) {
     __shared__ double sm[RED_THREADS / 32];

@@ -19,7 +19,7 @@ HN_COLUMNS_F64, HN_COLUMNS_F32, HN_COLUMNS_I16, HN_COLUMNS_AUTO = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
     "hn_default_config", "hn_abi_version", "hn_last_error", "hn_create", "hn_destroy", "hn_set_weights",
-    "hn_get_weights", "hn_set_integer_structure", "hn_integer_stream_active", "hn_set_targets", "hn_num_targets", "hn_get_targets", "hn_hebbian_epoch",
+    "hn_get_weights", "hn_set_integer_structure", "hn_set_norm_algorithm", "hn_integer_stream_active", "hn_set_targets", "hn_num_targets", "hn_get_targets", "hn_hebbian_epoch",
     "hn_delta_epoch", "hn_thermal_delta_epoch", "hn_rule_epoch", "hn_enforce_constraints", "hn_normalize_frobenius", "hn_energy_profiles",
     "hn_learn_states", "hn_learn_states_sharded", "hn_unit_energy", "hn_relax_batch", "hn_update_states", "hn_upload_perm_pool", "hn_upload_probes",
     "hn_generate_probes", "hn_download_probes", "hn_relax_resident", "hn_download_results", "hn_last_relax_timing", "hn_last_learn_timing", "hn_get_margin", "hn_unique_table_stats", "hn_debug_integer_fields",
@@ -96,6 +96,7 @@ def load():
     L.hn_set_weights.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_get_weights.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_set_integer_structure.argtypes = [C.c_void_p, C.c_void_p]
+    L.hn_set_norm_algorithm.argtypes = [C.c_void_p, C.c_int32]
     L.hn_integer_stream_active.argtypes = [C.c_void_p, C.c_void_p]
     L.hn_set_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hn_num_targets.argtypes = [C.c_void_p, C.c_void_p]

@@ -147,7 +147,7 @@ struct hn_handle_s {
     CUtensorMap dense_map;
     // zero-copy results (hn_relax_batch with page-locked host buffers): device-visible addresses of the caller's arrays
     int dense_box_rows = 32;           // rows per TMA box of the dense sweeps weight stream (HN_TMA_BOX_DENSE; 8-row boxes measured 2.3x slower)
-    bool exact_norm = true;            // Frobenius norm of quarter-integer weights by the reference's Dlassq recurrence (HN_EXACT_NORM=0: parallel sum)
+    bool exact_norm = false;           // hn_set_norm_algorithm: classic Dlassq recurrence on the host (true) / exact parallel sum = LAPACK-3.10 Dlassq (false); HN_EXACT_NORM presets it
     bool zero_copy = true;             // HN_ZERO_COPY=0 turns it off
     uint64_t* zc_finals = nullptr;
     int32_t* zc_dist = nullptr;
@@ -1672,6 +1672,16 @@ static double exact_frobenius_quarters(const int16_t* k, size_t count) {
         }
     }
     return scale * std::sqrt(ssq);
+}
+
+int hn_set_norm_algorithm(hn_handle h, int32_t algorithm) {
+    if (!check_handle(h, "hn_set_norm_algorithm")) return HN_E_INVALID;
+    if (algorithm != HN_NORM_DLASSQ_CLASSIC && algorithm != HN_NORM_DLASSQ_LAPACK310) {
+        set_error("hn_set_norm_algorithm: unknown algorithm %d", algorithm);
+        return HN_E_INVALID;
+    }
+    h->exact_norm = algorithm == HN_NORM_DLASSQ_CLASSIC;
+    return HN_OK;
 }
 
 int hn_normalize_frobenius(hn_handle h, double* norm_out) {

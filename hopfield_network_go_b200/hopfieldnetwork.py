@@ -426,6 +426,7 @@ class HopfieldNetworkBuilder:
         self.seed = None     # additive: SetSeed
         self.device = 0      # additive: SetDevice
         self.columnStream = capi.HN_COLUMNS_AUTO  # additive: SetColumnStream
+        self.normAlgorithm = 1  # additive: SetNormAlgorithm (hn_set_norm_algorithm: 1 LAPACK-3.10 Dlassq, the default; 0 classic)
 
     def SetRandMatrixInit(self, f): self.randMatrixInit = f; return self
     def SetNetworkDimension(self, d): self.dimension = d; return self
@@ -447,6 +448,7 @@ class HopfieldNetworkBuilder:
     def SetSeed(self, s): self.seed = s; return self
     def SetDevice(self, d): self.device = d; return self
     def SetColumnStream(self, m): self.columnStream = m; return self
+    def SetNormAlgorithm(self, a): self.normAlgorithm = a; return self
 
     def Build(self) -> HopfieldNetwork:
         # the four panics of HopfieldNetworkBuilder.go:215-229, as Python exceptions with the same text
@@ -467,6 +469,8 @@ class HopfieldNetworkBuilder:
                               self.learningMethod if self.learningMethod is not None else 0,
                               self.learningNoiseMethod, self.learningNoiseScale, self.unitsUpdatedPerStep, seed,
                               self.allowIntensiveDataCollection)
+        if self.normAlgorithm != 1:
+            check(capi.load().hn_set_norm_algorithm(net._h, int(self.normAlgorithm)))
         if self.randMatrixInit:
             # :235-246 distuv.Normal{0, 0.01, randSrc}.Rand() for every element, row-major
             w = np.empty(self.dimension * self.dimension)

@@ -152,6 +152,19 @@ int hn_get_weights(hn_handle h, double* w_host);
  * for some c > 0 (e.g. a host that saved both the normalised matrix and the pre-normalisation matrix and resumes).
  * Checked: 0.5, 1, 2 or 4 times w_unnormalized is integer valued within int16, and it is proportional to W.  Row-major float64, N*N.      */
 int hn_set_integer_structure(hn_handle h, const double* w_unnormalized_host);
+/* How hn_normalize_frobenius / hn_learn_states compute ||W||_F for quarter-integer weights (every Hebbian / Delta matrix
+ * learned from zero).  mat.Norm(W, 2) is Dlange('F') over gonum's Dlassq (HopfieldNetwork.go:260), and gonum replaced
+ * its classic Dlassq by a port of the LAPACK-3.10 routine (believed: before v0.11, so in the pinned v0.12.0); this
+ * cannot be checked without the module sources, and the two differ in the last digits of the norm (3e-14 relative at
+ * N=100) and hence in the last bits of W.  Both are reproduced BIT FOR BIT for such weights (oracle:
+ * orc_frobenius_variant):
+ *   HN_NORM_DLASSQ_LAPACK310 (default, what oracle/ assumes) three accumulators: for these weights an exact sum of
+ *                            squares, computed on the device
+ *   HN_NORM_DLASSQ_CLASSIC   the sequential scale/ssq recurrence (every addition rounds), run on the host
+ * Weights that are not quarter-integers use a deterministic parallel sum under both settings (<= 1e-9 relative). */
+#define HN_NORM_DLASSQ_CLASSIC   0
+#define HN_NORM_DLASSQ_LAPACK310 1
+int hn_set_norm_algorithm(hn_handle h, int32_t algorithm);
 /* 1 if the next relaxation will use the exact integer stream, else 0 */
 int hn_integer_stream_active(hn_handle h, int32_t* active);
 

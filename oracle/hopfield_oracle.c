@@ -374,11 +374,61 @@ static void dlassq(int32_t n, const double* x, double* scale, double* sumsq) {
         }
     }
 }
-/* Dlange(Frobenius): per-row Dlassq, scale*sqrt(sum) */
-double orc_frobenius(const double* w, int32_t n) {
+/* Dlassq as rewritten after LAPACK 3.10 (Blue's algorithm: three accumulators for big / medium / small magnitudes,
+ * thresholds 2^486 / 2^-511, scalings 2^-538 / 2^537).  gonum replaced its classic Dlassq by a port of this routine at some
+ * release (believed: before v0.11, so the pinned v0.12.0 of go.mod:5 has it); that cannot be checked here (no module
+ * sources), so both variants are restated and the library implements both (hn_set_norm_algorithm).  For the medium range — every weight
+ * matrix of this path — it is a plain sequential sum of squares per row plus the running total, scale = 1. */
+static void dlassq_310(int32_t n, const double* x, double* scale, double* sumsq) {
+    const double tsml = ldexp(1.0, -511), tbig = ldexp(1.0, 486), ssml = ldexp(1.0, 537), sbig = ldexp(1.0, -538);
+    if (isnan(*scale) || isnan(*sumsq)) return;
+    if (*sumsq == 0.0) *scale = 1.0;
+    if (*scale == 0.0) { *scale = 1.0; *sumsq = 0.0; }
+    if (n <= 0) return;
+    int notbig = 1;
+    double asml = 0.0, amed = 0.0, abig = 0.0;
+    for (int32_t i = 0; i < n; i++) {
+        double ax = fabs(x[i]);
+        if (ax > tbig) { double t = ax * sbig; abig += t * t; notbig = 0; }
+        else if (ax < tsml) { if (notbig) { double t = ax * ssml; asml += t * t; } }
+        else amed += ax * ax;
+    }
+    if (*sumsq > 0.0) {
+        double ax = *scale * sqrt(*sumsq);
+        if (ax > tbig) { double t = *scale * sbig; abig += t * t * *sumsq; notbig = 0; }
+        else if (ax < tsml) { if (notbig) { double t = *scale * ssml; asml += t * t * *sumsq; } }
+        else amed += *scale * *scale * *sumsq;
+    }
+    if (abig > 0.0) {
+        if (amed > 0.0 || isnan(amed)) abig += (amed * sbig) * sbig;
+        *scale = 1.0 / sbig; *sumsq = abig;
+    } else if (asml > 0.0) {
+        if (amed > 0.0 || isnan(amed)) {
+            double a = sqrt(amed), b = sqrt(asml) / ssml;
+            double ymin = b > a ? a : b, ymax = b > a ? b : a;
+            *scale = 1.0; *sumsq = ymax * ymax * (1.0 + (ymin / ymax) * (ymin / ymax));
+        } else { *scale = 1.0 / ssml; *sumsq = asml; }
+    } else { *scale = 1.0; *sumsq = amed; }
+}
+/* Dlange(Frobenius): per-row Dlassq, scale*sqrt(sum).  variant 0: classic Dlassq, 1: the LAPACK-3.10 rewrite */
+double orc_frobenius_variant(const double* w, int32_t n, int32_t variant) {
     double scale = 0.0, sum = 1.0;
-    for (int32_t i = 0; i < n; i++) dlassq(n, w + (size_t)i * n, &scale, &sum);
+    for (int32_t i = 0; i < n; i++) {
+        if (variant) dlassq_310(n, w + (size_t)i * n, &scale, &sum);
+        else dlassq(n, w + (size_t)i * n, &scale, &sum);
+    }
     return scale * sqrt(sum);
+}
+/* default: the LAPACK-3.10 rewrite — gonum's dlassq.go cites "Algorithm 978: Safe Scaling in the Level 1 BLAS" (Anderson
+ * 2017) and was ported from LAPACK 3.10 (2021) before v0.11; recalled, not verifiable here: parity stays UNPINNED and
+ * the classic variant remains selectable on both sides */
+double orc_frobenius(const double* w, int32_t n) { return orc_frobenius_variant(w, n, 1); }
+double orc_normalize_variant(orc_net* net, int32_t variant) {
+    double nrm = orc_frobenius_variant(net->w, net->n, variant);
+    double f = 1 / nrm;
+    size_t nn = (size_t)net->n * net->n;
+    for (size_t i = 0; i < nn; i++) net->w[i] = f * net->w[i];
+    return nrm;
 }
 double orc_normalize(orc_net* net) {
     double nrm = orc_frobenius(net->w, net->n);

@@ -124,6 +124,10 @@ void orc_thermal_delta(orc_net* net, const double* states, const double* noised,
 double orc_frobenius(const double* w, int32_t n);
 /* matrix.Scale(1/matrix.Norm(2), matrix): HopfieldNetwork.go:260; returns the norm */
 double orc_normalize(orc_net* net);
+/* the same with the Dlassq variant chosen: 0 classic scaled recurrence, 1 the LAPACK-3.10 rewrite (three accumulators;
+ * what orc_frobenius / orc_normalize use); see hopfield_oracle.c */
+double orc_frobenius_variant(const double* w, int32_t n, int32_t variant);
+double orc_normalize_variant(orc_net* net, int32_t variant);
 
 /* noiseapplication/NoiseApplication.go:51-105 on one f64 state, in place */
 void orc_apply_noise(orc_rng* rng, int32_t method, double scale, double* state, int32_t n);

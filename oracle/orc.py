@@ -62,6 +62,9 @@ def lib():
         L.orc_frobenius.restype = C.c_double
         L.orc_frobenius.argtypes = [C.c_void_p, C.c_int32]
         L.orc_normalize.restype = C.c_double
+        L.orc_normalize_variant.restype = C.c_double
+        L.orc_frobenius_variant.restype = C.c_double
+        L.orc_frobenius_variant.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.orc_rng_uint64.restype = C.c_uint64
         L.orc_rng_uint64n.restype = C.c_uint64
         L.orc_rng_uint64n.argtypes = [C.c_void_p, C.c_uint64]
@@ -218,8 +221,9 @@ class Net:
     def enforce_constraints(self):
         lib().orc_enforce_constraints(self.ref())
 
-    def normalize(self):
-        return lib().orc_normalize(self.ref())
+    def normalize(self, variant=1):
+        """variant 1: the LAPACK-3.10 Dlassq (the default everywhere), 0: the classic recurrence (hopfield_oracle.c)"""
+        return lib().orc_normalize_variant(self.ref(), C.c_int32(variant))
 
     def update_state(self, state, perm):
         s = np.ascontiguousarray(state, dtype=np.float64).copy()

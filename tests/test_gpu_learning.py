@@ -23,8 +23,8 @@ def test_hebbian_epoch_bitwise(built, n, p, domain):
     assert np.array_equal(net.GetMatrix(), onet.w)
     nrm_o = onet.normalize()
     nrm_g = net.normalize()
-    # quarter-integer weights: the norm is computed by the reference's own Dlassq recurrence (exact_frobenius_quarters),
-    # so the normalised W is bit-identical, not just within 1e-9
+    # quarter-integer weights: the sum of squares is exact, as in the reference's Dlassq (LAPACK-3.10 variant, the default;
+    # the classic recurrence is covered by test_both_dlassq_variants_are_bitwise), so the normalised W is bit-identical
     assert nrm_g == nrm_o
     assert np.array_equal(net.GetMatrix(), onet.w)
     net.close()
@@ -77,6 +77,36 @@ def test_learn_states_full_loop_matches_oracle(built):
     assert np.array_equal(net.GetMatrix(), onet.w)   # bitwise, through the normalisation (Delta from zero: quarter-integers)
     assert np.array_equal(net.GetLearnedStates(), orc.pack(t))
     net.close()
+
+
+@pytest.mark.parametrize("n,p,rule", [(100, 10, 0), (257, 33, 0), (512, 40, 2), (1024, 100, 0)])
+def test_both_dlassq_variants_are_bitwise(built, n, p, rule):
+    """hn_set_norm_algorithm: the classic Dlassq recurrence and the LAPACK-3.10 rewrite (gonum carries one or the other
+    depending on its release) are each reproduced bit for bit for quarter-integer weights."""
+    rng = orc.Rng(71)
+    t = rng.generate_states(0, n, p)
+    for variant in (0, 1):
+        onet = orc.Net(n)
+        net = gpu_net(n, rule=rule, epochs=3, seed=9, SetNormAlgorithm=variant, SetLearningNoiseMethod=hn.MaximalInversion,
+                      SetLearningNoiseRatio=0.1)
+        if rule == 0:
+            onet.hebbian(t)
+            net.hebbian_epoch(t)
+        else:
+            r2 = orc.Rng(9)
+            for _ in range(3):
+                noised = t.copy()
+                for s_ in range(p):
+                    r2.apply_noise(1, 0.1, noised[s_])
+                perms = r2.fresh_perms(n, p)
+                onet.delta(t, noised, perms)
+                net.delta_epoch(t, noised, perms)
+        assert np.array_equal(net.GetMatrix(), onet.w)
+        nrm_o = onet.normalize(variant)
+        nrm_g = net.normalize()
+        assert nrm_g == nrm_o, f"variant {variant}"
+        assert np.array_equal(net.GetMatrix(), onet.w), f"variant {variant}"
+        net.close()
 
 
 @pytest.mark.parametrize("n,p,stream", [(96, 6, 0), (96, 6, 3), (2048, 8, 3), (1100, 4, 0)])

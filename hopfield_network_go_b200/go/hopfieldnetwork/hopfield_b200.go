@@ -83,6 +83,10 @@ func newDeviceNetwork(net *HopfieldNetwork, device int, initial []float64) *Hopf
 	cfg.learning_rate = C.double(net.learningRate)
 	cfg.device = C.int32_t(device)
 	check(C.hn_create(&cfg, &net.handle))
+	// ||W||_F of LearnStates (:260): gonum's Dlassq exists in two variants across releases; the library reproduces both bit
+	// for bit for Hebbian / Delta weights.  A maintainer checks once which one their gonum has (mat.Norm of a saved Hebbian
+	// matrix against both) and, if it is the classic recurrence, selects it here:
+	//   check(C.hn_set_norm_algorithm(net.handle, C.HN_NORM_DLASSQ_CLASSIC))
 	if initial != nil {
 		check(C.hn_set_weights(net.handle, (*C.double)(unsafe.Pointer(&initial[0]))))
 	}

@@ -191,6 +191,8 @@ public:
     HopfieldNetworkBuilder& SetAllowIntensiveDataCollection(bool) { return *this; }
     HopfieldNetworkBuilder& SetSeed(uint64_t s) { seed_ = s; return *this; }   // additive: reproducible runs
     HopfieldNetworkBuilder& SetDevice(int d) { cfg_.device = d; return *this; } // additive
+    // additive: which of gonum's two Dlassq variants the Frobenius norm of LearnStates reproduces (hn_set_norm_algorithm)
+    HopfieldNetworkBuilder& SetNormAlgorithm(int a) { norm_algorithm_ = a; return *this; }
 
     std::unique_ptr<HopfieldNetwork> Build() {
         const std::string pre = "HopfieldNetworkBuilder encountered an error during build! ";
@@ -204,6 +206,7 @@ public:
         net->noise_scale_ = noise_scale_; net->units_updated_ = units_;
         check(hn_rng_create(seed_, &net->rng_));
         check(hn_create(&cfg_, &net->handle_));
+        if (norm_algorithm_ != HN_NORM_DLASSQ_LAPACK310) check(hn_set_norm_algorithm(net->handle_, norm_algorithm_));
         if (rand_init_) {  // :235-246 distuv.Normal{0, 0.01, randSrc}
             std::vector<double> w((size_t)cfg_.dimension * cfg_.dimension);
             for (double& x : w) x = hn_rng_norm_float64(net->rng_) * 0.01 + 0.0;
@@ -216,6 +219,7 @@ private:
     hn_config cfg_{};
     bool rand_init_ = false;
     int epochs_ = 0, rule_ = HebbianLearningRule, method_ = FullSetMethod, noise_ = None, units_ = 1;
+    int norm_algorithm_ = HN_NORM_DLASSQ_LAPACK310;
     double noise_scale_ = 0.0;
     uint64_t seed_ = 0x5EED;
 };

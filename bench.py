@@ -494,7 +494,9 @@ def dense_roofline(n, b, sweeps, dense_flips, stage, own, ncu):
             "flips_per_probe": dense_flips / b, "sweeps": int(sweeps),
             "fields_gemm": {"kernel": "igemm_tc05_kernel<true>", "top_s": useful / (gm * 1e-3) / 1e12 if gm > 0 else None, "peak": pk.get(256),
                             "frac": (useful / (gm * 1e-3) / 1e12) / pk[256] if gm > 0 and 256 in pk else None,
-                            "note": "131072 x 4096 x 4096 per sweep, int32 output written to HBM (2 GiB): bound by the output store"}}
+                            "note": "B x N x N per dense sweep with the stability scan fused into the epilogue; the int32 fields "
+                                    "(2 GiB at config 3) are stored only after the last dense sweep.  ncu: neither L2 nor the tensor "
+                                    "pipe saturated — the bits -> int8 expansion of the probe tile bounds a K step (DESIGN.md K1)"}}
 
 
 def measure_delta_epoch(hn, local, n, p, epochs, noise_scale=0.1, dist=None, rank=0, world=1, cpu=False):

@@ -328,9 +328,12 @@ relax_kernel(RelaxParams p) {
             const uint16_t* permrow = p.perm_pool + (size_t)row * p.ldp;
             const uint16_t* invrow = p.inv_pool + (size_t)row * p.ldp;
             __syncthreads();  // previous readers of s_perm / s_inv / s_cand are done
-            for (int i = tid; i < p.ldp / 2; i += RELAX_THREADS) {   // (128-bit copies make the integer kernel spill at 56 registers: +48% time)
-                reinterpret_cast<uint32_t*>(s_perm)[i] = reinterpret_cast<const uint32_t*>(permrow)[i];
-                reinterpret_cast<uint32_t*>(s_inv)[i] = reinterpret_cast<const uint32_t*>(invrow)[i];
+#pragma unroll 1
+            for (int i = tid; i < p.ldp / 4; i += RELAX_THREADS) {   // (128-bit copies make the integer kernel spill at 56 registers: +48% time)
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(permrow) + i);
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(invrow) + i);
+                reinterpret_cast<uint2*>(s_perm)[i] = a;
+                reinterpret_cast<uint2*>(s_inv)[i] = b;
             }
             for (int w = tid; w < ncw; w += RELAX_THREADS) s_cand[w] = 0u;
             __syncthreads();

@@ -146,6 +146,7 @@ struct hn_handle_s {
     DevBuf d_mperm, d_mbb, d_mx, d_info, d_state, d_sweeps, d_dflips, d_dmargin, d_finished, d_scan;   // d_scan: unstable[B], zero[B], only[B]
     CUtensorMap dense_map;
     // zero-copy results (hn_relax_batch with page-locked host buffers): device-visible addresses of the caller's arrays
+    bool dense_want_map3d = true, dense_map3d = false;   // HN_DENSE_MAP=2d keeps the four 2-D boxes per slot
     int dense_box_rows = 32;           // rows per TMA box of the dense sweeps weight stream (HN_TMA_BOX_DENSE; 8-row boxes measured 2.3x slower)
     bool exact_norm = false;           // hn_set_norm_algorithm: classic Dlassq recurrence on the host (true) / exact parallel sum = LAPACK-3.10 Dlassq (false); HN_EXACT_NORM presets it
     bool zero_copy = true;             // HN_ZERO_COPY=0 turns it off
@@ -630,7 +631,13 @@ int prepare_dense(hn_handle h, const uint16_t* d_pool, int rows) {
                                                                              h->d_info.as<DsPos>() + (size_t)r * rp);
     }
     HN_CUDA_TRY(cudaGetLastError());
-    const int rc = tc05::make_map_bytes_2d(&h->dense_map, h->d_mperm.p, (uint64_t)np, (uint64_t)rows * rp, (uint64_t)np, h->dense_box_rows);
+    int rc = -1;
+    h->dense_map3d = false;
+    if (h->dense_want_map3d && h->dense_box_rows == DS_BLK) {   // one 3-D box per ring slot; the 2-D boxes are the fallback
+        rc = tc05::make_map_bytes_3d_parts(&h->dense_map, h->d_mperm.p, (uint64_t)np / 4, 4, (uint64_t)rows * rp, (uint64_t)np, DS_BLK);
+        h->dense_map3d = rc == 0;
+    }
+    if (rc != 0) rc = tc05::make_map_bytes_2d(&h->dense_map, h->d_mperm.p, (uint64_t)np, (uint64_t)rows * rp, (uint64_t)np, h->dense_box_rows);
     if (rc != 0) { set_error("cuTensorMapEncodeTiled (dense sweeps) failed (%d)", rc); return HN_E_CUDA; }
     h->dense_rows = rows; h->dense_w_version = h->w_version; h->dense_pool_version = h->pool_version;
     return HN_OK;
@@ -679,7 +686,7 @@ int run_dense_sweeps(hn_handle h, const uint64_t* d_probes, int B, const uint16_
         HN_CUDA_TRY(cudaMemsetAsync(&sc->dense_flips, 0, 8, h->st));
         DenseParams dp{};
         dp.N = N; dp.np = np; dp.rows_p = rp; dp.words = words; dp.B = B; dp.domain = h->cfg.domain; dp.ldw = h->ldw;
-        dp.box_rows = h->dense_box_rows;
+        dp.box_rows = h->dense_box_rows; dp.map3d = h->dense_map3d ? 1 : 0;
         dp.mbb = h->d_mbb.as<int8_t>() + (size_t)r * rp * DS_BLK;
         dp.mx = h->d_mx.as<int8_t>() + (size_t)r * rp * DS_BLK;
         dp.info = h->d_info.as<DsPos>() + (size_t)r * rp;
@@ -1468,6 +1475,7 @@ int hn_create(const hn_config* cfg, hn_handle* out) {
     if (const char* e = getenv("HN_DENSE_MIN_FLIPS")) h->dense_min_flips = std::atof(e);
     if (const char* e = getenv("HN_ZERO_COPY")) h->zero_copy = std::atoi(e) != 0;
     if (const char* e = getenv("HN_EXACT_NORM")) h->exact_norm = std::atoi(e) != 0;
+    if (const char* e = getenv("HN_DENSE_MAP")) h->dense_want_map3d = std::strcmp(e, "2d") != 0;
     if (const char* e = getenv("HN_TMA_BOX_DENSE")) { const int x = std::atoi(e); if (x == 8 || x == 16 || x == 32) h->dense_box_rows = x; }
     *out = h;
     return HN_OK;

@@ -33,7 +33,7 @@ namespace hn {
 
 constexpr int DS_T = 32;            // probes per tile (x 4 K-quarters = 128 MMA rows)
 constexpr int DS_BLK = 32;          // positions per block
-constexpr int DS_STAGES = 4;        // ring of weight tiles: 4 quarters x 32 rows x 128 B = 16 KiB per stage
+constexpr int DS_STAGES = 5;        // ring of weight tiles: 4 quarters x 32 rows x 128 B = 16 KiB per stage
 constexpr int DS_STAGE_BYTES = 16384;
 constexpr int DS_THREADS = 256;
 constexpr uint32_t DS_NULL = 0x80000000u;
@@ -41,7 +41,7 @@ constexpr uint32_t DS_NULL = 0x80000000u;
 static inline int ds_np(int n) { return (n + 511) / 512 * 512; }        // padded K: four quarters of whole 128-byte chunks
 static inline int ds_rows(int n) { return (n + 31) / 32 * 32; }         // padded positions
 static inline size_t ds_smem_bytes(int n) {
-    return (size_t)DS_T * ds_np(n) + (size_t)DS_STAGES * DS_STAGE_BYTES + 4 * 32 * 33 * 4 + 2 * 1024 + 256 + 256 + 1024;
+    return (size_t)DS_T * ds_np(n) + (size_t)DS_STAGES * DS_STAGE_BYTES + 32 * 33 * 4 + 2 * 1024 + 128 + 256 + 256 + 1024;
 }
 
 // Per schedule row: the byte image with its rows in visiting order (zero padded to [rowsP][Np]), the in-block 32x32
@@ -86,6 +86,7 @@ __global__ void dense_prep_blocks_kernel(const int8_t* __restrict__ k8, int ld8,
 struct DenseParams {
     int N, np, rows_p, words, B, domain, ldw;
     int box_rows;              // rows per TMA box of the tensor map (a quarter's 32 rows arrive as 32 / box_rows boxes)
+    int map3d;                 // the tensor map is the 3-D view [quarter][row][kq bytes]: one box per ring slot
     const int8_t* mbb;         // [rows_p/32][32][32] of this schedule row
     const int8_t* mx;          // [rows_p/32][32][32] cross matrices block b <- block b-1
     const DsPos* info;         // [rows_p]
@@ -154,10 +155,16 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
     const int kq = p.np / 4, KC = kq / 128, nblk = p.rows_p / DS_BLK;
     unsigned char* s8 = smem;                                              // KC panels of 128 rows x 128 B
     unsigned char* ring = smem + (size_t)DS_T * p.np;                     // == KC * 16384
-    int* part = reinterpret_cast<int*>(ring + DS_STAGES * DS_STAGE_BYTES); // [4][32][33] partial fields [quarter][probe][position]
-    uint32_t* mbb_s = reinterpret_cast<uint32_t*>(part + 4 * 32 * 33);     // [32][8] words: in-block matrix of the current block
-    uint32_t* mx_s = mbb_s + 256;                                          // [32][8] words: cross matrix (previous block's flips)
-    uint32_t* pos_off = mx_s + 256;                                        // [32] state-byte offsets of the block's positions
+    int* part = reinterpret_cast<int*>(ring + DS_STAGES * DS_STAGE_BYTES); // [32][33] fields [probe][position]: the four K-quarters are
+                                                                           // ADDED here by their warps (shared-memory atomics; integers, any
+                                                                           // order) and every entry is zeroed again by the thread that reads it
+                                                                           // — one buffer instead of four buys the ring its fifth slot
+    uint32_t* mbb_s = reinterpret_cast<uint32_t*>(part + 32 * 33);         // [32][8] words: in-block matrix of the current block
+    uint32_t* mx_s = mbb_s + 256;                                          // [32] rows of 8 words: cross matrix (previous block's flips); row i at
+                                                                           // word 8 i + 4 (i >> 3): the four rows 8 sl + e that one 128-bit load of a
+                                                                           // warp touches then sit in four different bank groups (a plain [32][8]
+                                                                           // layout put them all on the same four banks: 16 wavefronts per load)
+    uint32_t* pos_off = mx_s + 288;                                        // [32] state-byte offsets of the block's positions
     uint32_t* pos_unit = pos_off + 32;                                     // [32] their units
     uint64_t* bars = reinterpret_cast<uint64_t*>(pos_unit + 32);
     uint64_t* full = bars;                  // [stages] TMA
@@ -177,6 +184,7 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
         mbar_fence_init();
         tma_prefetch_desc(&map_w);
     }
+    for (int i = tid; i < 32 * 33; i += DS_THREADS) part[i] = 0;
     if (warp == 1) tmem_alloc(tmem_slot, 256);   // two accumulators: block b+1 is contracted while block b is decided
     tc_fence_before_sync();
     __syncthreads();
@@ -230,24 +238,26 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
 
         if (warp == 0) {
             // ===== TMA producer: block by block, the 4 K-quarters of the block's 32 weight rows, chunk by chunk =====
-            if (lane == 0) {
-                for (int b = 0; b < nblk; b++)
-                    for (int kc = 0; kc < KC; kc++) {
-                        mbar_wait(&empty[stage], phase ^ 1u);
-                        mbar_arrive_expect_tx(&full[stage], DS_STAGE_BYTES);
-                        unsigned char* dst = ring + (size_t)stage * DS_STAGE_BYTES;
-#pragma unroll
+            // (the whole warp runs the loop converged; one elected lane issues, see tc05.cuh "warp-convergent variants")
+            for (int b = 0; b < nblk; b++)
+                for (int kc = 0; kc < KC; kc++) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx_elect(&full[stage], DS_STAGE_BYTES);
+                    unsigned char* dst = ring + (size_t)stage * DS_STAGE_BYTES;
+                    if (p.map3d) tma_load_3d_elect(dst, &map_w, kc * 128, p.row_base + b * DS_BLK, 0, &full[stage]);
+                    else
                         for (int q = 0; q < 4; q++)
                             for (int r = 0; r < DS_BLK; r += p.box_rows)
-                                tma_load_2d(dst + q * 4096 + r * 128, &map_w, q * kq + kc * 128, p.row_base + b * DS_BLK + r, &full[stage]);
-                        if (++stage == DS_STAGES) { stage = 0; phase ^= 1u; }
-                    }
-            }
+                                tma_load_2d_elect(dst + q * 4096 + r * 128, &map_w, q * kq + kc * 128, p.row_base + b * DS_BLK + r, &full[stage]);
+                    if (++stage == DS_STAGES) { stage = 0; phase ^= 1u; }
+                }
         } else if (warp == 1) {
-            // ===== MMA issuer =====
+            // ===== MMA issuer (converged warp, elected issue) =====
             constexpr uint32_t idesc = idesc_i8(128, 128, true, true);
-            const bool prof = p.prof && blockIdx.x == 0 && lane == 0;
+            const bool prof = p.prof && blockIdx.x == 0;
             long long pm_wait = 0, pm_issue = 0;
+            const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);   // warp-uniform by construction
+            const uint32_t s8_addr = smem_u32(s8), ring_addr = smem_u32(ring);
             for (int b = 0; b < nblk; b++) {
                 const long long m0 = prof ? clock64() : 0;
                 mbar_wait(s8_ready, s8_par);
@@ -258,22 +268,19 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 for (int kc = 0; kc < KC; kc++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after_sync();
-                    if (lane == 0) {
-                        const uint64_t da = smem_desc_k128(smem_u32(s8 + (size_t)kc * 16384));
-                        const uint64_t db = smem_desc_k128(smem_u32(ring + (size_t)stage * DS_STAGE_BYTES));
+                    const uint64_t da = smem_desc_k128(s8_addr + (uint32_t)kc * 16384u);
+                    const uint64_t db = smem_desc_k128(ring_addr + (uint32_t)stage * (uint32_t)DS_STAGE_BYTES);
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            mma_i8(tmem_base + (uint32_t)((b & 1) * 128), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
-                                   (uint32_t)((kc | j) != 0));
-                        mma_commit(&empty[stage]);
-                        if (kc == KC - 1) mma_commit(d_full);
-                    }
-                    __syncwarp();
+                    for (int j = 0; j < 4; j++)
+                        mma_i8_elect(tmem_u + (uint32_t)((b & 1) * 128), da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
+                                     (uint32_t)((kc | j) != 0));
+                    mma_commit_elect(&empty[stage]);
+                    if (kc == KC - 1) mma_commit_elect(d_full);
                     if (++stage == DS_STAGES) { stage = 0; phase ^= 1u; }
                 }
                 if (prof) pm_issue += clock64() - m1;
             }
-            if (prof) { atomicAdd(p.prof + 5, (unsigned long long)pm_wait); atomicAdd(p.prof + 6, (unsigned long long)pm_issue); }
+            if (prof && lane == 0) { atomicAdd(p.prof + 5, (unsigned long long)pm_wait); atomicAdd(p.prof + 6, (unsigned long long)pm_issue); }
         } else if (warp >= 4) {
             // ===== warps 4-7: partial fields out of TMEM (warp 4+q reads quarter q), then the block's 32 decisions =====
             // Pipeline: the contraction of block b+1 runs while block b is decided.  It reads S8 WITHOUT block b's flips;
@@ -319,15 +326,15 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                     tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((b & 1) * 128 + 32 * q), r);
                     tmem_ld_wait();
                     tc_fence_before_sync();
-                    int* dst = part + (q * 32 + lane) * 33;   // [quarter][probe][position]
+                    int* dst = part + lane * 33;   // [probe][position]
 #pragma unroll
-                    for (int i = 0; i < 32; i++) dst[i] = (int)r[i];
+                    for (int i = 0; i < 32; i++) atomicAdd(dst + i, (int)r[i]);
                 }
                 if (q == 0) {
-                    mbb_s[lane * 8 + 0] = mrow0.x; mbb_s[lane * 8 + 1] = mrow0.y; mbb_s[lane * 8 + 2] = mrow0.z; mbb_s[lane * 8 + 3] = mrow0.w;
-                    mbb_s[lane * 8 + 4] = mrow1.x; mbb_s[lane * 8 + 5] = mrow1.y; mbb_s[lane * 8 + 6] = mrow1.z; mbb_s[lane * 8 + 7] = mrow1.w;
-                    mx_s[lane * 8 + 0] = xrow0.x; mx_s[lane * 8 + 1] = xrow0.y; mx_s[lane * 8 + 2] = xrow0.z; mx_s[lane * 8 + 3] = xrow0.w;
-                    mx_s[lane * 8 + 4] = xrow1.x; mx_s[lane * 8 + 5] = xrow1.y; mx_s[lane * 8 + 6] = xrow1.z; mx_s[lane * 8 + 7] = xrow1.w;
+                    *reinterpret_cast<uint4*>(mbb_s + lane * 8) = mrow0;
+                    *reinterpret_cast<uint4*>(mbb_s + lane * 8 + 4) = mrow1;
+                    *reinterpret_cast<uint4*>(mx_s + lane * 8 + (lane >> 3) * 4) = xrow0;
+                    *reinterpret_cast<uint4*>(mx_s + lane * 8 + (lane >> 3) * 4 + 4) = xrow1;
                     pos_off[lane] = pinfo.off; pos_unit[lane] = pinfo.unit;
                     if (b + 1 < nblk) {   // prefetch; lands while this block is decided
                         const uint4* src = reinterpret_cast<const uint4*>(p.mbb + ((size_t)(b + 1) * 32 + lane) * 32);
@@ -347,17 +354,18 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                 int u8[8];
                 uint32_t soff[8], unit8[8], sb = 0, vm = 0;
                 {
-                    int pq[8][4];
+                    int pq[8];
                     uint4 xr[8][2];
                     uint32_t po[8];
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
                         const int idx = 8 * sl + e;
-#pragma unroll
-                        for (int qq = 0; qq < 4; qq++) pq[e][qq] = part[(qq * 32 + pl) * 33 + idx];
+                        pq[e] = part[pl * 33 + idx];
                         po[e] = pos_off[idx];
                         unit8[e] = pos_unit[idx];
                     }
+#pragma unroll
+                    for (int e = 0; e < 8; e++) part[pl * 33 + 8 * sl + e] = 0;   // ready for the next block's sums (after the block's closing barrier)
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
                         const bool valid = po[e] != DS_NULL;
@@ -369,13 +377,13 @@ dense_sweep_kernel(const __grid_constant__ CUtensorMap map_w, DenseParams p) {
                     for (int e = 0; e < 8; e++) sv[e] = (int)(signed char)s8[soff[e]];   // a unit is visited once per sweep: still the tile's initial byte
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
-                        xr[e][0] = *reinterpret_cast<const uint4*>(mx_s + (8 * sl + e) * 8);
-                        xr[e][1] = *reinterpret_cast<const uint4*>(mx_s + (8 * sl + e) * 8 + 4);
+                        xr[e][0] = *reinterpret_cast<const uint4*>(mx_s + (8 * sl + e) * 8 + sl * 4);
+                        xr[e][1] = *reinterpret_cast<const uint4*>(mx_s + (8 * sl + e) * 8 + sl * 4 + 4);
                     }
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
                         sb |= (uint32_t)(((vm >> e) & 1u) && sv[e] > 0) << e;
-                        int a0 = pq[e][0] + pq[e][1] - bias, a1 = pq[e][2] + pq[e][3];
+                        int a0 = pq[e] - bias, a1 = 0;
                         a0 = __dp4a((int)xr[e][0].x, (int)dsw_prev[0], a0); a1 = __dp4a((int)xr[e][0].y, (int)dsw_prev[1], a1);
                         a0 = __dp4a((int)xr[e][0].z, (int)dsw_prev[2], a0); a1 = __dp4a((int)xr[e][0].w, (int)dsw_prev[3], a1);
                         a0 = __dp4a((int)xr[e][1].x, (int)dsw_prev[4], a0); a1 = __dp4a((int)xr[e][1].y, (int)dsw_prev[5], a1);

@@ -83,26 +83,28 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (the whole warp runs the loop converged, one elected lane issues: tc05.cuh) =====
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int n0 = (tile % n_tiles) * TG_BN, m0 = (tile / n_tiles) * TG_BM;
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full[stage], A_BITS ? TG_B_BYTES : TG_A_BYTES + TG_B_BYTES);
+                    mbar_arrive_expect_tx_elect(&full[stage], A_BITS ? TG_B_BYTES : TG_A_BYTES + TG_B_BYTES);
                     for (int r = 0; r < TG_BN; r += box_rows)
-                        tma_load_2d(sB + (size_t)stage * TG_B_BYTES + (size_t)r * TG_BK, &map_b, kb * TG_BK, n0 + r, &full[stage]);
+                        tma_load_2d_elect(sB + (size_t)stage * TG_B_BYTES + (size_t)r * TG_BK, &map_b, kb * TG_BK, n0 + r, &full[stage]);
                     if constexpr (!A_BITS)
                         for (int r = 0; r < TG_BM; r += box_rows)
-                            tma_load_2d(sA + (size_t)stage * TG_A_BYTES + (size_t)r * TG_BK, &map_a, kb * TG_BK, m0 + r, &full[stage]);
+                            tma_load_2d_elect(sA + (size_t)stage * TG_A_BYTES + (size_t)r * TG_BK, &map_a, kb * TG_BK, m0 + r, &full[stage]);
                     if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer (converged warp, elected issue) =====
         constexpr uint32_t idesc = idesc_i8(TG_BM, TG_BN, true, true);
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);   // warp-uniform by construction
+        const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
         int stage = 0; uint32_t phase = 0; int it = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
             const int acc = it & 1;
@@ -112,17 +114,14 @@ igemm_tc05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int kb = 0; kb < kblocks; kb++) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after_sync();
-                if (lane == 0) {
-                    const uint64_t da = smem_desc_k128(smem_u32(sA + (size_t)stage * TG_A_BYTES));
-                    const uint64_t db = smem_desc_k128(smem_u32(sB + (size_t)stage * TG_B_BYTES));
+                const uint64_t da = smem_desc_k128(sA_addr + (uint32_t)stage * (uint32_t)TG_A_BYTES);
+                const uint64_t db = smem_desc_k128(sB_addr + (uint32_t)stage * (uint32_t)TG_B_BYTES);
 #pragma unroll
-                    for (int j = 0; j < TG_BK / 32; j++)   // K = 32 bytes per instruction: +32 B on the start address (>>4)
-                        mma_i8(tmem_base + (uint32_t)acc * TG_BN, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
-                               (uint32_t)((kb | j) != 0));
-                    mma_commit(&empty[stage]);             // frees the stage when these MMAs have read it
-                    if (kb == kblocks - 1) mma_commit(&acc_full[acc]);
-                }
-                __syncwarp();
+                for (int j = 0; j < TG_BK / 32; j++)   // K = 32 bytes per instruction: +32 B on the start address (>>4)
+                    mma_i8_elect(tmem_u + (uint32_t)acc * TG_BN, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
+                                 (uint32_t)((kb | j) != 0));
+                mma_commit_elect(&empty[stage]);             // frees the stage when these MMAs have read it
+                if (kb == kblocks - 1) mma_commit_elect(&acc_full[acc]);
                 if (++stage == TG_STAGES) { stage = 0; phase ^= 1u; }
             }
         }

@@ -358,7 +358,8 @@ def main():
     delta = {}
     if not args.no_delta:   # collective when world > 1: every rank takes part
         if world == 1:
-            delta["config2_N1024_P100_inversion0.1"] = measure_delta_epoch(hn, local, 1024, 100, 5, cpu=not args.no_cpu)
+            # config 2 runs 100 epochs: all of them are timed (the sweep's flips shrink as the network learns its targets)
+            delta["config2_N1024_P100_inversion0.1"] = measure_delta_epoch(hn, local, 1024, 100, 100, cpu=not args.no_cpu)
             delta["config5_N16384_P1024_one_gpu"] = measure_delta_epoch(hn, local, 16384, 1024, 2, cpu=False)
         delta[f"config5_N16384_P{128 * world}_sharded_128_per_gpu"] = measure_delta_epoch(
             hn, local, 16384, 128, 2, dist=dist if world > 1 else None, rank=rank, world=world, cpu=(world == 1 and not args.no_cpu))
@@ -553,7 +554,7 @@ def measure_delta_epoch(hn, local, n, p, epochs, noise_scale=0.1, dist=None, ran
     gemm_flop = 2.0 * n * n * p
     tf = lambda t_ms: gemm_flop / (t_ms * 1e-3) / 1e12 if t_ms > 0 else None
     sweep_bytes = 8.0 * n * st["sweep_flips"] + p * (8.0 * n + n / 4)       # one float64 column per flip + one pass over the fields
-    res = {"ms": ms, "targets_per_gpu": p, "n_gpus": world, "device_stage_ms": {k2: v for k2, v in st.items() if k2 != "sweep_flips"},
+    res = {"ms": ms, "epochs_timed": len(times), "ms_first_epoch": times[0], "ms_last_epoch": times[-1], "targets_per_gpu": p, "n_gpus": world, "device_stage_ms": {k2: v for k2, v in st.items() if k2 != "sweep_flips"},
            "sweep_flips_per_target": st["sweep_flips"] / p,
            "roofline": {"fp64_tensor": {"bound": "tensor", "unit": "TFLOP/s (equivalent: 2 N^2 P per contraction)", "peak": fp64_peak,
                                         "peak_source": "profiles/r02_peaks.json: mma.sync.m8n8k4.f64 issue rate (tcgen05 has no f64 kind)",

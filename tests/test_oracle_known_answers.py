@@ -196,3 +196,57 @@ def test_fast_oracle_equals_slow_oracle(built, n, p, domain):
     fast = net.relax_batch(probes.copy(), pool, threads=4, fast_k2=k2)
     for k in ("final", "num_steps", "stable", "distances", "flips", "margin_hits", "energies"):
         assert np.array_equal(slow[k], fast[k]), k
+
+
+def test_frobenius_variants_against_independent_restatements():
+    """orc_frobenius_variant: 0 = classic Dlassq (sequential scale/ssq recurrence), 1 = the LAPACK-3.10 rewrite, which for
+    weights of ordinary magnitude is a plain sequential sum of squares per row plus the running total.  Checked against
+    Python restatements written from the algorithms' published descriptions, on a quarter-integer Hebbian matrix (where
+    variant 1 must equal the exact integer sum) and on a generic float matrix."""
+    import math
+    import ctypes as C
+    rng = orc.Rng(5)
+    t = rng.generate_states(0, 60, 7)
+    w_h = (t.T @ t - 7 * np.eye(60)) * 0.5
+    w_f = np.random.default_rng(3).normal(size=(37, 37)) * 1e-3
+
+    def classic(w):
+        scale, ssq = 0.0, 1.0
+        for x in w.ravel():
+            a = abs(float(x))
+            if a > 0:
+                if scale < a:
+                    r = scale / a
+                    ssq = 1.0 + (ssq * r) * r
+                    scale = a
+                else:
+                    r = a / scale
+                    ssq += r * r
+        return scale * math.sqrt(ssq)
+
+    def lapack310(w):   # medium range only: amed accumulates x*x along the row, then the running total scl^2*sumsq
+        scale, ssq = 0.0, 1.0
+        for row in w:
+            if ssq == 0.0:
+                scale = 1.0
+            if scale == 0.0:
+                scale, ssq = 1.0, 0.0
+            amed = 0.0
+            for x in row:
+                amed += float(x) * float(x)
+            if ssq > 0.0:
+                amed += scale * scale * ssq
+            scale, ssq = 1.0, amed
+        return scale * math.sqrt(ssq)
+
+    for w in (w_h, w_f):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        n = w.shape[0]
+        got0 = orc.lib().orc_frobenius_variant(w.ctypes.data_as(C.c_void_p), n, 0)
+        got1 = orc.lib().orc_frobenius_variant(w.ctypes.data_as(C.c_void_p), n, 1)
+        assert got0 == classic(w)
+        assert got1 == lapack310(w)
+    exact = math.sqrt(float(np.sum(np.rint(w_h * 4).astype(np.int64) ** 2)) / 16.0)
+    n = w_h.shape[0]
+    wc = np.ascontiguousarray(w_h, dtype=np.float64)
+    assert orc.lib().orc_frobenius_variant(wc.ctypes.data_as(C.c_void_p), n, 1) == exact

@@ -159,7 +159,7 @@ struct hn_handle_s {
     uint64_t w_version = 1, pool_version = 1, dense_w_version = 0, dense_pool_version = 0;
     bool use_dense = true;
     int dense_max_rows = 6, dense_min_n = 2048;
-    double dense_min_flips = 200.0;   // sweep densely again while the last sweep flipped more than this per unfinished probe (the next one
+    double dense_min_flips = 150.0;   // sweep densely again while the last sweep flipped more than this per unfinished probe (the next one
                                       // flips ~0.75x as many; a dense sweep costs what ~160 flips per probe cost the sparse kernel)
     int last_dense_sweeps = 0;
     int frac_flags = 7; uint64_t frac_version = 0;   // which fractions occur in W (fused update kernel), and for which W

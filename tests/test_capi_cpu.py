@@ -131,3 +131,26 @@ def test_hot_kernels_do_not_spill(built):
             seen += 1
             assert int(stack) == 0, f"{name} spills ({stack} bytes of stack)"
     assert seen >= 20, "resource usage of the hot kernels not found in the library"
+
+
+def test_tensor_path_sass(built):
+    """The Blackwell tensor path is really there and is issued the cheap way: the dense-sweep and contraction kernels
+    contain UTCIMMA (tcgen05.mma.kind::i8), UTMALDG (TMA), LDTM (tcgen05.ld) and UTCBAR (tcgen05.commit), and NO
+    elect-broadcast-branch loop (BRA.U.ANY) around them — under a divergent `if (lane == 0)` the compiler wraps every
+    such instruction in one, which cost 450 cycles per ring slot."""
+    import re
+    import shutil
+    import subprocess
+    from hopfield_network_go_b200 import build
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([tool, "-sass", build.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = re.split(r"\n\s*Function : ", out)
+    seen = 0
+    for f in funcs[1:]:
+        name = f.split("\n", 1)[0]
+        if "dense_sweep_kernel" in name or "igemm_tc05_kernel" in name:
+            seen += 1
+            for mnemonic in ("UTCIMMA", "UTMALDG", "LDTM", "UTCBAR"):
+                assert re.search(r"\b" + mnemonic, f), f"{mnemonic} missing in {name}"
+            assert "BRA.U.ANY" not in f, f"elect-broadcast loop around a tensor / TMA instruction in {name}"
+    assert seen >= 4
